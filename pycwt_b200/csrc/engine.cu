@@ -1,0 +1,880 @@
+// B200-native CWT engine: host planning, kernel launches and the C ABI of
+// include/cwt_b200.h.  Device code is in kernels.cuh / fft_tile.cuh / cplx.cuh.
+//
+// Build (sm_100a):   nvcc -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a
+//                         -Xcompiler -fPIC -shared engine.cu -o libcwtb200.so
+// Build (CPU emulation of the kernels, TESTS ONLY, never shipped/loaded by the package):
+//                    nvcc -std=c++17 -O2 -DCWTB_HOST_EMU ... -o libcwtb200_emu.so
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <set>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/cwt_b200.h"
+#include "kernels.cuh"
+
+using namespace cwtb;
+
+// ======================================================================================
+// runtime abstraction
+// ======================================================================================
+#ifdef CWTB_HOST_EMU
+typedef int rt_stream;
+typedef double rt_event;
+static inline int rt_malloc(void **p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 1; }
+static inline int rt_free(void *p) { free(p); return 0; }
+static inline int rt_host_alloc(void **p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 1; }
+static inline int rt_host_free(void *p) { free(p); return 0; }
+static inline int rt_h2d(void *d, const void *s, size_t n, rt_stream) { memcpy(d, s, n); return 0; }
+static inline int rt_d2h(void *d, const void *s, size_t n, rt_stream) { memcpy(d, s, n); return 0; }
+static inline int rt_memset(void *d, int v, size_t n, rt_stream) { memset(d, v, n); return 0; }
+static inline int rt_sync(rt_stream) { return 0; }
+static inline const char *rt_errstr(int) { return "emulation error"; }
+#else
+typedef cudaStream_t rt_stream;
+typedef cudaEvent_t rt_event;
+static inline int rt_malloc(void **p, size_t n) { return (int)cudaMalloc(p, n ? n : 1); }
+static inline int rt_free(void *p) { return (int)cudaFree(p); }
+static inline int rt_host_alloc(void **p, size_t n) { return (int)cudaHostAlloc(p, n ? n : 1, cudaHostAllocDefault); }
+static inline int rt_host_free(void *p) { return (int)cudaFreeHost(p); }
+static inline int rt_h2d(void *d, const void *s, size_t n, rt_stream st) {
+  return (int)cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, st);
+}
+static inline int rt_d2h(void *d, const void *s, size_t n, rt_stream st) {
+  return (int)cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, st);
+}
+static inline int rt_memset(void *d, int v, size_t n, rt_stream st) { return (int)cudaMemsetAsync(d, v, n, st); }
+static inline int rt_sync(rt_stream st) { return (int)cudaStreamSynchronize(st); }
+static inline const char *rt_errstr(int e) { return cudaGetErrorString((cudaError_t)e); }
+
+template <class Body, int PH>
+__device__ __forceinline__ void run_phases(const typename Body::Args &a, void *sm) {
+  Body::template phase<PH>(a, (int)blockIdx.x, (int)blockIdx.y, (int)threadIdx.x, sm);
+  if constexpr (PH + 1 < Body::NPHASE) {
+    __syncthreads();
+    run_phases<Body, PH + 1>(a, sm);
+  }
+}
+template <class Body>
+__global__ void __launch_bounds__(NT) k_run(const __grid_constant__ typename Body::Args a) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  run_phases<Body, 0>(a, smraw);
+}
+#endif
+
+// ======================================================================================
+// context
+// ======================================================================================
+struct Buf {
+  void *p = nullptr;
+  size_t bytes = 0;
+};
+
+struct ClassRun {   // scales sharing one pruned length K'
+  int log2K;
+  int first, count; // range in the sorted descriptor array
+};
+
+struct Job {
+  bool valid = false;
+  int precision = 0;       // CWTB_F64 / CWTB_F32
+  long long n0 = 0;
+  unsigned N = 0;
+  int log2N = 0;
+  int S = 0;
+  double dt = 0;
+  Fam fam{};
+  std::vector<ScaleDesc> descs;   // sorted by class
+  std::vector<ClassRun> classes;
+  std::vector<int> plan_log2K;    // per input scale
+  size_t b_single = 0;            // elements of the band buffer used by single-kernel scales
+  int sig_is_f32 = 0;
+};
+
+struct NTabDev {
+  double2 *hi = nullptr, *lo = nullptr;
+  int h = 0;
+};
+
+struct cwtb_ctx {
+  int device = 0;
+  rt_stream stream{};
+  rt_stream copy_stream{};
+  std::string err;
+  double band_eps = 1e-20;
+  int group = 4;  // scales per two-kernel chunk
+  double2 *tw64 = nullptr;
+  float2 *tw32 = nullptr;
+  std::map<unsigned, NTabDev> ntabs;
+  Buf sig, spec, Z, B, W, descs, table, scratch;
+  Job job;
+  const void *job_dsig = nullptr;  // device signal of the last cwt_dev call (not owned)
+  double last_ms = 0;
+  int launches = 0;
+  std::set<const void *> configured;
+  std::set<void *> pinned, devallocs;
+#ifndef CWTB_HOST_EMU
+  cudaEvent_t e0{}, e1{};
+#endif
+};
+
+static int fail(cwtb_ctx *c, int code, const std::string &msg) {
+  if (c) c->err = msg;
+  return code;
+}
+#define RT(call)                                                                             \
+  do {                                                                                       \
+    int e_ = (call);                                                                         \
+    if (e_ != 0) return fail(c, CWTB_ERR_CUDA, std::string(#call) + ": " + rt_errstr(e_));   \
+  } while (0)
+
+static int ensure(cwtb_ctx *c, Buf &b, size_t bytes) {
+  if (b.bytes >= bytes && b.p) return 0;
+  if (b.p) rt_free(b.p);
+  b.p = nullptr;
+  b.bytes = 0;
+  if (rt_malloc(&b.p, bytes) != 0) return fail(c, CWTB_ERR_NOMEM, "device allocation failed");
+  b.bytes = bytes;
+  return 0;
+}
+
+// ======================================================================================
+// launcher
+// ======================================================================================
+#ifdef CWTB_HOST_EMU
+template <class Body, int PH>
+static void emu_phases(const typename Body::Args &a, int bx, int by, void *sm) {
+  for (int tid = 0; tid < NT; ++tid) Body::template phase<PH>(a, bx, by, tid, sm);
+  if constexpr (PH + 1 < Body::NPHASE) emu_phases<Body, PH + 1>(a, bx, by, sm);
+}
+#endif
+
+template <class Body>
+static int launch(cwtb_ctx *c, unsigned gx, unsigned gy, const typename Body::Args &a) {
+  if (gx == 0 || gy == 0) return 0;
+#ifdef CWTB_HOST_EMU
+  std::vector<unsigned char> sm(Body::SMEM + 64);
+  for (unsigned by = 0; by < gy; ++by)
+    for (unsigned bx = 0; bx < gx; ++bx) emu_phases<Body, 0>(a, (int)bx, (int)by, sm.data());
+  c->launches++;
+  return 0;
+#else
+  const void *fn = (const void *)k_run<Body>;
+  if (Body::SMEM > 48 * 1024 && !c->configured.count(fn)) {
+    RT(cudaFuncSetAttribute(k_run<Body>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Body::SMEM));
+    c->configured.insert(fn);
+  }
+  // gridDim.y is limited to 65535
+  if (gy > 65535) return fail(c, CWTB_ERR_ARG, "too many rows in one launch");
+  k_run<Body><<<dim3(gx, gy), NT, Body::SMEM, c->stream>>>(a);
+  RT(cudaGetLastError());
+  c->launches++;
+  return 0;
+#endif
+}
+
+// ======================================================================================
+// tables
+// ======================================================================================
+static int make_table(cwtb_ctx *c, double2 *o64, float2 *o32, unsigned count, double step) {
+  TabArgs a{o64, o32, count, step};
+  return launch<TabBody>(c, (count + NT - 1) / NT, 1, a);
+}
+
+static int init_tables(cwtb_ctx *c) {
+  RT(rt_malloc((void **)&c->tw64, sizeof(double2) * KT));
+  RT(rt_malloc((void **)&c->tw32, sizeof(float2) * KT));
+  return make_table(c, c->tw64, c->tw32, KT, 1.0 / KT);
+}
+
+static int get_ntab(cwtb_ctx *c, unsigned N, int log2N, NTab *out) {
+  auto it = c->ntabs.find(N);
+  if (it == c->ntabs.end()) {
+    NTabDev t;
+    t.h = (log2N + 1) / 2;
+    unsigned nlo = 1u << t.h, nhi = N >> t.h;
+    if (nhi == 0) nhi = 1;
+    RT(rt_malloc((void **)&t.lo, sizeof(double2) * nlo));
+    RT(rt_malloc((void **)&t.hi, sizeof(double2) * nhi));
+    int e = make_table(c, t.lo, nullptr, nlo, 1.0 / (double)N);
+    if (e) return e;
+    e = make_table(c, t.hi, nullptr, nhi, (double)nlo / (double)N);
+    if (e) return e;
+    it = c->ntabs.emplace(N, t).first;
+  }
+  out->hi = it->second.hi;
+  out->lo = it->second.lo;
+  out->h = it->second.h;
+  out->lomask = (1u << it->second.h) - 1;
+  out->nmask = N - 1;
+  return 0;
+}
+
+// ======================================================================================
+// planning (host): band of each scale -> pruned length K'
+// ======================================================================================
+static int ilog2(unsigned long long v) {
+  int l = 0;
+  while ((1ull << l) < v) ++l;
+  return l;
+}
+
+// largest f (beyond the maximum of g) with  m*ln f - a(f) = target
+static double solve_upper(double m, bool gaussian, double target, double fstart) {
+  auto g = [&](double f) { return m * std::log(f) - (gaussian ? 0.5 * f * f : f); };
+  double lo = fstart, hi = fstart + 1;
+  while (g(hi) > target && hi < 1e7) hi *= 2;
+  for (int it = 0; it < 200; ++it) {
+    double mid = 0.5 * (lo + hi);
+    if (g(mid) > target) lo = mid; else hi = mid;
+  }
+  return hi;
+}
+
+// frequency-domain support [flo, fhi] (in f = s*w) where |psi_ft| >= eps * max|psi_ft|
+static void family_band(int family, double param, double eps, double *flo, double *fhi, bool *pos_only) {
+  const double LN_MIN = -745.2;  // exp() underflows to exactly 0 below this
+  const double lneps = eps > 0 ? std::log(eps) : 0;
+  *pos_only = false;
+  if (family == CWTB_MORLET) {
+    double xc = std::sqrt(-2.0 * (eps > 0 ? lneps : LN_MIN));
+    *flo = param - xc;
+    *fhi = param + xc;
+  } else if (family == CWTB_PAUL) {
+    double m = param;
+    double target = eps > 0 ? lneps + (m * std::log(m) - m) : LN_MIN;
+    *flo = 0;
+    *fhi = solve_upper(m, false, target, m);
+    *pos_only = true;
+  } else {  // DOG
+    double m = param;
+    double mx = m > 0 ? 0.5 * m * std::log(m) - 0.5 * m : 0.0;
+    double target = eps > 0 ? lneps + mx : LN_MIN;
+    double fc = solve_upper(m, true, target, std::sqrt(m > 0 ? m : 1.0));
+    *flo = -fc;
+    *fhi = fc;
+  }
+}
+
+static int build_job(cwtb_ctx *c, Job &job, long long n0, double dt, const double *scales, int S,
+                     int family, double param, int precision, bool have_table) {
+  if (n0 < 1 || S < 1 || !(dt > 0)) return fail(c, CWTB_ERR_ARG, "bad n0 / n_scales / dt");
+  if (family < 0 || family > 3) return fail(c, CWTB_ERR_ARG, "unknown wavelet family");
+  if (family == CWTB_TABLE && !have_table) return fail(c, CWTB_ERR_ARG, "CWTB_TABLE needs a table");
+  if ((family == CWTB_PAUL || family == CWTB_DOG) && (param != std::floor(param) || param < 1 || param > 64))
+    return fail(c, CWTB_ERR_ARG, "Paul/DOG order must be an integer in [1, 64]");
+  if (n0 > (1ll << 28)) return fail(c, CWTB_ERR_UNSUPPORTED, "signal longer than 2^28");
+  job = Job();
+  job.precision = precision;
+  job.n0 = n0;
+  job.log2N = ilog2((unsigned long long)n0);   // pycwt/helpers.py:27-30
+  job.N = 1u << job.log2N;
+  job.S = S;
+  job.dt = dt;
+  const unsigned N = job.N;
+  Fam &fam = job.fam;
+  fam.family = family;
+  fam.m = (int)param;
+  fam.f0 = param;
+  fam.unit = 0;
+  fam.dw = 1.0 / ((double)N * dt);
+  fam.table = nullptr;
+  fam.tpitch = N;
+  double fconst = 1.0;
+  if (family == CWTB_MORLET) fconst = std::pow(M_PI, -0.25);
+  else if (family == CWTB_PAUL) {
+    int m = (int)param;
+    double fact = 1;
+    for (int i = 2; i < 2 * m; ++i) fact *= i;  // prod(range(2, 2m)) = (2m-1)!
+    fconst = std::pow(2.0, m) / std::sqrt(m * fact);
+  } else if (family == CWTB_DOG) {
+    int m = (int)param;
+    fconst = 1.0 / std::sqrt(std::tgamma(m + 0.5));
+    // conj(-(1j**m)):  m%4: 0 -> -1, 1 -> +i, 2 -> +1, 3 -> -i
+    static const int unit_of[4] = {2, 1, 0, 3};
+    fam.unit = unit_of[m & 3];
+  }
+  const double w1 = 6.283185307179586 * (1.0 * fam.dw);  // ftfreqs[1]
+  double flo = 0, fhi = 0;
+  bool pos_only = false;
+  if (family != CWTB_TABLE) family_band(family, param, c->band_eps, &flo, &fhi, &pos_only);
+
+  std::vector<ScaleDesc> ds(S);
+  job.plan_log2K.assign(S, 0);
+  const long long half = (long long)N / 2;
+  for (int j = 0; j < S; ++j) {
+    ScaleDesc &d = ds[j];
+    const double s = scales[j];
+    d.s = s;
+    d.row = j;
+    d.trow = j;
+    d.boff = 0;
+    const double norm = std::sqrt(s * w1 * (double)N);  // wavelet.py:103
+    d.amp = (family == CWTB_TABLE ? 1.0 : norm * fconst) / (double)N;
+    long long klo = -half, khi = half - 1;
+    if (family != CWTB_TABLE && s > 0 && std::isfinite(s)) {
+      const double cc = (double)N * dt / (6.283185307179586 * s);
+      double a = std::ceil(flo * cc) - 1, b = std::floor(fhi * cc) + 1;
+      if (a > (double)klo) klo = (long long)a;
+      if (b < (double)khi) khi = (long long)b;
+      if (pos_only && klo < 1) klo = 1;
+    }
+    if (N == 1) { klo = 0; khi = 0; }
+    if (khi < klo) { klo = 1; khi = 0; }  // empty band: every B is zero
+    d.k_lo = (int)klo;
+    d.k_hi = (int)khi;
+    // window [lo, lo + K') must contain k = 0 (see DESIGN.md "pruned transform")
+    long long lo = std::min<long long>(klo, 0), hi = std::max<long long>(khi, 0);
+    if (khi < klo) { lo = 0; hi = 0; }
+    int lk = std::max(5, ilog2((unsigned long long)(hi - lo + 1)));
+    if (lk > 10) {  // two-kernel path: negative part must be a multiple of K2
+      lo = -((-lo + K2C - 1) / K2C) * K2C;
+      lk = std::max(11, ilog2((unsigned long long)(hi - lo + 1)));
+    }
+    if (lk >= job.log2N) {  // dense
+      lk = job.log2N;
+      d.rsplit = (int)half;
+      if (N == 1) d.rsplit = 1;
+    } else {
+      d.rsplit = (int)((1ll << lk) + lo);  // lo <= 0
+    }
+    d.log2K = lk;
+    job.plan_log2K[j] = (N < 32) ? 0 : lk;
+  }
+  // sort by class (descending K': small scales first), stable
+  std::vector<int> order(S);
+  for (int j = 0; j < S; ++j) order[j] = j;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return ds[a].log2K > ds[b].log2K; });
+  job.descs.resize(S);
+  size_t boff = 0;
+  for (int i = 0; i < S; ++i) {
+    job.descs[i] = ds[order[i]];
+    ScaleDesc &d = job.descs[i];
+    if (job.classes.empty() || job.classes.back().log2K != d.log2K)
+      job.classes.push_back(ClassRun{d.log2K, i, 0});
+    job.classes.back().count++;
+    if (d.log2K <= 10) {  // single-kernel scale: own slot in the band buffer
+      d.boff = (long long)boff;
+      boff += (size_t)1 << d.log2K;
+    }
+  }
+  job.b_single = boff;
+  job.valid = true;
+  return 0;
+}
+
+// ======================================================================================
+// execution
+// ======================================================================================
+template <typename T> struct Tw;
+template <> struct Tw<double> { static const double2 *get(cwtb_ctx *c) { return c->tw64; } };
+template <> struct Tw<float> { static const float2 *get(cwtb_ctx *c) { return c->tw32; } };
+
+// batched FFT over matrix rows, any power-of-two n >= 2; in/out on device.
+// real_in: input rows are T (zero-padded from n_in to n); else cx<T>.
+template <typename T, int SIGN>
+static int fft_rows(cwtb_ctx *c, const void *in, int real_in, long long in_pitch, long long n_in,
+                    cx<T> *out, long long out_pitch, unsigned n, int nrows, const T *mul,
+                    long long mul_pitch);
+
+template <typename T, int SIGN, int K>
+static int fft_rows_small(cwtb_ctx *c, const RowsArgs<T> &a) {
+  constexpr int P = Lay<T, K>::P;
+  return launch<RowsBody<T, K, SIGN>>(c, (a.nrows + P - 1) / P, 1, a);
+}
+
+template <typename T, int SIGN, int K1, int MODE>
+static int launch_passA(cwtb_ctx *c, const PassAArgs<T> &a, int ny) {
+  using B = PassABody<T, K1, MODE, SIGN>;
+  const unsigned M = a.N / ((unsigned)K1 * K2C);
+  return launch<B>(c, M * B::NTILE2, ny, a);
+}
+
+template <typename T, int SIGN, int MODE>
+static int dispatch_passA(cwtb_ctx *c, int log2K1, const PassAArgs<T> &a, int ny) {
+  switch (log2K1) {
+    case 1: return launch_passA<T, SIGN, 2, MODE>(c, a, ny);
+    case 2: return launch_passA<T, SIGN, 4, MODE>(c, a, ny);
+    case 3: return launch_passA<T, SIGN, 8, MODE>(c, a, ny);
+    case 4: return launch_passA<T, SIGN, 16, MODE>(c, a, ny);
+    case 5: return launch_passA<T, SIGN, 32, MODE>(c, a, ny);
+    case 6: return launch_passA<T, SIGN, 64, MODE>(c, a, ny);
+    case 7: return launch_passA<T, SIGN, 128, MODE>(c, a, ny);
+    case 8: return launch_passA<T, SIGN, 256, MODE>(c, a, ny);
+    case 9: return launch_passA<T, SIGN, 512, MODE>(c, a, ny);
+    case 10: return launch_passA<T, SIGN, 1024, MODE>(c, a, ny);
+  }
+  return fail(c, CWTB_ERR_UNSUPPORTED, "transform longer than 2^20 per row is not supported yet");
+}
+
+template <typename T, int SIGN>
+static int fft_rows(cwtb_ctx *c, const void *in, int real_in, long long in_pitch, long long n_in,
+                    cx<T> *out, long long out_pitch, unsigned n, int nrows, const T *mul,
+                    long long mul_pitch) {
+  const int l2 = ilog2(n);
+  if (n <= 1024) {
+    RowsArgs<T> a;
+    a.in = in; a.out = out; a.tw = Tw<T>::get(c); a.mul = mul;
+    a.in_pitch = in_pitch; a.out_pitch = out_pitch; a.n_in = n_in; a.mul_pitch = mul_pitch;
+    a.nrows = nrows; a.real_in = real_in;
+    switch (l2) {
+      case 1: return fft_rows_small<T, SIGN, 2>(c, a);
+      case 2: return fft_rows_small<T, SIGN, 4>(c, a);
+      case 3: return fft_rows_small<T, SIGN, 8>(c, a);
+      case 4: return fft_rows_small<T, SIGN, 16>(c, a);
+      case 5: return fft_rows_small<T, SIGN, 32>(c, a);
+      case 6: return fft_rows_small<T, SIGN, 64>(c, a);
+      case 7: return fft_rows_small<T, SIGN, 128>(c, a);
+      case 8: return fft_rows_small<T, SIGN, 256>(c, a);
+      case 9: return fft_rows_small<T, SIGN, 512>(c, a);
+      case 10: return fft_rows_small<T, SIGN, 1024>(c, a);
+    }
+    return fail(c, CWTB_ERR_ARG, "fft_rows: bad length");
+  }
+  if (mul) return fail(c, CWTB_ERR_UNSUPPORTED, "fft_rows: multiplier only for n <= 1024");
+  // two kernels through Z, in chunks of rows
+  NTab nt;
+  int e = get_ntab(c, n, l2, &nt);
+  if (e) return e;
+  const int chunk = std::max(1, std::min(nrows, (int)std::max<size_t>(1, (64u << 20) / ((size_t)n * sizeof(cx<T>)))));
+  e = ensure(c, c->Z, (size_t)chunk * n * sizeof(cx<T>));
+  if (e) return e;
+  for (int r0 = 0; r0 < nrows; r0 += chunk) {
+    const int nr = std::min(chunk, nrows - r0);
+    PassAArgs<T> a{};
+    a.in = in; a.Z = (cx<T> *)c->Z.p; a.tw = Tw<T>::get(c); a.nt = nt;
+    a.in_pitch = in_pitch; a.n_in = n_in; a.N = n; a.first = 0; a.row0 = r0;
+    e = real_in ? dispatch_passA<T, SIGN, MODE_REAL>(c, l2 - 10, a, nr)
+                : dispatch_passA<T, SIGN, MODE_CPLX>(c, l2 - 10, a, nr);
+    if (e) return e;
+    PassBArgs<T> b{};
+    b.Z = (const cx<T> *)c->Z.p; b.out = out; b.tw = Tw<T>::get(c); b.descs = nullptr;
+    b.pitch = out_pitch; b.nout = n; b.N = n; b.first = 0; b.row0 = r0;
+    e = launch<PassBBody<T, SIGN>>(c, (n / K2C + Lay<T, K2C>::P - 1) / Lay<T, K2C>::P, nr, b);
+    if (e) return e;
+  }
+  return 0;
+}
+
+template <typename T, int K>
+static int launch_single(cwtb_ctx *c, const SingleArgs<T> &a, int count) {
+  constexpr int P = Lay<T, K>::P;
+  const unsigned M = a.N / K;
+  return launch<SingleBody<T, K>>(c, (M + P - 1) / P, count, a);
+}
+
+// all kernels of one transform: forward FFT of the (device, type T) signal, then every scale
+template <typename T>
+static int run_job(cwtb_ctx *c, const Job &job, const T *dsig) {
+  using V = cx<T>;
+  const unsigned N = job.N;
+  const int S = job.S;
+  int e;
+  if ((e = ensure(c, c->spec, (size_t)N * sizeof(V)))) return e;
+  if ((e = ensure(c, c->W, (size_t)S * job.n0 * sizeof(V)))) return e;
+  V *spec = (V *)c->spec.p;
+  V *W = (V *)c->W.p;
+  const ScaleDesc *ddesc = (const ScaleDesc *)c->descs.p;
+  Fam fam = job.fam;
+  if (fam.family == CWTB_TABLE) fam.table = (const double2 *)c->table.p;
+
+  // ---- forward transform of the zero-padded signal (wavelet.py:91) ----
+  if (N < 32) {
+    TinyFwdArgs<T> fa{dsig, spec, job.n0, N};
+    if ((e = launch<TinyFwdBody<T>>(c, 1, 1, fa))) return e;
+    TinyArgs<T> ta{ddesc, spec, W, fam, job.n0, N, 0};
+    return launch<TinyBody<T>>(c, (unsigned)((job.n0 + NT - 1) / NT), S, ta);
+  }
+  if ((e = fft_rows<T, -1>(c, dsig, 1, job.n0, job.n0, spec, N, N, 1, nullptr, 0))) return e;
+
+  NTab nt;
+  if ((e = get_ntab(c, N, job.log2N, &nt))) return e;
+  const int G = std::max(1, c->group);
+  const size_t bchunk = (size_t)G * (N / 2);
+  if ((e = ensure(c, c->B, (job.b_single + bchunk) * sizeof(V)))) return e;
+  V *Bbuf = (V *)c->B.p;
+
+  for (const ClassRun &cl : job.classes) {
+    const unsigned K = 1u << cl.log2K;
+    if (cl.log2K <= 10) {
+      // ---- single kernel: band product, then pruned K'-point transforms ----
+      BandArgs<T> ba{ddesc, spec, Bbuf, fam, N, cl.first};
+      if ((e = launch<BandBody<T>>(c, (K + NT * BandBody<T>::PER - 1) / (NT * BandBody<T>::PER), cl.count, ba)))
+        return e;
+      SingleArgs<T> sa{ddesc, Bbuf, W, Tw<T>::get(c), nt, job.n0, N, cl.first};
+      switch (cl.log2K) {
+        case 5: e = launch_single<T, 32>(c, sa, cl.count); break;
+        case 6: e = launch_single<T, 64>(c, sa, cl.count); break;
+        case 7: e = launch_single<T, 128>(c, sa, cl.count); break;
+        case 8: e = launch_single<T, 256>(c, sa, cl.count); break;
+        case 9: e = launch_single<T, 512>(c, sa, cl.count); break;
+        case 10: e = launch_single<T, 1024>(c, sa, cl.count); break;
+        default: e = fail(c, CWTB_ERR_STATE, "bad single-kernel class");
+      }
+      if (e) return e;
+      continue;
+    }
+    // ---- two kernels through Z, G scales at a time ----
+    const bool dense = (cl.log2K == job.log2N);
+    if ((e = ensure(c, c->Z, (size_t)G * N * sizeof(V)))) return e;
+    for (int g0 = 0; g0 < cl.count; g0 += G) {
+      const int ng = std::min(G, cl.count - g0);
+      PassAArgs<T> a{};
+      a.descs = ddesc; a.spec = spec; a.Bbuf = Bbuf; a.Z = (V *)c->Z.p; a.tw = Tw<T>::get(c);
+      a.fam = fam; a.nt = nt; a.N = N; a.first = cl.first + g0; a.row0 = 0;
+      if (dense) {
+        e = dispatch_passA<T, +1, MODE_DENSE>(c, cl.log2K - 10, a, ng);
+      } else {
+        BandArgs<T> ba{ddesc, spec, Bbuf, fam, N, cl.first + g0};
+        if ((e = launch<BandBody<T>>(c, (K + NT * BandBody<T>::PER - 1) / (NT * BandBody<T>::PER), ng, ba)))
+          return e;
+        e = dispatch_passA<T, +1, MODE_BAND>(c, cl.log2K - 10, a, ng);
+      }
+      if (e) return e;
+      PassBArgs<T> b{};
+      b.Z = (const V *)c->Z.p; b.out = W; b.tw = Tw<T>::get(c); b.descs = ddesc;
+      b.pitch = job.n0; b.nout = job.n0; b.N = N; b.first = cl.first + g0; b.row0 = 0;
+      if ((e = launch<PassBBody<T, +1>>(c, (N / K2C + Lay<T, K2C>::P - 1) / Lay<T, K2C>::P, ng, b))) return e;
+    }
+  }
+  return 0;
+}
+
+// band-buffer offsets of the two-kernel scales depend on the chunk position; set them here
+static void assign_chunk_offsets(cwtb_ctx *c, Job &job) {
+  const int G = std::max(1, c->group);
+  for (const ClassRun &cl : job.classes) {
+    if (cl.log2K <= 10 || cl.log2K == job.log2N) continue;
+    for (int i = 0; i < cl.count; ++i)
+      job.descs[cl.first + i].boff = (long long)(job.b_single + (size_t)(i % G) * ((size_t)1 << cl.log2K));
+  }
+}
+
+static int upload_descs(cwtb_ctx *c, Job &job) {
+  assign_chunk_offsets(c, job);
+  int e = ensure(c, c->descs, job.descs.size() * sizeof(ScaleDesc));
+  if (e) return e;
+  RT(rt_h2d(c->descs.p, job.descs.data(), job.descs.size() * sizeof(ScaleDesc), c->stream));
+  RT(rt_sync(c->stream));  // job.descs is pageable host memory
+  return 0;
+}
+
+static int timed_run(cwtb_ctx *c, const void *dsig, int iters, double *ms_out) {
+  const Job &job = c->job;
+  c->launches = 0;
+#ifndef CWTB_HOST_EMU
+  RT(cudaEventRecord(c->e0, c->stream));
+#endif
+  for (int it = 0; it < iters; ++it) {
+    int e = job.precision == CWTB_F64 ? run_job<double>(c, job, (const double *)dsig)
+                                      : run_job<float>(c, job, (const float *)dsig);
+    if (e) return e;
+  }
+  float ms = 0;
+#ifndef CWTB_HOST_EMU
+  RT(cudaEventRecord(c->e1, c->stream));
+  RT(cudaEventSynchronize(c->e1));
+  RT(cudaEventElapsedTime(&ms, c->e0, c->e1));
+#endif
+  if (ms_out) *ms_out = (double)ms / iters;
+  c->launches /= std::max(1, iters);
+  return 0;
+}
+
+// ---- conversions ---------------------------------------------------------------------
+template <typename TI, typename TO> struct CvtArgs { const TI *in; TO *out; long long n; };
+template <typename TI, typename TO> struct CvtBody {
+  using Args = CvtArgs<TI, TO>;
+  static constexpr int NPHASE = 1;
+  static constexpr size_t SMEM = 0;
+  template <int PH> HD static void phase(const Args &a, int bx, int, int tid, void *) {
+    long long i = (long long)bx * NT + tid;
+    if (i < a.n) a.out[i] = (TO)a.in[i];
+  }
+};
+
+// ======================================================================================
+// C ABI
+// ======================================================================================
+extern "C" {
+
+const char *cwtb_version(void) {
+#ifdef CWTB_HOST_EMU
+  return "cwt_b200 0.1 (host emulation build - tests only)";
+#else
+  return "cwt_b200 0.1 (sm_100a)";
+#endif
+}
+
+int cwtb_device_count(void) {
+#ifdef CWTB_HOST_EMU
+  return 1;
+#else
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+#endif
+}
+
+int cwtb_create(int device, cwtb_ctx **out) {
+  if (!out) return CWTB_ERR_ARG;
+  *out = nullptr;
+  cwtb_ctx *c = new cwtb_ctx();
+  c->device = device;
+#ifndef CWTB_HOST_EMU
+  if (cudaSetDevice(device) != cudaSuccess) { delete c; return CWTB_ERR_CUDA; }
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return CWTB_ERR_CUDA; }
+  if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return CWTB_ERR_CUDA; }
+  cudaEventCreate(&c->e0);
+  cudaEventCreate(&c->e1);
+#endif
+  if (const char *g = getenv("CWTB_GROUP")) c->group = std::max(1, atoi(g));
+  if (const char *g = getenv("CWTB_BAND_EPS")) c->band_eps = atof(g);
+  int e = init_tables(c);
+  if (e == 0) e = rt_sync(c->stream) ? CWTB_ERR_CUDA : 0;
+  if (e) { delete c; return e; }
+  *out = c;
+  return CWTB_OK;
+}
+
+void cwtb_destroy(cwtb_ctx *c) {
+  if (!c) return;
+#ifndef CWTB_HOST_EMU
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+#endif
+  for (Buf *b : {&c->sig, &c->spec, &c->Z, &c->B, &c->W, &c->descs, &c->table, &c->scratch})
+    if (b->p) rt_free(b->p);
+  for (auto &kv : c->ntabs) { rt_free(kv.second.hi); rt_free(kv.second.lo); }
+  if (c->tw64) rt_free(c->tw64);
+  if (c->tw32) rt_free(c->tw32);
+  for (void *p : c->pinned) rt_host_free(p);
+  for (void *p : c->devallocs) rt_free(p);
+#ifndef CWTB_HOST_EMU
+  cudaEventDestroy(c->e0);
+  cudaEventDestroy(c->e1);
+  cudaStreamDestroy(c->stream);
+  cudaStreamDestroy(c->copy_stream);
+#endif
+  delete c;
+}
+
+const char *cwtb_last_error(cwtb_ctx *c) { return c ? c->err.c_str() : "null context"; }
+
+int cwtb_set_band_eps(cwtb_ctx *c, double eps) {
+  if (!c || !(eps >= 0) || eps >= 1e-6) return fail(c, CWTB_ERR_ARG, "band eps must be in [0, 1e-6)");
+  c->band_eps = eps;
+  return 0;
+}
+
+int cwtb_host_alloc(cwtb_ctx *c, size_t bytes, void **out) {
+  if (!c || !out) return CWTB_ERR_ARG;
+  if (rt_host_alloc(out, bytes) != 0) return fail(c, CWTB_ERR_NOMEM, "pinned allocation failed");
+  c->pinned.insert(*out);
+  return 0;
+}
+int cwtb_host_free(cwtb_ctx *c, void *p) {
+  if (!c || !c->pinned.count(p)) return CWTB_ERR_ARG;
+  c->pinned.erase(p);
+  rt_host_free(p);
+  return 0;
+}
+int cwtb_dev_alloc(cwtb_ctx *c, size_t bytes, void **out) {
+  if (!c || !out) return CWTB_ERR_ARG;
+  if (rt_malloc(out, bytes) != 0) return fail(c, CWTB_ERR_NOMEM, "device allocation failed");
+  c->devallocs.insert(*out);
+  return 0;
+}
+int cwtb_dev_free(cwtb_ctx *c, void *p) {
+  if (!c || !c->devallocs.count(p)) return CWTB_ERR_ARG;
+  c->devallocs.erase(p);
+  rt_free(p);
+  return 0;
+}
+int cwtb_memcpy_h2d(cwtb_ctx *c, void *dst, const void *src, size_t bytes) {
+  RT(rt_h2d(dst, src, bytes, c->stream));
+  RT(rt_sync(c->stream));
+  return 0;
+}
+int cwtb_memcpy_d2h(cwtb_ctx *c, void *dst, const void *src, size_t bytes) {
+  RT(rt_d2h(dst, src, bytes, c->stream));
+  RT(rt_sync(c->stream));
+  return 0;
+}
+int cwtb_sync(cwtb_ctx *c) {
+  RT(rt_sync(c->stream));
+  return 0;
+}
+
+static int prepare(cwtb_ctx *c, long long n0, double dt, const double *scales, int S, int family,
+                   double param, int precision, const void *table) {
+  if (!c) return CWTB_ERR_ARG;
+  if (precision != CWTB_F64 && precision != CWTB_F32) return fail(c, CWTB_ERR_ARG, "bad precision");
+  if (!scales) return fail(c, CWTB_ERR_ARG, "null scales");
+#ifndef CWTB_HOST_EMU
+  RT(cudaSetDevice(c->device));
+#endif
+  int e = build_job(c, c->job, n0, dt, scales, S, family, param, precision, table != nullptr);
+  if (e) return e;
+  if (family == CWTB_TABLE) {
+    size_t bytes = (size_t)S * c->job.N * sizeof(double2);
+    if ((e = ensure(c, c->table, bytes))) return e;
+    RT(rt_h2d(c->table.p, table, bytes, c->stream));
+  }
+  return upload_descs(c, c->job);
+}
+
+int cwtb_cwt_dev(cwtb_ctx *c, const void *d_signal, int signal_is_f32, int64_t n0, double dt,
+                 const double *scales, int n_scales, int family, double param, int precision) {
+  if (!c || !d_signal) return fail(c, CWTB_ERR_ARG, "null argument");
+  if (family == CWTB_TABLE) return fail(c, CWTB_ERR_UNSUPPORTED, "use cwtb_cwt for CWTB_TABLE");
+  int e = prepare(c, n0, dt, scales, n_scales, family, param, precision, nullptr);
+  if (e) return e;
+  const void *dsig = d_signal;
+  const bool want_f32 = (precision == CWTB_F32);
+  if ((signal_is_f32 != 0) != want_f32) {  // convert to the engine's real type
+    if ((e = ensure(c, c->sig, (size_t)n0 * (want_f32 ? 4 : 8)))) return e;
+    unsigned gx = (unsigned)((n0 + NT - 1) / NT);
+    if (want_f32) {
+      CvtArgs<double, float> a{(const double *)d_signal, (float *)c->sig.p, n0};
+      e = launch<CvtBody<double, float>>(c, gx, 1, a);
+    } else {
+      CvtArgs<float, double> a{(const float *)d_signal, (double *)c->sig.p, n0};
+      e = launch<CvtBody<float, double>>(c, gx, 1, a);
+    }
+    if (e) return e;
+    dsig = c->sig.p;
+  }
+  c->job_dsig = dsig;
+  c->job.sig_is_f32 = want_f32;
+  return timed_run(c, dsig, 1, &c->last_ms);
+}
+
+int cwtb_cwt(cwtb_ctx *c, const void *signal, int signal_is_f32, int64_t n0, double dt,
+             const double *scales, int n_scales, int family, double param, int precision,
+             const void *table) {
+  if (!c || !signal) return fail(c, CWTB_ERR_ARG, "null argument");
+  int e = prepare(c, n0, dt, scales, n_scales, family, param, precision, table);
+  if (e) return e;
+  const bool want_f32 = (precision == CWTB_F32);
+  const size_t esz = want_f32 ? 4 : 8;
+  if ((e = ensure(c, c->sig, (size_t)n0 * esz))) return e;
+  if ((signal_is_f32 != 0) == want_f32) {
+    RT(rt_h2d(c->sig.p, signal, (size_t)n0 * esz, c->stream));
+    RT(rt_sync(c->stream));
+  } else {
+    std::vector<unsigned char> tmp((size_t)n0 * esz);
+    if (want_f32) for (int64_t i = 0; i < n0; ++i) ((float *)tmp.data())[i] = (float)((const double *)signal)[i];
+    else for (int64_t i = 0; i < n0; ++i) ((double *)tmp.data())[i] = (double)((const float *)signal)[i];
+    RT(rt_h2d(c->sig.p, tmp.data(), (size_t)n0 * esz, c->stream));
+    RT(rt_sync(c->stream));
+  }
+  c->job_dsig = c->sig.p;
+  c->job.sig_is_f32 = want_f32;
+  return timed_run(c, c->sig.p, 1, &c->last_ms);
+}
+
+int cwtb_bench_last(cwtb_ctx *c, int iters, double *ms_out) {
+  if (!c || !c->job.valid || !c->job_dsig) return fail(c, CWTB_ERR_STATE, "no transform to re-run");
+  if (iters < 1) return fail(c, CWTB_ERR_ARG, "iters < 1");
+  return timed_run(c, c->job_dsig, iters, ms_out);
+}
+
+double cwtb_last_kernel_ms(cwtb_ctx *c) { return c ? c->last_ms : -1; }
+int cwtb_last_launch_count(cwtb_ctx *c) { return c ? c->launches : -1; }
+int64_t cwtb_padded_length(cwtb_ctx *c) { return (c && c->job.valid) ? (int64_t)c->job.N : -1; }
+void *cwtb_w_device_ptr(cwtb_ctx *c) { return (c && c->job.valid) ? c->W.p : nullptr; }
+
+int cwtb_last_plan(cwtb_ctx *c, int *out, int n) {
+  if (!c || !c->job.valid || !out) return CWTB_ERR_ARG;
+  int m = std::min<int>(n, (int)c->job.plan_log2K.size());
+  for (int i = 0; i < m; ++i) out[i] = c->job.plan_log2K[i];
+  return m;
+}
+
+int cwtb_get_w(cwtb_ctx *c, void *out, int out_f64, int row0, int nrows) {
+  if (!c || !c->job.valid || !out) return fail(c, CWTB_ERR_STATE, "no transform resident");
+  const Job &job = c->job;
+  if (row0 < 0 || nrows < 0 || row0 + nrows > job.S) return fail(c, CWTB_ERR_ARG, "row range");
+  const size_t cnt = (size_t)nrows * job.n0;
+  if (job.precision == CWTB_F64) {
+    RT(rt_d2h(out, (const double2 *)c->W.p + (size_t)row0 * job.n0, cnt * sizeof(double2), c->stream));
+    RT(rt_sync(c->stream));
+  } else if (!out_f64) {
+    RT(rt_d2h(out, (const float2 *)c->W.p + (size_t)row0 * job.n0, cnt * sizeof(float2), c->stream));
+    RT(rt_sync(c->stream));
+  } else {
+    std::vector<float> tmp(cnt * 2);
+    RT(rt_d2h(tmp.data(), (const float2 *)c->W.p + (size_t)row0 * job.n0, cnt * sizeof(float2), c->stream));
+    RT(rt_sync(c->stream));
+    double *o = (double *)out;
+    for (size_t i = 0; i < cnt * 2; ++i) o[i] = (double)tmp[i];
+  }
+  return 0;
+}
+
+int cwtb_get_signal_fft(cwtb_ctx *c, void *out) {
+  if (!c || !c->job.valid || !out) return fail(c, CWTB_ERR_STATE, "no transform resident");
+  const Job &job = c->job;
+  const size_t cnt = job.N / 2 > 0 ? job.N / 2 - 1 : 0;
+  if (cnt == 0) return 0;
+  const double sc = 1.0 / std::sqrt((double)job.N);
+  double *o = (double *)out;
+  if (job.precision == CWTB_F64) {
+    RT(rt_d2h(out, (const double2 *)c->spec.p + 1, cnt * sizeof(double2), c->stream));
+    RT(rt_sync(c->stream));
+    for (size_t i = 0; i < cnt * 2; ++i) o[i] *= sc;
+  } else {
+    std::vector<float> tmp(cnt * 2);
+    RT(rt_d2h(tmp.data(), (const float2 *)c->spec.p + 1, cnt * sizeof(float2), c->stream));
+    RT(rt_sync(c->stream));
+    for (size_t i = 0; i < cnt * 2; ++i) o[i] = (double)tmp[i] * sc;
+  }
+  return 0;
+}
+
+int cwtb_fft_c2c(cwtb_ctx *c, const void *in, void *out, int64_t n, int batch, int sign, int precision) {
+  if (!c || !in || !out || n < 2 || (n & (n - 1)) || batch < 1 || (sign != 1 && sign != -1))
+    return fail(c, CWTB_ERR_ARG, "fft_c2c: bad argument");
+  if (n > (1ll << 20)) return fail(c, CWTB_ERR_UNSUPPORTED, "fft_c2c: n > 2^20");
+  const size_t cnt = (size_t)n * batch;
+  void *din = nullptr, *dout = nullptr;
+  const size_t esz = precision == CWTB_F64 ? sizeof(double2) : sizeof(float2);
+  RT(rt_malloc(&din, cnt * esz));
+  RT(rt_malloc(&dout, cnt * esz));
+  int e = 0;
+  if (precision == CWTB_F64) {
+    rt_h2d(din, in, cnt * esz, c->stream);
+    e = sign < 0 ? fft_rows<double, -1>(c, din, 0, n, n, (double2 *)dout, n, (unsigned)n, batch, nullptr, 0)
+                 : fft_rows<double, +1>(c, din, 0, n, n, (double2 *)dout, n, (unsigned)n, batch, nullptr, 0);
+    if (!e) { rt_d2h(out, dout, cnt * esz, c->stream); e = rt_sync(c->stream) ? CWTB_ERR_CUDA : 0; }
+  } else {
+    std::vector<float> tmp(cnt * 2);
+    const double *src = (const double *)in;
+    for (size_t i = 0; i < cnt * 2; ++i) tmp[i] = (float)src[i];
+    rt_h2d(din, tmp.data(), cnt * esz, c->stream);
+    rt_sync(c->stream);
+    e = sign < 0 ? fft_rows<float, -1>(c, din, 0, n, n, (float2 *)dout, n, (unsigned)n, batch, nullptr, 0)
+                 : fft_rows<float, +1>(c, din, 0, n, n, (float2 *)dout, n, (unsigned)n, batch, nullptr, 0);
+    if (!e) {
+      rt_d2h(tmp.data(), dout, cnt * esz, c->stream);
+      e = rt_sync(c->stream) ? CWTB_ERR_CUDA : 0;
+      double *o = (double *)out;
+      for (size_t i = 0; i < cnt * 2; ++i) o[i] = (double)tmp[i];
+    }
+  }
+  rt_sync(c->stream);
+  rt_free(din);
+  rt_free(dout);
+  return e;
+}
+
+}  // extern "C"

@@ -1,0 +1,225 @@
+// Batched K-point FFT on a [P][K] tile: the compute core shared by every kernel
+// of the engine.
+//
+// One CTA (NT threads) owns a tile of P independent K-point transforms
+// (P * K = TILE elements).  The transform is an in-place decimation-in-frequency
+// mixed-radix FFT with radices (R1, R2, R3) taken from Plan<K>:
+//
+//   * every pass but the last:  lanes run over the position inside the transform,
+//     each thread LOOPS over the batch index b with the pass twiddles held in
+//     registers (loaded once per thread, reused for all its b);
+//   * the last pass is twiddle-free and its lanes run over b, so that the results
+//     leave the CTA straight from registers as P*sizeof(complex)-byte contiguous
+//     segments (b is the contiguous index in global memory for every output
+//     layout the engine uses);
+//   * between passes the tile lives in shared memory; a thread reads and writes
+//     the same positions in a pass (in-place), so only one barrier per pass.
+//
+// After the passes, output index q of a transform is  q = c1 + R1*(c2 + R2*c3)
+// where c_i is the output digit of pass i (digit reversal is absorbed by the
+// final global store).
+//
+// All functions take the thread id as an argument and are __host__ __device__:
+// tests emulate a CTA on the CPU by looping over tid phase by phase.
+#pragma once
+#include "cplx.cuh"
+
+namespace cwtb {
+
+constexpr int NT = 128;     // threads per CTA
+constexpr int KT = 4096;    // size of the master twiddle table e^{2 pi i t / KT}
+constexpr int K2C = 1024;   // length of the second-pass transform (two-kernel scales)
+
+template <typename T> struct TileCfg {
+  static constexpr int TILE = sizeof(T) == 8 ? 4096 : 8192;  // elements per CTA (64 KiB)
+  static constexpr int Q = 128 / (2 * (int)sizeof(T));       // lanes per smem conflict domain
+};
+
+template <int K> struct Plan;
+#define CWTB_PLAN(K_, A_, B_, C_)                                                   \
+  template <> struct Plan<K_> {                                                     \
+    static constexpr int R1 = A_, R2 = B_, R3 = C_;                                 \
+    static constexpr int NP = (B_ == 1) ? 1 : ((C_ == 1) ? 2 : 3);                  \
+    static constexpr int RL = (NP == 1) ? A_ : ((NP == 2) ? B_ : C_); /* last */    \
+    HD static int qlow(int g) {                                                     \
+      return NP == 3 ? (g / B_) + A_ * (g % B_) : (NP == 2 ? g : 0);                \
+    }                                                                               \
+  };
+CWTB_PLAN(2, 2, 1, 1)
+CWTB_PLAN(4, 4, 1, 1)
+CWTB_PLAN(8, 8, 1, 1)
+CWTB_PLAN(16, 16, 1, 1)
+CWTB_PLAN(32, 4, 8, 1)
+CWTB_PLAN(64, 8, 8, 1)
+CWTB_PLAN(128, 8, 16, 1)
+CWTB_PLAN(256, 16, 16, 1)
+CWTB_PLAN(512, 8, 8, 8)
+CWTB_PLAN(1024, 8, 8, 16)
+#undef CWTB_PLAN
+
+// Shared-memory layout of the tile: [b][pos] with a row pitch chosen so that both
+// access patterns (lanes over pos, lanes over b) are bank-conflict free.
+template <typename T, int K> struct Lay {
+  static constexpr int TILE = TileCfg<T>::TILE;
+  static constexpr int P = TILE / K;
+  static constexpr int Q = TileCfg<T>::Q;
+  static constexpr bool SKEW = (P < Q);  // last pass mixes b and position lanes
+  static constexpr int KS = SKEW ? K + K / 16 : K;
+  static constexpr int PITCH = SKEW ? (KS - (KS % Q) + 2 + ((KS % Q) > 2 ? Q : 0)) : K + 1;
+  static constexpr int ELEMS = P * PITCH;
+  static constexpr size_t BYTES = (Plan<K>::NP == 1) ? 0 : (size_t)ELEMS * 2 * sizeof(T);
+  HD static int phys(int b, int pos) { return b * PITCH + pos + (SKEW ? (pos >> 4) : 0); }
+};
+
+template <typename V> HD V ldg(const V *p) {
+#ifdef __CUDA_ARCH__
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+
+// e^{2 pi i e / N} from a two-level table (N a power of two): hi[e >> h] * lo[e & mask].
+struct NTab {
+  const double2 *hi;
+  const double2 *lo;
+  int h;
+  unsigned lomask;
+  unsigned nmask;  // N - 1
+};
+HD double2 nroot(const NTab &t, unsigned e) {
+  e &= t.nmask;
+  return cmul(ldg(&t.hi[e >> t.h]), ldg(&t.lo[e & t.lomask]));
+}
+template <typename T> HD cx<T> nroot_t(const NTab &t, unsigned e) {
+  double2 w = nroot(t, e);
+  return mk<T>((T)w.x, (T)w.y);
+}
+
+// ---- loaders for the first pass (template on radix R) -------------------------
+// Interface:  begin(base, stride, bstart, bstep);  load(b, x[R])
+//   the R inputs of the butterfly sit at positions base + i*stride.
+
+template <typename T, int K> struct SmemLoader {
+  using V = cx<T>;
+  const V *sm;
+  int base, stride;
+  HD void begin(int base_, int stride_, int, int) { base = base_; stride = stride_; }
+  template <int R> HD void load(int b, V (&x)[R]) const {
+#pragma unroll
+    for (int i = 0; i < R; ++i) x[i] = sm[Lay<T, K>::phys(b, base + i * stride)];
+  }
+};
+
+// rows of a [rows][K] global array (second-pass kernel: Z[u][r2])
+template <typename T, int K> struct RowLoader {
+  using V = cx<T>;
+  const V *src;   // already offset to row u0
+  int nvalid;     // rows available from u0
+  int base, stride;
+  HD void begin(int base_, int stride_, int, int) { base = base_; stride = stride_; }
+  template <int R> HD void load(int b, V (&x)[R]) const {
+    if (b < nvalid) {
+      const V *row = src + (size_t)b * K + base;
+#pragma unroll
+      for (int i = 0; i < R; ++i) x[i] = row[i * stride];
+    } else {
+#pragma unroll
+      for (int i = 0; i < R; ++i) x[i] = mk<T>(0, 0);
+    }
+  }
+};
+
+// pruned-band generator: a_p[r] = B[r] * e^{2 pi i k p / N}, p = p0 + b, advanced by
+// recurrence over b (a <- a * delta, delta = e^{2 pi i k bstep / N}).
+template <typename T, int K, int R> struct GenLoader {
+  using V = cx<T>;
+  const V *B;      // K entries, residue order
+  NTab nt;
+  int rsplit;      // r >= rsplit  ->  k = r - K
+  unsigned p0;
+  V a[R], d[R];
+  HD void begin(int base, int stride, int bstart, int bstep) {
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      int r = base + i * stride;
+      int k = r - (r >= rsplit ? K : 0);
+      V e0 = nroot_t<T>(nt, (unsigned)k * (p0 + (unsigned)bstart));
+      d[i] = nroot_t<T>(nt, (unsigned)k * (unsigned)bstep);
+      a[i] = cmul(ldg(&B[r]), e0);
+    }
+  }
+  HD void load(int, V (&x)[R]) {
+#pragma unroll
+    for (int i = 0; i < R; ++i) { x[i] = a[i]; a[i] = cmul(a[i], d[i]); }
+  }
+};
+
+// ---- passes --------------------------------------------------------------------
+// One non-final pass on sub-transforms of length L (K/L of them per row).
+template <typename T, int K, int L, int R, int SIGN, class Loader>
+HD void pass_mid(cx<T> *sm, const cx<T> *__restrict__ tw, Loader &ld, int tid) {
+  using V = cx<T>;
+  using LY = Lay<T, K>;
+  constexpr int Ln = L / R, I = K / R, P = LY::P;
+  constexpr int LANES = (I >= NT) ? NT : I;
+  constexpr int GROUPS = NT / LANES;
+  const int tp0 = tid % LANES, bg = tid / LANES;
+  for (int tp = tp0; tp < I; tp += LANES) {
+    const int g = tp / Ln, j = tp % Ln;
+    V twv[R];
+#pragma unroll
+    for (int c = 1; c < R; ++c) {
+      V w = ldg(&tw[(j * c) * (KT / L)]);
+      if (SIGN < 0) w.y = -w.y;
+      twv[c] = w;
+    }
+    ld.begin(g * L + j, Ln, bg, GROUPS);
+    for (int b = bg; b < P; b += GROUPS) {
+      V x[R];
+      ld.load(b, x);
+      dftR<R, SIGN, T>(x);
+#pragma unroll
+      for (int c = 1; c < R; ++c) x[c] = cmul(x[c], twv[c]);
+#pragma unroll
+      for (int c = 0; c < R; ++c) sm[LY::phys(b, g * L + c * Ln + j)] = x[c];
+    }
+  }
+}
+
+// Final pass: radix R = Plan<K>::RL on K/R sub-transforms per row, lanes over b.
+// Storer interface: store(b, qlow, qstride, x[R])  with output index q = qlow + c*qstride.
+template <typename T, int K, int SIGN, class Storer>
+HD void pass_last(const cx<T> *sm, Storer &st, int tid) {
+  using V = cx<T>;
+  using LY = Lay<T, K>;
+  constexpr int R = Plan<K>::RL, G = K / R, P = LY::P;
+  for (int idx = tid; idx < G * P; idx += NT) {
+    const int b = idx % P, g = idx / P;
+    V x[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) x[i] = sm[LY::phys(b, g * R + i)];
+    dftR<R, SIGN, T>(x);
+    st.store(b, Plan<K>::qlow(g), G, x);
+  }
+}
+
+// Runs passes [first .. last) of the plan that go through shared memory.
+// phase 0: first pass (with the caller's loader); phase 1: second pass (3-pass plans);
+// final phase: pass_last.  Returns nothing; the caller inserts barriers between phases.
+template <typename T, int K> struct TilePhases {
+  static constexpr int NP = Plan<K>::NP;  // number of phases of the multi-pass core
+};
+
+template <typename T, int K, int SIGN, class Loader>
+HD void tile_first(cx<T> *sm, const cx<T> *tw, Loader &ld, int tid) {
+  pass_mid<T, K, K, Plan<K>::R1, SIGN>(sm, tw, ld, tid);
+}
+template <typename T, int K, int SIGN>
+HD void tile_second(cx<T> *sm, const cx<T> *tw, int tid) {  // only for 3-pass plans
+  SmemLoader<T, K> ld;
+  ld.sm = sm;
+  pass_mid<T, K, K / Plan<K>::R1, Plan<K>::R2, SIGN>(sm, tw, ld, tid);
+}
+
+}  // namespace cwtb

@@ -1,0 +1,488 @@
+// Kernel bodies of the CWT engine.  Every kernel is a `Body` struct with
+//   Args, NPHASE, SMEM (bytes), and  template<int PH> phase(args, bx, by, tid, smem)
+// Phases are separated by a CTA barrier.  The generic __global__ wrapper lives in
+// engine.cu; tests/emu runs the same phases sequentially on the CPU.
+#pragma once
+#include <math.h>
+#include "fft_tile.cuh"
+
+namespace cwtb {
+
+// ---- per-scale descriptor (host-planned, read by the kernels) -------------------
+struct ScaleDesc {
+  double s;        // scale s_j
+  double amp;      // sqrt(s*w1*Np) * family constant / Np
+  int row;         // output row of W (after NaN-row removal, done by the host)
+  int k_lo, k_hi;  // signed band limits (inclusive) outside which psi_ft is treated as 0
+  int log2K;       // pruned transform length K' = 1 << log2K  (K' == Np: dense)
+  int rsplit;      // residue r >= rsplit  <->  signed bin k = r - K'
+  int trow;        // row in the caller's psi_ft table (CWTB_TABLE family)
+  long long boff;  // offset of this scale's band product B[] in the band buffer
+};
+
+struct Fam {
+  int family;      // 0 Morlet, 1 Paul, 2 DOG, 3 table
+  int m;           // order (Paul, DOG)
+  int unit;        // multiply by i^unit  (conj(-(1j**m)) for DOG)
+  int pad_;
+  double f0;       // Morlet wavenumber
+  double dw;       // 1 / (Np * dt)   (numpy fftfreq's `val`)
+  const double2 *table;  // [S][Np] complex128: sqrt(s*w1*Np)*conj(psi_ft)  (family 3)
+  long long tpitch;
+};
+
+HD double ipow(double f, int m) {
+  double r = 1.0, b = f;
+  int e = m < 0 ? -m : m;
+  while (e) { if (e & 1) r *= b; b *= b; e >>= 1; }
+  return m < 0 ? 1.0 / r : r;
+}
+
+// |conj(psi_ft(s*w_k))| without the family constant; pycwt/mothers.py:26-28,118-122,170-173.
+// w_k is formed as numpy does: 2*pi * (k * (1/(Np*dt))).
+HD double amp_eval(const Fam &fp, double s, int k) {
+  const double w = 6.283185307179586 * ((double)k * fp.dw);
+  const double f = s * w;
+  if (fp.family == 0) {
+    const double d = f - fp.f0;
+    return exp(-0.5 * d * d);
+  } else if (fp.family == 1) {
+    return f > 0.0 ? ipow(f, fp.m) * exp(-f) : 0.0;
+  } else {
+    return ipow(f, fp.m) * exp(-0.5 * f * f);
+  }
+}
+
+template <typename T> HD cx<T> rot_unit(cx<T> v, int unit) {
+  switch (unit & 3) {
+    case 1: return mk<T>(-v.y, v.x);
+    case 2: return mk<T>(-v.x, -v.y);
+    case 3: return mk<T>(v.y, -v.x);
+    default: return v;
+  }
+}
+
+// value of x^[bin] * conj(psi_ft)(s, k) * norm / Np  for one scale
+template <typename T>
+HD cx<T> band_value(const Fam &fp, const ScaleDesc &d, const cx<T> *spec, unsigned bin, int k) {
+  cx<T> v = ldg(&spec[bin]);
+  if (fp.family == 3) {
+    double2 t = ldg(&fp.table[(size_t)d.trow * fp.tpitch + bin]);
+    cx<T> tt = mk<T>((T)(t.x * d.amp), (T)(t.y * d.amp));
+    return cmul(v, tt);
+  }
+  const T a = (T)(amp_eval(fp, d.s, k) * d.amp);
+  return rot_unit<T>(cscale(v, a), fp.unit);
+}
+
+// ---- storers -------------------------------------------------------------------
+// final output: out[row][u + q*U], u = u0 + b, trimmed to n < nout
+template <typename T> struct OutStorer {
+  using V = cx<T>;
+  V *row;          // out + row*pitch
+  long long nout;  // keep n < nout
+  int u0, U;
+  template <int R> HD void store(int b, int ql, int qs, V (&x)[R]) const {
+    const int u = u0 + b;
+    if (u >= U) return;
+#pragma unroll
+    for (int c = 0; c < R; ++c) {
+      long long n = u + (long long)(ql + c * qs) * U;
+      if (n < nout) row[n] = x[c];
+    }
+  }
+};
+
+// first-kernel output: Z[(p + q*M)*K2 + r2] = x_q * e^{SIGN 2 pi i r2 (p+qM)/N}
+template <typename T, int SIGN> struct ZStorer {
+  using V = cx<T>;
+  V *Z;
+  NTab nt;
+  int p, M, r20, bmax;
+  template <int R> HD void store(int b, int ql, int qs, V (&x)[R]) const {
+    if (b >= bmax) return;
+    const unsigned r2 = (unsigned)(r20 + b);
+    const unsigned u = (unsigned)(p + ql * M);
+    const unsigned du = (unsigned)(qs * M);
+    V t = nroot_t<T>(nt, r2 * u);
+    V st = nroot_t<T>(nt, r2 * du);
+    if (SIGN < 0) { t.y = -t.y; st.y = -st.y; }
+    V *dst = Z + (size_t)u * K2C + r2;
+#pragma unroll
+    for (int c = 0; c < R; ++c) {
+      dst[(size_t)c * du * K2C] = cmul(x[c], t);
+      t = cmul(t, st);
+    }
+  }
+};
+
+// ---- Body: single-kernel pruned inverse transform (K' <= 1024) -------------------
+template <typename T> struct SingleArgs {
+  const ScaleDesc *descs;  // device
+  const cx<T> *Bbuf;       // band products
+  cx<T> *W;                // [rows][n0]
+  const cx<T> *tw;         // master twiddle table (KT entries)
+  NTab nt;
+  long long n0;
+  unsigned N;
+  int first;               // descs[first + blockIdx.y]
+};
+
+template <typename T, int K> struct SingleBody {
+  using V = cx<T>;
+  using Args = SingleArgs<T>;
+  using LY = Lay<T, K>;
+  static constexpr int NP = Plan<K>::NP;
+  static_assert(NP >= 2, "single-kernel path needs a multi-pass plan");
+  static constexpr int NPHASE = NP;
+  static constexpr size_t SMEM = LY::BYTES;
+  template <int PH> HD static void phase(const Args &a, int bx, int by, int tid, void *smraw) {
+    V *sm = (V *)smraw;
+    const ScaleDesc d = a.descs[a.first + by];
+    const int M = (int)(a.N / K);
+    const int p0 = bx * LY::P;
+    if (PH == 0) {
+      GenLoader<T, K, Plan<K>::R1> ld;
+      ld.B = a.Bbuf + d.boff;
+      ld.nt = a.nt;
+      ld.rsplit = d.rsplit;
+      ld.p0 = (unsigned)p0;
+      tile_first<T, K, +1>(sm, a.tw, ld, tid);
+    } else if (PH == 1 && NP == 3) {
+      tile_second<T, K, +1>(sm, a.tw, tid);
+    } else {
+      OutStorer<T> st;
+      st.row = a.W + (size_t)d.row * a.n0;
+      st.nout = a.n0;
+      st.u0 = p0;
+      st.U = M;
+      pass_last<T, K, +1>(sm, st, tid);
+    }
+  }
+};
+
+// ---- Body: second kernel of the two-kernel path: K2 = 1024 over r2, rows of Z -------
+template <typename T> struct PassBArgs {
+  const cx<T> *Z;          // [ny][U][K2]
+  cx<T> *out;              // [rows][pitch]
+  const cx<T> *tw;
+  const ScaleDesc *descs;  // may be null: output row = blockIdx.y + row0
+  long long pitch, nout;
+  unsigned N;
+  int first, row0;
+};
+
+template <typename T, int SIGN> struct PassBBody {
+  using V = cx<T>;
+  using Args = PassBArgs<T>;
+  static constexpr int K = K2C;
+  using LY = Lay<T, K>;
+  static constexpr int NP = Plan<K>::NP;
+  static constexpr int NPHASE = NP;
+  static constexpr size_t SMEM = LY::BYTES;
+  template <int PH> HD static void phase(const Args &a, int bx, int by, int tid, void *smraw) {
+    V *sm = (V *)smraw;
+    const int U = (int)(a.N / K);
+    const int u0 = bx * LY::P;
+    if (PH == 0) {
+      RowLoader<T, K> ld;
+      ld.src = a.Z + (size_t)by * a.N + (size_t)u0 * K;
+      ld.nvalid = U - u0;
+      tile_first<T, K, SIGN>(sm, a.tw, ld, tid);
+    } else if (PH == 1 && NP == 3) {
+      tile_second<T, K, SIGN>(sm, a.tw, tid);
+    } else {
+      const int row = a.descs ? a.descs[a.first + by].row : a.row0 + by;
+      OutStorer<T> st;
+      st.row = a.out + (size_t)row * a.pitch;
+      st.nout = a.nout;
+      st.u0 = u0;
+      st.U = U;
+      pass_last<T, K, SIGN>(sm, st, tid);
+    }
+  }
+};
+
+// ---- Body: first kernel of the two-kernel path: K1-point transforms over r1 --------
+enum { MODE_DENSE = 0, MODE_BAND = 1, MODE_REAL = 2, MODE_CPLX = 3 };
+
+template <typename T> struct PassAArgs {
+  const ScaleDesc *descs;
+  const cx<T> *spec;   // x^ (MODE_DENSE)
+  const cx<T> *Bbuf;   // band products (MODE_BAND)
+  const void *in;      // T* (MODE_REAL) or cx<T>* (MODE_CPLX), rows of `in_pitch`
+  cx<T> *Z;            // [ny][U][K2]
+  const cx<T> *tw;
+  Fam fam;
+  NTab nt;
+  long long in_pitch, n_in;
+  unsigned N;
+  int first, row0;
+};
+
+template <typename T, int K1, int MODE, int SIGN> struct PassABody {
+  using V = cx<T>;
+  using Args = PassAArgs<T>;
+  using LY = Lay<T, K1>;
+  static constexpr int NP = Plan<K1>::NP;
+  static constexpr int P = LY::P;
+  static constexpr int T2 = P < K2C ? P : K2C;  // r2 values per tile
+  static constexpr int NTILE2 = K2C / T2;
+  static constexpr int NPHASE = NP == 1 ? 1 : NP + 1;
+  static constexpr size_t SMEM = LY::BYTES;
+
+  struct Src {
+    const Args &a;
+    ScaleDesc d;
+    int by, p;
+    V twist0;
+    HD Src(const Args &a_, int by_, int p_) : a(a_), by(by_), p(p_) {
+      if (MODE == MODE_DENSE || MODE == MODE_BAND) d = a.descs[a.first + by];
+    }
+    // element r = pos*K2 + r2 of the K'-point input
+    HD V get(int pos, int r2) const {
+      const unsigned r = (unsigned)pos * K2C + (unsigned)r2;
+      if (MODE == MODE_DENSE) {
+        const int k = (int)r - (r >= a.N / 2 ? (int)a.N : 0);
+        return band_value<T>(a.fam, d, a.spec, r, k);
+      } else if (MODE == MODE_BAND) {
+        V v = ldg(&a.Bbuf[d.boff + r]);
+        if (p == 0) return v;
+        const int k1 = pos - ((int)r >= d.rsplit ? K1 : 0);
+        // e^{2 pi i k1 p / (K1 M)} = e^{2 pi i (k1 p K2) / N}
+        V w = nroot_t<T>(a.nt, (unsigned)k1 * (unsigned)p * (unsigned)K2C);
+        return cmul(v, w);
+      } else if (MODE == MODE_REAL) {
+        const T *row = (const T *)a.in + (size_t)(a.row0 + by) * a.in_pitch;
+        return mk<T>((long long)r < a.n_in ? ldg(&row[r]) : (T)0, (T)0);
+      } else {
+        const V *row = (const V *)a.in + (size_t)(a.row0 + by) * a.in_pitch;
+        return (long long)r < a.n_in ? ldg(&row[r]) : mk<T>(0, 0);
+      }
+    }
+  };
+
+  template <int PH> HD static void phase(const Args &a, int bx, int by, int tid, void *smraw) {
+    V *sm = (V *)smraw;
+    const int p = bx / NTILE2;
+    const int r20 = (bx % NTILE2) * T2;
+    const int M = (int)(a.N / ((unsigned)K1 * K2C));
+    ZStorer<T, SIGN> st;
+    st.Z = a.Z + (size_t)by * a.N;
+    st.nt = a.nt;
+    st.p = p;
+    st.M = M;
+    st.r20 = r20;
+    st.bmax = T2;
+    if (NP == 1) {
+      Src src(a, by, p);
+      for (int b = tid; b < T2; b += NT) {
+        V x[K1];
+#pragma unroll
+        for (int i = 0; i < K1; ++i) x[i] = src.get(i, r20 + b);
+        dftR<K1, SIGN, T>(x);
+        st.store(b, 0, 1, x);
+      }
+    } else if (PH == 0) {
+      Src src(a, by, p);
+      for (int idx = tid; idx < K1 * T2; idx += NT) {
+        const int b = idx % T2, pos = idx / T2;
+        sm[LY::phys(b, pos)] = src.get(pos, r20 + b);
+      }
+    } else if (PH == 1) {
+      SmemLoader<T, K1> ld;
+      ld.sm = sm;
+      tile_first<T, K1, SIGN>(sm, a.tw, ld, tid);
+    } else if (PH == 2 && NP == 3) {
+      tile_second<T, K1, SIGN>(sm, a.tw, tid);
+    } else {
+      pass_last<T, K1, SIGN>(sm, st, tid);
+    }
+  }
+};
+
+// ---- Body: band product B[r] = x^[k] * conj(psi_ft) * norm / Np for pruned scales ------
+template <typename T> struct BandArgs {
+  const ScaleDesc *descs;
+  const cx<T> *spec;
+  cx<T> *Bbuf;
+  Fam fam;
+  unsigned N;
+  int first;
+};
+template <typename T> struct BandBody {
+  using V = cx<T>;
+  using Args = BandArgs<T>;
+  static constexpr int NPHASE = 1;
+  static constexpr size_t SMEM = 0;
+  static constexpr int PER = 4;
+  template <int PH> HD static void phase(const Args &a, int bx, int by, int tid, void *) {
+    const ScaleDesc d = a.descs[a.first + by];
+    const int K = 1 << d.log2K;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int r = (bx * PER + i) * NT + tid;
+      if (r >= K) return;
+      const int k = r - (r >= d.rsplit ? K : 0);
+      V v = mk<T>(0, 0);
+      if (k >= d.k_lo && k <= d.k_hi) v = band_value<T>(a.fam, d, a.spec, (unsigned)k & (a.N - 1), k);
+      a.Bbuf[d.boff + r] = v;
+    }
+  }
+};
+
+// ---- Body: batched K-point FFT over matrix rows (N <= 1024): forward FFT of short
+// signals, the c2c test hook, the Gaussian smoothing transforms ----------------------
+template <typename T> struct RowsArgs {
+  const void *in;      // T* if real_in else cx<T>*
+  cx<T> *out;
+  const cx<T> *tw;
+  const T *mul;        // optional per-(row, q) real multiplier applied to the OUTPUT (may be null)
+  long long in_pitch, out_pitch, n_in, mul_pitch;
+  int nrows, real_in;
+};
+
+template <typename T, int K> struct RowsLoader {
+  using V = cx<T>;
+  const RowsArgs<T> *a;
+  int row0;
+  int base, stride;
+  HD void begin(int base_, int stride_, int, int) { base = base_; stride = stride_; }
+  HD V get(int b, int pos) const {
+    const int row = row0 + b;
+    if (row >= a->nrows || pos >= a->n_in) return mk<T>(0, 0);
+    if (a->real_in) return mk<T>(ldg((const T *)a->in + (size_t)row * a->in_pitch + pos), (T)0);
+    return ldg((const V *)a->in + (size_t)row * a->in_pitch + pos);
+  }
+  template <int R> HD void load(int b, V (&x)[R]) const {
+#pragma unroll
+    for (int i = 0; i < R; ++i) x[i] = get(b, base + i * stride);
+  }
+};
+template <typename T> struct RowsStorer {
+  using V = cx<T>;
+  const RowsArgs<T> *a;
+  int row0;
+  template <int R> HD void store(int b, int ql, int qs, V (&x)[R]) const {
+    const int row = row0 + b;
+    if (row >= a->nrows) return;
+#pragma unroll
+    for (int c = 0; c < R; ++c) {
+      const int q = ql + c * qs;
+      V v = x[c];
+      if (a->mul) v = cscale(v, ldg(&a->mul[(size_t)row * a->mul_pitch + q]));
+      a->out[(size_t)row * a->out_pitch + q] = v;
+    }
+  }
+};
+template <typename T, int K, int SIGN> struct RowsBody {
+  using V = cx<T>;
+  using Args = RowsArgs<T>;
+  using LY = Lay<T, K>;
+  static constexpr int NP = Plan<K>::NP;
+  static constexpr int NPHASE = NP;
+  static constexpr size_t SMEM = LY::BYTES;
+  template <int PH> HD static void phase(const Args &a, int bx, int, int tid, void *smraw) {
+    V *sm = (V *)smraw;
+    const int row0 = bx * LY::P;
+    RowsStorer<T> st;
+    st.a = &a;
+    st.row0 = row0;
+    RowsLoader<T, K> ld;
+    ld.a = &a;
+    ld.row0 = row0;
+    if (NP == 1) {
+      for (int b = tid; b < LY::P; b += NT) {
+        V x[K];
+#pragma unroll
+        for (int i = 0; i < K; ++i) x[i] = ld.get(b, i);
+        dftR<K, SIGN, T>(x);
+        st.store(b, 0, 1, x);
+      }
+    } else if (PH == 0) {
+      tile_first<T, K, SIGN>(sm, a.tw, ld, tid);
+    } else if (PH == 1 && NP == 3) {
+      tile_second<T, K, SIGN>(sm, a.tw, tid);
+    } else {
+      pass_last<T, K, SIGN>(sm, st, tid);
+    }
+  }
+};
+
+// ---- Body: direct O(N^2) transform for tiny padded lengths (Np < 32) ---------------
+template <typename T> struct TinyArgs {
+  const ScaleDesc *descs;
+  const cx<T> *spec;
+  cx<T> *W;
+  Fam fam;
+  long long n0;
+  unsigned N;
+  int first;
+};
+template <typename T> struct TinyBody {
+  using V = cx<T>;
+  using Args = TinyArgs<T>;
+  static constexpr int NPHASE = 1;
+  static constexpr size_t SMEM = 0;
+  template <int PH> HD static void phase(const Args &a, int bx, int by, int tid, void *) {
+    const ScaleDesc d = a.descs[a.first + by];
+    const int n = bx * NT + tid;
+    if (n >= a.n0) return;
+    double sr = 0, si = 0;
+    for (unsigned r = 0; r < a.N; ++r) {
+      const int k = (int)r - (r >= a.N / 2 && a.N > 1 ? (int)a.N : 0);
+      V v = band_value<T>(a.fam, d, a.spec, r, k);
+      double sn, cs;
+      sincospi_hd(2.0 * (double)((r * (unsigned)n) % a.N) / (double)a.N, &sn, &cs);
+      sr += (double)v.x * cs - (double)v.y * sn;
+      si += (double)v.x * sn + (double)v.y * cs;
+    }
+    a.W[(size_t)d.row * a.n0 + n] = mk<T>((T)sr, (T)si);
+  }
+};
+// forward DFT of a tiny real signal
+template <typename T> struct TinyFwdArgs {
+  const T *sig;
+  cx<T> *spec;
+  long long n0;
+  unsigned N;
+};
+template <typename T> struct TinyFwdBody {
+  using Args = TinyFwdArgs<T>;
+  static constexpr int NPHASE = 1;
+  static constexpr size_t SMEM = 0;
+  template <int PH> HD static void phase(const Args &a, int, int, int tid, void *) {
+    if ((unsigned)tid >= a.N) return;
+    double sr = 0, si = 0;
+    for (unsigned n = 0; n < a.N && (long long)n < a.n0; ++n) {
+      double sn, cs;
+      sincospi_hd(2.0 * (double)(((unsigned)tid * n) % a.N) / (double)a.N, &sn, &cs);
+      sr += (double)a.sig[n] * cs;
+      si -= (double)a.sig[n] * sn;
+    }
+    a.spec[tid] = mk<T>((T)sr, (T)si);
+  }
+};
+
+// ---- Body: twiddle tables ---------------------------------------------------------
+struct TabArgs {
+  double2 *out64;
+  float2 *out32;
+  unsigned count;
+  double step;  // entry i = e^{2 pi i * i * step}
+};
+struct TabBody {
+  using Args = TabArgs;
+  static constexpr int NPHASE = 1;
+  static constexpr size_t SMEM = 0;
+  template <int PH> HD static void phase(const Args &a, int bx, int, int tid, void *) {
+    const unsigned i = (unsigned)bx * NT + tid;
+    if (i >= a.count) return;
+    double sn, cs;
+    sincospi_hd(2.0 * ((double)i * a.step), &sn, &cs);
+    if (a.out64) a.out64[i] = make_double2(cs, sn);
+    if (a.out32) a.out32[i] = make_float2((float)cs, (float)sn);
+  }
+};
+
+}  // namespace cwtb
