@@ -1,0 +1,223 @@
+"""ctypes binding of the C-ABI engine (include/cwt_b200.h).  No PyTorch, no CPU
+fallback: if the CUDA library or a device is missing, calls raise EngineError."""
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcwtb200.so")
+
+MORLET, PAUL, DOG, TABLE = 0, 1, 2, 3
+F64, F32 = 0, 1
+
+_P = ctypes.c_void_p
+_I64 = ctypes.c_int64
+_D = ctypes.c_double
+_I = ctypes.c_int
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+_SIGNATURES = {
+    "cwtb_device_count": (_I, []),
+    "cwtb_create": (_I, [_I, ctypes.POINTER(_P)]),
+    "cwtb_destroy": (None, [_P]),
+    "cwtb_last_error": (ctypes.c_char_p, [_P]),
+    "cwtb_version": (ctypes.c_char_p, []),
+    "cwtb_set_band_eps": (_I, [_P, _D]),
+    "cwtb_host_alloc": (_I, [_P, ctypes.c_size_t, ctypes.POINTER(_P)]),
+    "cwtb_host_free": (_I, [_P, _P]),
+    "cwtb_cwt": (_I, [_P, _P, _I, _I64, _D, _P, _I, _I, _D, _I, _P]),
+    "cwtb_cwt_dev": (_I, [_P, _P, _I, _I64, _D, _P, _I, _I, _D, _I]),
+    "cwtb_get_w": (_I, [_P, _P, _I, _I, _I]),
+    "cwtb_get_signal_fft": (_I, [_P, _P]),
+    "cwtb_padded_length": (_I64, [_P]),
+    "cwtb_w_device_ptr": (_P, [_P]),
+    "cwtb_last_kernel_ms": (_D, [_P]),
+    "cwtb_last_launch_count": (_I, [_P]),
+    "cwtb_last_plan": (_I, [_P, _P, _I]),
+    "cwtb_bench_last": (_I, [_P, _I, ctypes.POINTER(_D)]),
+    "cwtb_dev_alloc": (_I, [_P, ctypes.c_size_t, ctypes.POINTER(_P)]),
+    "cwtb_dev_free": (_I, [_P, _P]),
+    "cwtb_memcpy_h2d": (_I, [_P, _P, _P, ctypes.c_size_t]),
+    "cwtb_memcpy_d2h": (_I, [_P, _P, _P, ctypes.c_size_t]),
+    "cwtb_sync": (_I, [_P]),
+    "cwtb_fft_c2c": (_I, [_P, _P, _P, _I64, _I, _I, _I]),
+}
+
+
+def load_library(path=None):
+    """dlopen the engine and declare the prototypes of every exported symbol."""
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise EngineError(
+            "CUDA engine not built: %s is missing (run `python -m pycwt_b200.build`)" % path)
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_P)
+
+
+class Engine(object):
+    """One context = one device + one stream.  Calls are serialised by a lock."""
+
+    def __init__(self, device=0, lib_path=None):
+        self.lib = load_library(lib_path)
+        if self.lib.cwtb_device_count() <= 0:
+            raise EngineError("no CUDA device visible: the B200 engine has no CPU fallback")
+        h = _P()
+        rc = self.lib.cwtb_create(int(device), ctypes.byref(h))
+        if rc != 0:
+            raise EngineError("cwtb_create(device=%d) failed with status %d" % (device, rc))
+        self.h = h
+        self.device = device
+        self.lock = threading.Lock()
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cwtb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = self.lib.cwtb_last_error(self.h)
+            raise EngineError("engine status %d: %s" % (rc, (msg or b"").decode()))
+
+    def version(self):
+        return self.lib.cwtb_version().decode()
+
+    def set_band_eps(self, eps):
+        self._check(self.lib.cwtb_set_band_eps(self.h, float(eps)))
+
+    # ---- pinned host arrays -------------------------------------------------------
+    def pinned_empty(self, shape, dtype):
+        """numpy array backed by page-locked memory owned by the engine context."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        p = _P()
+        self._check(self.lib.cwtb_host_alloc(self.h, max(n, 1), ctypes.byref(p)))
+        buf = (ctypes.c_char * max(n, 1)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        return arr, p
+
+    def pinned_free(self, p):
+        self.lib.cwtb_host_free(self.h, p)
+
+    # ---- transform ------------------------------------------------------------------
+    def cwt(self, signal, dt, scales, family, param, precision=F64, table=None,
+            fetch=True, out_f64=True):
+        sig = np.ascontiguousarray(signal)
+        if sig.dtype == np.float32:
+            is32 = 1
+        else:
+            sig = np.ascontiguousarray(sig, dtype=np.float64)
+            is32 = 0
+        sj = np.ascontiguousarray(scales, dtype=np.float64)
+        tptr = None
+        if table is not None:
+            table = np.ascontiguousarray(table, dtype=np.complex128)
+            tptr = _ptr(table)
+        with self.lock:
+            self._check(self.lib.cwtb_cwt(self.h, _ptr(sig), is32, sig.size, float(dt),
+                                          _ptr(sj), sj.size, int(family), float(param),
+                                          int(precision), tptr))
+            if not fetch:
+                return None
+            return self.get_w(sj.size, sig.size, precision, out_f64)
+
+    def get_w(self, nrows, n0, precision=F64, out_f64=True):
+        dtype = np.complex128 if (precision == F64 or out_f64) else np.complex64
+        W = np.empty((nrows, n0), dtype=dtype)
+        self._check(self.lib.cwtb_get_w(self.h, _ptr(W), 1 if out_f64 else 0, 0, nrows))
+        return W
+
+    def signal_fft(self):
+        npad = int(self.lib.cwtb_padded_length(self.h))
+        out = np.empty(max(npad // 2 - 1, 0), dtype=np.complex128)
+        if out.size:
+            self._check(self.lib.cwtb_get_signal_fft(self.h, _ptr(out)))
+        return out
+
+    def padded_length(self):
+        return int(self.lib.cwtb_padded_length(self.h))
+
+    def last_plan(self, n):
+        out = (ctypes.c_int * n)()
+        m = self.lib.cwtb_last_plan(self.h, out, n)
+        return list(out)[:max(m, 0)]
+
+    def last_kernel_ms(self):
+        return float(self.lib.cwtb_last_kernel_ms(self.h))
+
+    def last_launch_count(self):
+        return int(self.lib.cwtb_last_launch_count(self.h))
+
+    def fft_c2c(self, x, sign, precision=F64):
+        x = np.ascontiguousarray(x, dtype=np.complex128)
+        if x.ndim == 1:
+            x = x[None, :]
+        out = np.empty_like(x)
+        self._check(self.lib.cwtb_fft_c2c(self.h, _ptr(x), _ptr(out), x.shape[1],
+                                          x.shape[0], int(sign), int(precision)))
+        return out
+
+    # ---- device-resident benchmarking helpers -------------------------------------
+    def dev_alloc(self, nbytes):
+        p = _P()
+        self._check(self.lib.cwtb_dev_alloc(self.h, nbytes, ctypes.byref(p)))
+        return p
+
+    def dev_free(self, p):
+        self.lib.cwtb_dev_free(self.h, p)
+
+    def h2d(self, dptr, arr):
+        arr = np.ascontiguousarray(arr)
+        self._check(self.lib.cwtb_memcpy_h2d(self.h, dptr, _ptr(arr), arr.nbytes))
+
+    def cwt_dev(self, dptr, is_f32, n0, dt, scales, family, param, precision=F64):
+        sj = np.ascontiguousarray(scales, dtype=np.float64)
+        self._check(self.lib.cwtb_cwt_dev(self.h, dptr, int(is_f32), int(n0), float(dt),
+                                          _ptr(sj), sj.size, int(family), float(param),
+                                          int(precision)))
+
+    def bench_last(self, iters):
+        ms = _D()
+        self._check(self.lib.cwtb_bench_last(self.h, int(iters), ctypes.byref(ms)))
+        return ms.value
+
+    def sync(self):
+        self._check(self.lib.cwtb_sync(self.h))
+
+
+_default = {}
+_default_lock = threading.Lock()
+
+
+def device_count():
+    return int(load_library().cwtb_device_count())
+
+
+def default_engine(device=None):
+    """Process-wide engine per device (device from CWTB_DEVICE / LOCAL_RANK, default 0)."""
+    if device is None:
+        device = int(os.environ.get("CWTB_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    with _default_lock:
+        if device not in _default:
+            _default[device] = Engine(device)
+        return _default[device]

@@ -302,7 +302,9 @@ static int build_job(cwtb_ctx *c, Job &job, long long n0, double dt, const doubl
     static const int unit_of[4] = {2, 1, 0, 3};
     fam.unit = unit_of[m & 3];
   }
-  const double w1 = 6.283185307179586 * (1.0 * fam.dw);  // ftfreqs[1]
+  // ftfreqs[1]; for Np == 2 numpy's fftfreq(2)[1] is -0.5/dt, so the reference's
+  // normalisation sqrt(s*w1*Np) is NaN there -- reproduced.
+  const double w1 = 6.283185307179586 * ((N == 2 ? -1.0 : 1.0) * fam.dw);
   double flo = 0, fhi = 0;
   bool pos_only = false;
   if (family != CWTB_TABLE) family_band(family, param, c->band_eps, &flo, &fhi, &pos_only);

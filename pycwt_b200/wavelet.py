@@ -1,0 +1,374 @@
+"""Continuous wavelet transform API with the signatures of pycwt/wavelet.py, executed by
+the B200 CUDA engine (pycwt_b200/csrc, C ABI in include/cwt_b200.h).
+
+Division of labour:
+  * O(S) scalar work -- scale resolution, cone of influence, chi-square significance,
+    NaN-row bookkeeping -- stays in NumPy on the host, written so that `sj`, `freqs` and
+    `coi` are bit-identical to the reference's;
+  * everything that touches an [S, N] array -- forward FFT, analytic wavelet response,
+    per-scale inverse transforms, cross products, smoothing, coherence, Monte-Carlo
+    histograms, the icwt reduction -- runs on the GPU.
+There is no CPU fallback: without the CUDA library or a device, calls raise EngineError.
+"""
+import os
+
+import numpy as np
+from scipy.stats import chi2
+from tqdm import tqdm
+
+from . import _engine
+from .helpers import (ar1, ar1_spectrum, fft, fft_kwargs, find, get_cache_dir,
+                      rednoise)
+from .mothers import Morlet, Paul, DOG, MexicanHat
+
+_PRECISIONS = {'fp64': _engine.F64, 'f64': _engine.F64, 'float64': _engine.F64,
+               'fp32': _engine.F32, 'f32': _engine.F32, 'float32': _engine.F32}
+
+
+def _precision():
+    """Arithmetic of the engine: fp64 (default, matches the reference) or fp32 via the
+    CWTB_PRECISION environment variable."""
+    return _PRECISIONS[os.environ.get('CWTB_PRECISION', 'fp64').lower()]
+
+
+def _resolve_scales(n0, dt, dj, s0, J, wavelet, freqs):
+    """Scale vector exactly as the reference builds it (wavelet.py:75-88)."""
+    if freqs is None:
+        if s0 == -1:
+            s0 = 2 * dt / wavelet.flambda()
+        if J == -1:
+            J = int(np.round(np.log2(n0 * dt / s0) / dj))
+        sj = s0 * 2 ** (np.arange(0, J + 1) * dj)
+        freqs = 1 / (wavelet.flambda() * sj)
+    else:
+        sj = 1 / (wavelet.flambda() * freqs)
+    return sj, freqs
+
+
+def _nan_rows(wavelet, sj, npad, dt):
+    """Rows the reference would find all-NaN (wavelet.py:111): psi_ft evaluates to NaN at
+    some bin (Paul: inf*0 once s*pi/dt > 709.78).  Evaluated at the two extreme bins, where
+    overflow happens first; O(S) host work."""
+    edge = 2 * np.pi * fft.fftfreq(npad, dt)[[npad // 2, max(npad // 2 - 1, 0)]]
+    with np.errstate(all='ignore'):
+        resp = wavelet.psi_ft(sj[:, None] * edge[None, :])
+    return np.isnan(resp).any(axis=1)
+
+
+def _transform(signal, dt, sj, wavelet, precision=None, engine=None):
+    """W[S, n0] (complex128) for the given scales; rows are NOT yet NaN-filtered."""
+    eng = engine or _engine.default_engine()
+    precision = _precision() if precision is None else precision
+    spec = wavelet._engine_spec() if hasattr(wavelet, '_engine_spec') else None
+    sig = np.asarray(signal)
+    if sig.dtype != np.float32:
+        sig = np.asarray(sig, dtype=np.float64)
+    if spec is not None:
+        family, param = spec
+        W = eng.cwt(sig, dt, sj, family, param, precision)
+    else:
+        # duck-typed wavelet: the host evaluates psi_ft on the [S, Np] grid exactly as
+        # wavelet.py:102-104 does; the device multiplies and inverse-transforms.
+        npad = fft_kwargs(sig)['n']
+        ftfreqs = 2 * np.pi * fft.fftfreq(npad, dt)
+        col = np.asarray(sj)[:, np.newaxis]
+        table = ((col * ftfreqs[1] * npad) ** .5 *
+                 np.conjugate(wavelet.psi_ft(col * ftfreqs))).astype(np.complex128)
+        W = eng.cwt(sig, dt, sj, _engine.TABLE, 0.0, precision, table=table)
+    return W, eng
+
+
+def cwt(signal, dt, dj=1/12, s0=-1, J=-1, wavelet='morlet', freqs=None):
+    """Continuous wavelet transform of `signal` (reference wavelet.py:13-124).
+
+    Returns (W, sj, freqs, coi, fft, fftfreqs) exactly like the reference: W is
+    complex128 of shape (len(sj), len(signal)); scales whose transform is all-NaN
+    (Paul at very large scales) are removed from W, sj and freqs."""
+    wavelet = _check_parameter_wavelet(wavelet)
+    n0 = len(signal)
+    sj, freqs = _resolve_scales(n0, dt, dj, s0, J, wavelet, freqs)
+    npad = fft_kwargs(signal)['n']
+
+    bad = _nan_rows(wavelet, np.asarray(sj, dtype=float), npad, dt)
+    keep = ~bad
+    if keep.any():
+        W, eng = _transform(signal, dt, np.asarray(sj)[keep], wavelet)
+        sj, freqs = sj[keep], freqs[keep]
+    else:
+        # every row NaN: the reference keeps them all (np.any(sel) is False)
+        _, eng = _transform(signal, dt, np.asarray(sj)[:1], wavelet)
+        W = np.full((len(sj), n0), np.nan + 1j * np.nan)
+
+    coi = (n0 / 2 - np.abs(np.arange(0, n0) - (n0 - 1) / 2))
+    coi = wavelet.flambda() * wavelet.coi() * dt * coi
+    ftfreqs = 2 * np.pi * fft.fftfreq(npad, dt)
+    return (W, sj, freqs, coi, eng.signal_fft(), ftfreqs[1:npad // 2] / (2 * np.pi))
+
+
+def icwt(W, sj, dt, dj=1/12, wavelet='morlet'):
+    """Inverse continuous wavelet transform (reference wavelet.py:127-171).
+
+    The sum over scales of Re(W)/sqrt(s) runs on the GPU; W may be (S, N) or (N, S)
+    as in the reference (which always reduces axis 0)."""
+    wavelet = _check_parameter_wavelet(wavelet)
+    W = np.asarray(W)
+    sj = np.asarray(sj, dtype=float)
+    a, b = W.shape
+    c = sj.size
+    if a == c:
+        red = _engine.default_engine().icwt_sum(W, sj)
+    elif b == c:
+        # scales vary along axis 1 but the reference still sums axis 0
+        red = _engine.default_engine().icwt_sum(W / np.sqrt(sj)[None, :], np.ones(a))
+    else:
+        raise Warning('Input array dimensions do not match.')
+    return dj * np.sqrt(dt) / (wavelet.cdelta * wavelet.psi(0)) * red
+
+
+def significance(signal, dt, scales, sigma_test=0, alpha=None,
+                 significance_level=0.95, dof=-1, wavelet='morlet'):
+    """Chi-square significance levels of the wavelet power spectrum against a red-noise
+    background (reference wavelet.py:174-313; Torrence & Compo 1998 sec. 4-5).
+    O(S) host arithmetic."""
+    wavelet = _check_parameter_wavelet(wavelet)
+    try:
+        n0 = len(signal)
+    except TypeError:
+        n0 = 1
+    scales = np.asarray(scales)
+    J = len(scales) - 1
+    dj = np.log2(scales[1] / scales[0])
+    variance = signal if n0 == 1 else signal.std() ** 2
+    if alpha is None:
+        alpha, _, _ = ar1(signal)
+
+    period = scales * wavelet.flambda()
+    freq = dt / period
+    dofmin = wavelet.dofmin
+    # discrete red-noise spectrum, TC98 eq. 16 (evaluated at k/N = freq, N = n0)
+    k_over = 2 * np.pi * freq / n0
+    fft_theor = variance * (1 - alpha ** 2) / (1 + alpha ** 2 - 2 * alpha * np.cos(k_over))
+    signif = fft_theor
+    try:
+        if dof == -1:
+            dof = dofmin
+    except ValueError:
+        pass
+
+    if sigma_test == 0:  # TC98 eq. 18
+        dof = dofmin
+        signif = fft_theor * (chi2.ppf(significance_level, dof) / dof)
+    elif sigma_test == 1:  # time-averaged, TC98 eq. 23
+        if len(dof) == 1:
+            dof = np.zeros(1, J + 1) + dof  # TypeError as in the reference
+        dof[find(dof < 1)] = 1
+        dof = dofmin * (1 + (dof * dt / wavelet.gamma / scales) ** 2) ** 0.5
+        dof[find(dof < dofmin)] = dofmin
+        for n, d in enumerate(dof):
+            signif[n] = fft_theor[n] * (chi2.ppf(significance_level, d) / d)
+    elif sigma_test == 2:  # scale-averaged, TC98 eq. 25-28
+        if len(dof) != 2:
+            raise Exception('DOF must be set to [s1, s2], '
+                            'the range of scale-averages')
+        if wavelet.cdelta == -1:
+            raise ValueError('Cdelta and dj0 not defined '
+                             'for {} with f0={}'.format(wavelet.name, wavelet.f0))
+        s1, s2 = dof
+        sel = find((scales >= s1) & (scales <= s2))
+        navg = sel.size
+        if navg == 0:
+            raise ValueError('No valid scales between {} and {}.'.format(s1, s2))
+        Savg = 1 / sum(1. / scales[sel])
+        Smid = np.exp((np.log(s1) + np.log(s2)) / 2.)
+        dof = (dofmin * navg * Savg / Smid) * ((1 + (navg * dj / wavelet.deltaj0) ** 2) ** 0.5)
+        fft_theor = Savg * sum(fft_theor[sel] / scales[sel])
+        chisquare = chi2.ppf(significance_level, dof) / dof
+        signif = (dj * dt / wavelet.cdelta / Savg) * fft_theor * chisquare
+    else:
+        raise ValueError('sigma_test must be either 0, 1, or 2.')
+    return signif, fft_theor
+
+
+def _standardise(y, normalize):
+    y = np.asarray(y)
+    std = y.std()
+    return y, ((y - y.mean()) / std if normalize else y), std
+
+
+def xwt(y1, y2, dt, dj=1/12, s0=-1, J=-1, significance_level=0.95,
+        wavelet='morlet', normalize=True):
+    """Cross wavelet transform W1 * conj(W2) (reference wavelet.py:316-419).
+
+    Both transforms and the conjugate product (fused into the second transform's output
+    pass) run on the GPU.  Returns (W12, coi, freq, signif)."""
+    wavelet = _check_parameter_wavelet(wavelet)
+    y1, y1n, std1 = _standardise(y1, normalize)
+    y2, y2n, std2 = _standardise(y2, normalize)
+    n0 = len(y1n)
+    sj, freq = _resolve_scales(n0, dt, dj, s0, J, wavelet, None)
+    npad = fft_kwargs(y1n)['n']
+    keep = ~_nan_rows(wavelet, sj, npad, dt)
+    if not keep.any():
+        keep[:] = True
+    sj, freq = sj[keep], freq[keep]
+    W12 = _pair_engine(wavelet).xwt(y1n, y2n, dt, sj, *_family_of(wavelet))
+    coi = (n0 / 2 - np.abs(np.arange(0, n0) - (n0 - 1) / 2))
+    coi = wavelet.flambda() * wavelet.coi() * dt * coi
+
+    if normalize:
+        std1 = std2 = 1.
+    a1, _, _ = ar1(y1)
+    a2, _, _ = ar1(y2)
+    Pk1 = ar1_spectrum(freq * dt, a1)
+    Pk2 = ar1_spectrum(freq * dt, a2)
+    dof = wavelet.dofmin
+    PPF = chi2.ppf(significance_level, dof)
+    signif = (std1 * std2 * (Pk1 * Pk2) ** 0.5 * PPF / dof)
+    return W12, coi, freq, signif
+
+
+def _family_of(wavelet):
+    spec = wavelet._engine_spec() if hasattr(wavelet, '_engine_spec') else None
+    if spec is None:
+        raise NotImplementedError(
+            'xwt/wct on the GPU need a Morlet, Paul or DOG mother wavelet')
+    return spec
+
+
+def _pair_engine(wavelet):
+    return _engine.default_engine()
+
+
+def _boxcar_len(wavelet, dj):
+    """Number of taps of the scale-axis boxcar, int(round(2*deltaj0/dj)) (mothers.py:100)."""
+    return int(np.round(wavelet.deltaj0 / dj * 2))
+
+
+def wct(y1, y2, dt, dj=1/12, s0=-1, J=-1, sig=True,
+        significance_level=0.95, wavelet='morlet', normalize=True, **kwargs):
+    """Wavelet coherence (reference wavelet.py:422-528).
+
+    Returns (WCT, aWCT, coi, freq, sig).  The two transforms, the |W|^2/s and W12/s
+    products, the Gaussian time smoothing, the scale boxcar and the coherence ratio run
+    on the GPU; `sig` comes from wct_significance (GPU Monte-Carlo) when sig=True."""
+    wavelet = _check_parameter_wavelet(wavelet)
+    if not hasattr(wavelet, 'smooth'):
+        # same failure mode as the reference for Paul / DOG (no smoothing operator)
+        raise AttributeError("'{}' object has no attribute 'smooth'".format(
+            type(wavelet).__name__))
+    if s0 == -1:
+        s0 = 2 * dt / wavelet.flambda()
+    if J == -1:
+        J = int(np.round(np.log2(y1.size * dt / s0) / dj))  # y1.size: ndarray required, as in the reference
+    y1, y1n, _ = _standardise(y1, normalize)
+    y2, y2n, _ = _standardise(y2, normalize)
+    n0 = y1n.size
+    sj, freq = _resolve_scales(n0, dt, dj, s0, J, wavelet, None)
+    WCT, aWCT = _pair_engine(wavelet).wct(y1n, y2n, dt, dj, sj, *_family_of(wavelet),
+                                          boxcar_len=_boxcar_len(wavelet, dj))
+    coi = (n0 / 2 - np.abs(np.arange(0, n0) - (n0 - 1) / 2))
+    coi = wavelet.flambda() * wavelet.coi() * dt * coi
+    if sig:
+        a1, b1, c1 = ar1(y1)
+        a2, b2, c2 = ar1(y2)
+        sig = wct_significance(a1, a2, dt=dt, dj=dj, s0=s0, J=J,
+                               significance_level=significance_level,
+                               wavelet=wavelet, **kwargs)
+    else:
+        sig = np.asarray([0])
+    return WCT, aWCT, coi, freq, sig
+
+
+def wct_significance(al1, al2, dt, dj, s0, J, significance_level=0.95,
+                     wavelet='morlet', mc_count=300, progress=True,
+                     cache=True):
+    """Monte-Carlo significance level of the wavelet coherence per scale (reference
+    wavelet.py:531-647).
+
+    Surrogates are drawn on the host with numpy's global RNG in exactly the reference's
+    order (one set-up draw, then noise1, noise2 per iteration), so a seeded run
+    reproduces the reference's numbers; transforms, smoothing, coherence and the
+    1000-bin histograms are accumulated on the GPU.  The on-disk cache keeps the
+    reference's key and format (~/.cache/pycwt/<key>.gz)."""
+    wavelet = _check_parameter_wavelet(wavelet)
+    if cache:
+        aa = np.round(np.arctanh(np.array([al1, al2]) * 4))
+        aa = np.abs(aa) + 0.5 * (aa < 0)
+        cache_file = 'wct_sig_{:0.5f}_{:0.5f}_{:0.5f}_{:0.5f}_{:d}_{}'\
+            .format(aa[0], aa[1], dj, s0 / dt, J, wavelet.name)
+        cache_dir = get_cache_dir()
+        try:
+            dat = np.loadtxt('{}/{}.gz'.format(cache_dir, cache_file), unpack=True)
+            print('NOTE: WCT significance loaded from cache.\n')
+            return dat
+        except IOError:
+            pass
+    print('Calculating wavelet coherence significance')
+
+    ms = s0 * (2 ** (J * dj)) / dt
+    N = int(np.ceil(ms * 6))
+    rednoise(N, al1, 1)  # the reference's set-up draw (its transform only yields sj/freq/coi)
+    sj = s0 * 2 ** (np.arange(0, J + 1) * dj)
+    freq = 1 / (wavelet.flambda() * sj)
+    coi = (N / 2 - np.abs(np.arange(0, N) - (N - 1) / 2))
+    coi = wavelet.flambda() * wavelet.coi() * dt * coi
+
+    period = np.ones([1, N]) / freq[:, None]
+    outsidecoi = (period <= (np.ones([J + 1, 1]) * coi[None, :]))
+    sig95 = np.zeros(J + 1)
+    maxscale = find(outsidecoi.any(axis=1))[-1]
+    sig95[outsidecoi.any(axis=1)] = np.nan
+
+    nbins = 1000
+    hist = np.zeros((J + 1, nbins), dtype=np.int64)
+    eng = _pair_engine(wavelet)
+    fam = _family_of(wavelet)
+    mask = np.ascontiguousarray(outsidecoi, dtype=np.uint8)
+    batch = max(1, min(mc_count, int((256 << 20) // (16 * N)) or 1))
+    done = 0
+    bar = tqdm(total=mc_count, disable=not progress)
+    while done < mc_count:
+        nb = min(batch, mc_count - done)
+        noise = np.empty((nb, 2, N))
+        for i in range(nb):
+            noise[i, 0] = rednoise(N, al1, 1)
+            noise[i, 1] = rednoise(N, al2, 1)
+        eng.wct_mc(noise, dt, dj, sj, fam[0], fam[1], _boxcar_len(wavelet, dj), mask,
+                   int(maxscale), nbins, hist)
+        done += nb
+        bar.update(nb)
+    bar.close()
+
+    R2y = (np.arange(nbins) + 0.5) / nbins
+    for s in range(maxscale):
+        sel = hist[s] != 0
+        P = hist[s, sel].astype(float).cumsum()
+        P = (P - 0.5) / P[-1]
+        sig95[s] = np.interp(significance_level, P, R2y[sel])
+
+    if cache:
+        np.savetxt('{}/{}.gz'.format(cache_dir, cache_file), sig95)
+    return sig95
+
+
+def _smooth_device(W, dt, dj, scales, deltaj0):
+    """Morlet.smooth on the GPU (reference mothers.py:61-104)."""
+    W = np.asarray(W)
+    scales = np.asarray(scales, dtype=float)
+    klen = int(np.round(deltaj0 / dj * 2))
+    if klen < 1:
+        # deltaj0 = -1 (f0 != 6): the reference fails inside rect()
+        raise ValueError('smoothing window undefined for this wavelet (deltaj0 = -1)')
+    eng = _engine.default_engine()
+    if np.isreal(W).all():
+        return eng.smooth(np.ascontiguousarray(W.real, dtype=np.float64), dt, scales, klen)
+    return eng.smooth(np.ascontiguousarray(W, dtype=np.complex128), dt, scales, klen)
+
+
+def _check_parameter_wavelet(wavelet):
+    """Strings map to default-constructed mother wavelets, anything else is returned as
+    is (reference wavelet.py:650-663); unknown names raise KeyError."""
+    mothers = {'morlet': Morlet, 'paul': Paul, 'dog': DOG, 'mexicanhat': MexicanHat}
+    if isinstance(wavelet, str):
+        return mothers[wavelet]()
+    return wavelet

@@ -11,8 +11,28 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+def pytest_addoption(parser):
+    parser.addoption("--emu", action="store_true", default=False,
+                     help="developer aid: run gpu-marked tests against the host-emulation "
+                          "build of the kernels (tests/_emu), for debugging test logic "
+                          "without a GPU.  Never used by the driver.")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    if config.getoption("--emu"):
+        use_emulation_library()
+
+
+def use_emulation_library():
+    """Point the ctypes loader at tests/_emu/libcwtb200_emu.so (same kernel sources,
+    compiled with -DCWTB_HOST_EMU so every CTA runs as a C++ loop on the CPU).  This is
+    test-side patching: the package itself has no switch for it."""
+    from pycwt_b200 import build as _build, _engine
+    lib = _build.build_emulation(os.path.join(ROOT, "tests", "_emu"))
+    _engine.LIB_PATH = lib
+    _engine._default.clear()
+    return lib
 
 
 def load_golden(name):
