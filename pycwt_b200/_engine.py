@@ -47,6 +47,16 @@ _SIGNATURES = {
     "cwtb_memcpy_d2h": (_I, [_P, _P, _P, ctypes.c_size_t]),
     "cwtb_sync": (_I, [_P]),
     "cwtb_fft_c2c": (_I, [_P, _P, _P, _I64, _I, _I, _I]),
+    "cwtb_cwt_to_host": (_I, [_P, _P, _I, _I64, _D, _P, _I, _I, _D, _I, _P, _I]),
+    "cwtb_icwt_sum": (_I, [_P, _P]),
+    "cwtb_icwt_sum_host": (_I, [_P, _P, _P, _I, _I64, _P]),
+    "cwtb_get_power": (_I, [_P, _P]),
+    "cwtb_global_power": (_I, [_P, _P]),
+    "cwtb_xwt": (_I, [_P, _P, _P, _I64, _D, _P, _I, _I, _D, _P]),
+    "cwtb_wct": (_I, [_P, _P, _P, _I64, _D, _D, _P, _I, _I, _D, _I, _P, _P]),
+    "cwtb_smooth": (_I, [_P, _P, _I, _I, _I64, _D, _P, _I, _P]),
+    "cwtb_wct_mc": (_I, [_P, _P, _I, _I64, _D, _D, _P, _I, _I, _D, _I, _P, _I, _I, _P]),
+    "cwtb_cwt_batch": (_I, [_P, _P, _I, _I, _I64, _D, _P, _I, _I, _D, _I, _P, _P]),
 }
 
 
@@ -137,6 +147,7 @@ class Engine(object):
             self._check(self.lib.cwtb_cwt(self.h, _ptr(sig), is32, sig.size, float(dt),
                                           _ptr(sj), sj.size, int(family), float(param),
                                           int(precision), tptr))
+            self._resident_n0 = sig.size
             if not fetch:
                 return None
             return self.get_w(sj.size, sig.size, precision, out_f64)
@@ -176,6 +187,106 @@ class Engine(object):
         self._check(self.lib.cwtb_fft_c2c(self.h, _ptr(x), _ptr(out), x.shape[1],
                                           x.shape[0], int(sign), int(precision)))
         return out
+
+    # ---- reductions / derived products of the resident transform ------------------------
+    def icwt_sum(self, W=None, scales=None):
+        """sum_j Re(W[j, :]) / sqrt(s_j): of the resident transform (W is None) or of a host
+        array W[S, n]."""
+        with self.lock:
+            if W is None:
+                n0 = self._resident_n0
+                out = np.empty(n0, dtype=np.float64)
+                self._check(self.lib.cwtb_icwt_sum(self.h, _ptr(out)))
+                return out
+            W = np.ascontiguousarray(W, dtype=np.complex128)
+            sj = np.ascontiguousarray(scales, dtype=np.float64)
+            out = np.empty(W.shape[1], dtype=np.float64)
+            self._check(self.lib.cwtb_icwt_sum_host(self.h, _ptr(W), _ptr(sj), W.shape[0],
+                                                    W.shape[1], _ptr(out)))
+            return out
+
+    def global_power(self, nrows):
+        out = np.empty(nrows, dtype=np.float64)
+        self._check(self.lib.cwtb_global_power(self.h, _ptr(out)))
+        return out
+
+    def power(self, nrows, n0):
+        out = np.empty((nrows, n0), dtype=np.float64)
+        self._check(self.lib.cwtb_get_power(self.h, _ptr(out)))
+        return out
+
+    # ---- cross wavelet / coherence ------------------------------------------------------
+    def xwt(self, y1, y2, dt, scales, family, param):
+        y1 = np.ascontiguousarray(y1, dtype=np.float64)
+        y2 = np.ascontiguousarray(y2, dtype=np.float64)
+        if y1.shape != y2.shape or y1.ndim != 1:
+            raise ValueError("xwt: the two series must be 1-D and of equal length")
+        sj = np.ascontiguousarray(scales, dtype=np.float64)
+        out = np.empty((sj.size, y1.size), dtype=np.complex128)
+        with self.lock:
+            self._check(self.lib.cwtb_xwt(self.h, _ptr(y1), _ptr(y2), y1.size, float(dt), _ptr(sj),
+                                          sj.size, int(family), float(param), _ptr(out)))
+        return out
+
+    def wct(self, y1, y2, dt, dj, scales, family, param, boxcar_len, want_angle=True):
+        y1 = np.ascontiguousarray(y1, dtype=np.float64)
+        y2 = np.ascontiguousarray(y2, dtype=np.float64)
+        if y1.shape != y2.shape or y1.ndim != 1:
+            raise ValueError("wct: the two series must be 1-D and of equal length")
+        sj = np.ascontiguousarray(scales, dtype=np.float64)
+        WCT = np.empty((sj.size, y1.size), dtype=np.float64)
+        aWCT = np.empty((sj.size, y1.size), dtype=np.float64) if want_angle else None
+        with self.lock:
+            self._check(self.lib.cwtb_wct(self.h, _ptr(y1), _ptr(y2), y1.size, float(dt), float(dj),
+                                          _ptr(sj), sj.size, int(family), float(param),
+                                          int(boxcar_len), _ptr(WCT),
+                                          _ptr(aWCT) if want_angle else None))
+        return WCT, aWCT
+
+    def smooth(self, W, dt, scales, boxcar_len):
+        W = np.ascontiguousarray(W)
+        is_c = np.iscomplexobj(W)
+        W = np.ascontiguousarray(W, dtype=np.complex128 if is_c else np.float64)
+        sj = np.ascontiguousarray(scales, dtype=np.float64)
+        out = np.empty_like(W)
+        with self.lock:
+            self._check(self.lib.cwtb_smooth(self.h, _ptr(W), int(is_c), W.shape[0], W.shape[1],
+                                             float(dt), _ptr(sj), int(boxcar_len), _ptr(out)))
+        return out
+
+    def wct_mc(self, noise, dt, dj, scales, family, param, boxcar_len, mask, maxscale, nbins,
+               hist):
+        noise = np.ascontiguousarray(noise, dtype=np.float64)
+        assert noise.ndim == 3 and noise.shape[1] == 2
+        sj = np.ascontiguousarray(scales, dtype=np.float64)
+        mask = np.ascontiguousarray(mask, dtype=np.uint8)
+        assert mask.shape == (sj.size, noise.shape[2])
+        assert hist.dtype == np.int64 and hist.flags.c_contiguous and hist.shape == (sj.size, nbins)
+        with self.lock:
+            self._check(self.lib.cwtb_wct_mc(self.h, _ptr(noise), noise.shape[0], noise.shape[2],
+                                             float(dt), float(dj), _ptr(sj), sj.size, int(family),
+                                             float(param), int(boxcar_len), _ptr(mask),
+                                             int(maxscale), int(nbins), _ptr(hist)))
+        return hist
+
+    def cwt_batch(self, X, dt, scales, family, param, precision=F64, want_power=True,
+                  want_w=False):
+        X = np.ascontiguousarray(X)
+        if X.dtype != np.float32:
+            X = np.ascontiguousarray(X, dtype=np.float64)
+        sj = np.ascontiguousarray(scales, dtype=np.float64)
+        nch, n0 = X.shape
+        power = np.empty((nch, sj.size), dtype=np.float64) if want_power else None
+        W = None
+        if want_w:
+            W = np.empty((nch, sj.size, n0), dtype=np.complex128 if precision == F64 else np.complex64)
+        with self.lock:
+            self._check(self.lib.cwtb_cwt_batch(self.h, _ptr(X), int(X.dtype == np.float32), nch, n0,
+                                                float(dt), _ptr(sj), sj.size, int(family),
+                                                float(param), int(precision),
+                                                _ptr(power) if want_power else None,
+                                                _ptr(W) if want_w else None))
+        return power, W
 
     # ---- device-resident benchmarking helpers -------------------------------------
     def dev_alloc(self, nbytes):

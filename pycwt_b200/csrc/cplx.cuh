@@ -6,7 +6,11 @@
 #include <cuda_runtime.h>
 
 #ifndef HD
+#ifdef CWTB_HOST_EMU
+#define HD inline  // tests-only CPU emulation build: no device code at all
+#else
 #define HD __host__ __device__ __forceinline__
+#endif
 #endif
 
 namespace cwtb {
@@ -38,7 +42,7 @@ template <typename V, typename T> HD V cscale(V a, T s) { a.x *= s; a.y *= s; re
 
 // sin(pi x), cos(pi x)
 HD void sincospi_hd(double x, double *s, double *c) {
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) && !defined(CWTB_HOST_EMU)
   sincospi(x, s, c);
 #else
   ::sincos(3.14159265358979323846 * x, s, c);

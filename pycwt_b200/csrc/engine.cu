@@ -95,6 +95,7 @@ struct Job {
   std::vector<ScaleDesc> descs;   // sorted by class
   std::vector<ClassRun> classes;
   std::vector<int> plan_log2K;    // per input scale
+  std::vector<double> scales;     // per input scale (= output row)
   size_t b_single = 0;            // elements of the band buffer used by single-kernel scales
   int sig_is_f32 = 0;
 };
@@ -114,7 +115,7 @@ struct cwtb_ctx {
   double2 *tw64 = nullptr;
   float2 *tw32 = nullptr;
   std::map<unsigned, NTabDev> ntabs;
-  Buf sig, spec, Z, B, W, descs, table, scratch;
+  Buf sig, sig2, spec, Z, B, W, W2, descs, table, scratch, C, A12, F, aux, rowd, win, mask, hist, noise;
   Job job;
   const void *job_dsig = nullptr;  // device signal of the last cwt_dev call (not owned)
   double last_ms = 0;
@@ -311,6 +312,7 @@ static int build_job(cwtb_ctx *c, Job &job, long long n0, double dt, const doubl
 
   std::vector<ScaleDesc> ds(S);
   job.plan_log2K.assign(S, 0);
+  job.scales.assign(scales, scales + S);
   const long long half = (long long)N / 2;
   for (int j = 0; j < S; ++j) {
     ScaleDesc &d = ds[j];
@@ -384,8 +386,8 @@ template <> struct Tw<float> { static const float2 *get(cwtb_ctx *c) { return c-
 // real_in: input rows are T (zero-padded from n_in to n); else cx<T>.
 template <typename T, int SIGN>
 static int fft_rows(cwtb_ctx *c, const void *in, int real_in, long long in_pitch, long long n_in,
-                    cx<T> *out, long long out_pitch, unsigned n, int nrows, const T *mul,
-                    long long mul_pitch);
+                    cx<T> *out, long long out_pitch, unsigned n, int nrows, long long nout = -1,
+                    const double *grow = nullptr, double post = 1.0);
 
 template <typename T, int SIGN, int K>
 static int fft_rows_small(cwtb_ctx *c, const RowsArgs<T> &a) {
@@ -419,14 +421,15 @@ static int dispatch_passA(cwtb_ctx *c, int log2K1, const PassAArgs<T> &a, int ny
 
 template <typename T, int SIGN>
 static int fft_rows(cwtb_ctx *c, const void *in, int real_in, long long in_pitch, long long n_in,
-                    cx<T> *out, long long out_pitch, unsigned n, int nrows, const T *mul,
-                    long long mul_pitch) {
+                    cx<T> *out, long long out_pitch, unsigned n, int nrows, long long nout,
+                    const double *grow, double post) {
   const int l2 = ilog2(n);
+  if (nout < 0) nout = n;
   if (n <= 1024) {
     RowsArgs<T> a;
-    a.in = in; a.out = out; a.tw = Tw<T>::get(c); a.mul = mul;
-    a.in_pitch = in_pitch; a.out_pitch = out_pitch; a.n_in = n_in; a.mul_pitch = mul_pitch;
-    a.nrows = nrows; a.real_in = real_in;
+    a.in = in; a.out = out; a.tw = Tw<T>::get(c); a.grow = grow;
+    a.in_pitch = in_pitch; a.out_pitch = out_pitch; a.n_in = n_in; a.nout = nout;
+    a.post = post; a.nrows = nrows; a.real_in = real_in; a.n = (int)n;
     switch (l2) {
       case 1: return fft_rows_small<T, SIGN, 2>(c, a);
       case 2: return fft_rows_small<T, SIGN, 4>(c, a);
@@ -441,7 +444,6 @@ static int fft_rows(cwtb_ctx *c, const void *in, int real_in, long long in_pitch
     }
     return fail(c, CWTB_ERR_ARG, "fft_rows: bad length");
   }
-  if (mul) return fail(c, CWTB_ERR_UNSUPPORTED, "fft_rows: multiplier only for n <= 1024");
   // two kernels through Z, in chunks of rows
   NTab nt;
   int e = get_ntab(c, n, l2, &nt);
@@ -459,7 +461,8 @@ static int fft_rows(cwtb_ctx *c, const void *in, int real_in, long long in_pitch
     if (e) return e;
     PassBArgs<T> b{};
     b.Z = (const cx<T> *)c->Z.p; b.out = out; b.tw = Tw<T>::get(c); b.descs = nullptr;
-    b.pitch = out_pitch; b.nout = n; b.N = n; b.first = 0; b.row0 = r0;
+    b.pitch = out_pitch; b.nout = nout; b.N = n; b.first = 0; b.row0 = r0;
+    b.epi = grow ? EPI_GAUSS : EPI_STORE; b.grow = grow; b.post = post;
     e = launch<PassBBody<T, SIGN>>(c, (n / K2C + Lay<T, K2C>::P - 1) / Lay<T, K2C>::P, nr, b);
     if (e) return e;
   }
@@ -475,15 +478,18 @@ static int launch_single(cwtb_ctx *c, const SingleArgs<T> &a, int count) {
 
 // all kernels of one transform: forward FFT of the (device, type T) signal, then every scale
 template <typename T>
-static int run_job(cwtb_ctx *c, const Job &job, const T *dsig) {
+static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nullptr, int epi = EPI_STORE) {
   using V = cx<T>;
   const unsigned N = job.N;
   const int S = job.S;
   int e;
   if ((e = ensure(c, c->spec, (size_t)N * sizeof(V)))) return e;
-  if ((e = ensure(c, c->W, (size_t)S * job.n0 * sizeof(V)))) return e;
+  if (!Wout) {
+    if ((e = ensure(c, c->W, (size_t)S * job.n0 * sizeof(V)))) return e;
+    Wout = (V *)c->W.p;
+  }
   V *spec = (V *)c->spec.p;
-  V *W = (V *)c->W.p;
+  V *W = Wout;
   const ScaleDesc *ddesc = (const ScaleDesc *)c->descs.p;
   Fam fam = job.fam;
   if (fam.family == CWTB_TABLE) fam.table = (const double2 *)c->table.p;
@@ -492,10 +498,10 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig) {
   if (N < 32) {
     TinyFwdArgs<T> fa{dsig, spec, job.n0, N};
     if ((e = launch<TinyFwdBody<T>>(c, 1, 1, fa))) return e;
-    TinyArgs<T> ta{ddesc, spec, W, fam, job.n0, N, 0};
+    TinyArgs<T> ta{ddesc, spec, W, fam, job.n0, N, 0, epi};
     return launch<TinyBody<T>>(c, (unsigned)((job.n0 + NT - 1) / NT), S, ta);
   }
-  if ((e = fft_rows<T, -1>(c, dsig, 1, job.n0, job.n0, spec, N, N, 1, nullptr, 0))) return e;
+  if ((e = fft_rows<T, -1>(c, dsig, 1, job.n0, job.n0, spec, N, N, 1))) return e;
 
   NTab nt;
   if ((e = get_ntab(c, N, job.log2N, &nt))) return e;
@@ -511,7 +517,7 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig) {
       BandArgs<T> ba{ddesc, spec, Bbuf, fam, N, cl.first};
       if ((e = launch<BandBody<T>>(c, (K + NT * BandBody<T>::PER - 1) / (NT * BandBody<T>::PER), cl.count, ba)))
         return e;
-      SingleArgs<T> sa{ddesc, Bbuf, W, Tw<T>::get(c), nt, job.n0, N, cl.first};
+      SingleArgs<T> sa{ddesc, Bbuf, W, Tw<T>::get(c), nt, job.n0, N, cl.first, epi};
       switch (cl.log2K) {
         case 5: e = launch_single<T, 32>(c, sa, cl.count); break;
         case 6: e = launch_single<T, 64>(c, sa, cl.count); break;
@@ -544,6 +550,7 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig) {
       PassBArgs<T> b{};
       b.Z = (const V *)c->Z.p; b.out = W; b.tw = Tw<T>::get(c); b.descs = ddesc;
       b.pitch = job.n0; b.nout = job.n0; b.N = N; b.first = cl.first + g0; b.row0 = 0;
+      b.epi = epi; b.grow = nullptr; b.post = 1.0;
       if ((e = launch<PassBBody<T, +1>>(c, (N / K2C + Lay<T, K2C>::P - 1) / Lay<T, K2C>::P, ng, b))) return e;
     }
   }
@@ -653,7 +660,8 @@ void cwtb_destroy(cwtb_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
 #endif
-  for (Buf *b : {&c->sig, &c->spec, &c->Z, &c->B, &c->W, &c->descs, &c->table, &c->scratch})
+  for (Buf *b : {&c->sig, &c->sig2, &c->spec, &c->Z, &c->B, &c->W, &c->W2, &c->descs, &c->table, &c->scratch,
+                 &c->C, &c->A12, &c->F, &c->aux, &c->rowd, &c->win, &c->mask, &c->hist, &c->noise})
     if (b->p) rt_free(b->p);
   for (auto &kv : c->ntabs) { rt_free(kv.second.hi); rt_free(kv.second.lo); }
   if (c->tw64) rt_free(c->tw64);
@@ -855,8 +863,8 @@ int cwtb_fft_c2c(cwtb_ctx *c, const void *in, void *out, int64_t n, int batch, i
   int e = 0;
   if (precision == CWTB_F64) {
     rt_h2d(din, in, cnt * esz, c->stream);
-    e = sign < 0 ? fft_rows<double, -1>(c, din, 0, n, n, (double2 *)dout, n, (unsigned)n, batch, nullptr, 0)
-                 : fft_rows<double, +1>(c, din, 0, n, n, (double2 *)dout, n, (unsigned)n, batch, nullptr, 0);
+    e = sign < 0 ? fft_rows<double, -1>(c, din, 0, n, n, (double2 *)dout, n, (unsigned)n, batch)
+                 : fft_rows<double, +1>(c, din, 0, n, n, (double2 *)dout, n, (unsigned)n, batch);
     if (!e) { rt_d2h(out, dout, cnt * esz, c->stream); e = rt_sync(c->stream) ? CWTB_ERR_CUDA : 0; }
   } else {
     std::vector<float> tmp(cnt * 2);
@@ -864,8 +872,8 @@ int cwtb_fft_c2c(cwtb_ctx *c, const void *in, void *out, int64_t n, int batch, i
     for (size_t i = 0; i < cnt * 2; ++i) tmp[i] = (float)src[i];
     rt_h2d(din, tmp.data(), cnt * esz, c->stream);
     rt_sync(c->stream);
-    e = sign < 0 ? fft_rows<float, -1>(c, din, 0, n, n, (float2 *)dout, n, (unsigned)n, batch, nullptr, 0)
-                 : fft_rows<float, +1>(c, din, 0, n, n, (float2 *)dout, n, (unsigned)n, batch, nullptr, 0);
+    e = sign < 0 ? fft_rows<float, -1>(c, din, 0, n, n, (float2 *)dout, n, (unsigned)n, batch)
+                 : fft_rows<float, +1>(c, din, 0, n, n, (float2 *)dout, n, (unsigned)n, batch);
     if (!e) {
       rt_d2h(tmp.data(), dout, cnt * esz, c->stream);
       e = rt_sync(c->stream) ? CWTB_ERR_CUDA : 0;
@@ -877,6 +885,299 @@ int cwtb_fft_c2c(cwtb_ctx *c, const void *in, void *out, int64_t n, int batch, i
   rt_free(din);
   rt_free(dout);
   return e;
+}
+
+// ---- helpers for the post-processing entry points ---------------------------------------
+static int upload_doubles(cwtb_ctx *c, Buf &b, const std::vector<double> &v) {
+  int e = ensure(c, b, v.size() * sizeof(double));
+  if (e) return e;
+  RT(rt_h2d(b.p, v.data(), v.size() * sizeof(double), c->stream));
+  RT(rt_sync(c->stream));
+  return 0;
+}
+
+static int upload_signal_f64(cwtb_ctx *c, Buf &b, const double *y, long long n0) {
+  int e = ensure(c, b, (size_t)n0 * sizeof(double));
+  if (e) return e;
+  RT(rt_h2d(b.p, y, (size_t)n0 * sizeof(double), c->stream));
+  RT(rt_sync(c->stream));
+  return 0;
+}
+
+// boxcar with half-weight end taps, normalised (helpers.py:176-191)
+static int upload_window(cwtb_ctx *c, int K) {
+  if (K < 1) return fail(c, CWTB_ERR_ARG, "boxcar length must be >= 1");
+  std::vector<double> w(K, 1.0);
+  w[0] = 0.5;
+  w[K - 1] = 0.5;   // K == 1: single tap 0.5, normalised to 1
+  double sum = 0;
+  for (double v : w) sum += v;
+  for (double &v : w) v /= sum;
+  return upload_doubles(c, c->win, w);
+}
+
+// Morlet.smooth, time part (mothers.py:83-93), in place on X[S][n0] (complex128, device):
+// forward transform of the zero-padded rows with the Gaussian folded into its output pass,
+// inverse transform trimmed to n0.
+static int smooth_time(cwtb_ctx *c, double2 *X, int S, long long n0, unsigned N, const double *d_g) {
+  int e = ensure(c, c->F, (size_t)S * N * sizeof(double2));
+  if (e) return e;
+  double2 *F = (double2 *)c->F.p;
+  if (N < 2) return 0;  // single sample: filter is exp(0) = 1
+  if ((e = fft_rows<double, -1>(c, X, 0, n0, n0, F, N, N, S, N, d_g, 1.0 / (double)N))) return e;
+  return fft_rows<double, +1>(c, F, 0, N, N, X, n0, N, S, n0);
+}
+
+// two transforms + coherence pipeline; outputs are device pointers (any may be null)
+static int wct_core(cwtb_ctx *c, const Job &job, const double *dsig1, const double *dsig2, int K,
+                    double *dWCT, double *daWCT, const unsigned char *dmask, int maxscale, int nbins,
+                    unsigned long long *dhist) {
+  const int S = job.S;
+  const long long n0 = job.n0;
+  const size_t cnt = (size_t)S * n0;
+  int e;
+  if ((e = ensure(c, c->W, cnt * sizeof(double2)))) return e;
+  if ((e = ensure(c, c->W2, cnt * sizeof(double2)))) return e;
+  if ((e = ensure(c, c->C, cnt * sizeof(double2)))) return e;
+  if ((e = ensure(c, c->A12, cnt * sizeof(double2)))) return e;
+  if ((e = run_job<double>(c, job, dsig1, (double2 *)c->W.p, EPI_STORE))) return e;
+  if ((e = run_job<double>(c, job, dsig2, (double2 *)c->W2.p, EPI_STORE))) return e;
+  const double *d_scale = (const double *)c->rowd.p;      // [S] scales, then [S] g
+  const double *d_g = d_scale + S;
+  WctPrepArgs pa{(const double2 *)c->W.p, (const double2 *)c->W2.p, d_scale, (double2 *)c->C.p,
+                 (double2 *)c->A12.p, daWCT, n0};
+  const unsigned gx = (unsigned)((n0 + NT - 1) / NT);
+  if ((e = launch<WctPrepBody>(c, gx, S, pa))) return e;
+  if ((e = smooth_time(c, (double2 *)c->C.p, S, n0, job.N, d_g))) return e;
+  if ((e = smooth_time(c, (double2 *)c->A12.p, S, n0, job.N, d_g))) return e;
+  WctFinalArgs fa{(const double2 *)c->C.p, (const double2 *)c->A12.p, (const double *)c->win.p, dWCT,
+                  dmask, dhist, n0, S, K, maxscale, nbins};
+  return launch<WctFinalBody>(c, gx, S, fa);
+}
+
+static int upload_row_tables(cwtb_ctx *c, const Job &job) {
+  std::vector<double> v(2 * (size_t)job.S);
+  for (int j = 0; j < job.S; ++j) {
+    v[j] = job.scales[j];
+    const double snorm = job.scales[j] / job.dt;
+    v[job.S + j] = -0.5 * (snorm * snorm);
+  }
+  return upload_doubles(c, c->rowd, v);
+}
+
+int cwtb_cwt_to_host(cwtb_ctx *c, const void *signal, int signal_is_f32, int64_t n0, double dt,
+                     const double *scales, int n_scales, int family, double param, int precision,
+                     void *out, int out_f64) {
+  int e = cwtb_cwt(c, signal, signal_is_f32, n0, dt, scales, n_scales, family, param, precision, nullptr);
+  if (e) return e;
+  return cwtb_get_w(c, out, out_f64, 0, n_scales);
+}
+
+int cwtb_icwt_sum(cwtb_ctx *c, double *out) {
+  if (!c || !c->job.valid || !out) return fail(c, CWTB_ERR_STATE, "no transform resident");
+  const Job &job = c->job;
+  std::vector<double> rs(job.S);
+  for (int j = 0; j < job.S; ++j) rs[j] = std::sqrt(job.scales[j]);
+  int e = upload_doubles(c, c->rowd, rs);
+  if (e) return e;
+  if ((e = ensure(c, c->aux, (size_t)job.n0 * sizeof(double)))) return e;
+  const unsigned gx = (unsigned)((job.n0 + NT - 1) / NT);
+  if (job.precision == CWTB_F64) {
+    IcwtArgs<double> a{(const double2 *)c->W.p, (const double *)c->rowd.p, (double *)c->aux.p, job.n0, job.n0, job.S, 0};
+    e = launch<IcwtBody<double>>(c, gx, 1, a);
+  } else {
+    IcwtArgs<float> a{(const float2 *)c->W.p, (const double *)c->rowd.p, (double *)c->aux.p, job.n0, job.n0, job.S, 0};
+    e = launch<IcwtBody<float>>(c, gx, 1, a);
+  }
+  if (e) return e;
+  RT(rt_d2h(out, c->aux.p, (size_t)job.n0 * sizeof(double), c->stream));
+  RT(rt_sync(c->stream));
+  return 0;
+}
+
+int cwtb_icwt_sum_host(cwtb_ctx *c, const void *W, const double *scales, int n_scales, int64_t n, double *out) {
+  if (!c || !W || !scales || !out || n_scales < 1 || n < 1) return fail(c, CWTB_ERR_ARG, "icwt: bad argument");
+  std::vector<double> rs(n_scales);
+  for (int j = 0; j < n_scales; ++j) rs[j] = std::sqrt(scales[j]);
+  int e = upload_doubles(c, c->rowd, rs);
+  if (e) return e;
+  if ((e = ensure(c, c->aux, (size_t)n * sizeof(double)))) return e;
+  const int chunk = (int)std::max<long long>(1, std::min<long long>(n_scales, (256ll << 20) / (n * 16)));
+  if ((e = ensure(c, c->scratch, (size_t)chunk * n * sizeof(double2)))) return e;
+  const unsigned gx = (unsigned)((n + NT - 1) / NT);
+  for (int r0 = 0; r0 < n_scales; r0 += chunk) {
+    const int nr = std::min(chunk, n_scales - r0);
+    RT(rt_h2d(c->scratch.p, (const double2 *)W + (size_t)r0 * n, (size_t)nr * n * sizeof(double2), c->stream));
+    IcwtArgs<double> a{(const double2 *)c->scratch.p, (const double *)c->rowd.p + r0, (double *)c->aux.p, n, n, nr, r0 > 0};
+    if ((e = launch<IcwtBody<double>>(c, gx, 1, a))) return e;
+    RT(rt_sync(c->stream));
+  }
+  RT(rt_d2h(out, c->aux.p, (size_t)n * sizeof(double), c->stream));
+  RT(rt_sync(c->stream));
+  return 0;
+}
+
+static int power_common(cwtb_ctx *c, double *power_out, double *mean_out) {
+  if (!c || !c->job.valid) return fail(c, CWTB_ERR_STATE, "no transform resident");
+  const Job &job = c->job;
+  const size_t cnt = (size_t)job.S * job.n0;
+  int e = ensure(c, c->aux, (power_out ? cnt : 0) * sizeof(double) + (size_t)job.S * sizeof(double));
+  if (e) return e;
+  double *dsum = (double *)c->aux.p;
+  double *dpow = power_out ? dsum + job.S : nullptr;
+  RT(rt_memset(dsum, 0, (size_t)job.S * sizeof(double), c->stream));
+  const unsigned gx = (unsigned)((job.n0 + 8 * NT - 1) / (8 * NT));
+  if (job.precision == CWTB_F64) {
+    PowerArgs<double> a{(const double2 *)c->W.p, dpow, dsum, job.n0};
+    e = launch<PowerBody<double>>(c, gx, job.S, a);
+  } else {
+    PowerArgs<float> a{(const float2 *)c->W.p, dpow, dsum, job.n0};
+    e = launch<PowerBody<float>>(c, gx, job.S, a);
+  }
+  if (e) return e;
+  if (power_out) RT(rt_d2h(power_out, dpow, cnt * sizeof(double), c->stream));
+  if (mean_out) RT(rt_d2h(mean_out, dsum, (size_t)job.S * sizeof(double), c->stream));
+  RT(rt_sync(c->stream));
+  if (mean_out) for (int j = 0; j < job.S; ++j) mean_out[j] /= (double)job.n0;
+  return 0;
+}
+int cwtb_get_power(cwtb_ctx *c, double *out) { return power_common(c, out, nullptr); }
+int cwtb_global_power(cwtb_ctx *c, double *out) { return power_common(c, nullptr, out); }
+
+int cwtb_xwt(cwtb_ctx *c, const double *y1, const double *y2, int64_t n0, double dt, const double *scales,
+             int n_scales, int family, double param, void *W12_out) {
+  if (!c || !y1 || !y2) return fail(c, CWTB_ERR_ARG, "null argument");
+  if (family == CWTB_TABLE) return fail(c, CWTB_ERR_UNSUPPORTED, "xwt needs an analytic wavelet family");
+  int e = prepare(c, n0, dt, scales, n_scales, family, param, CWTB_F64, nullptr);
+  if (e) return e;
+  if ((e = upload_signal_f64(c, c->sig, y1, n0))) return e;
+  if ((e = upload_signal_f64(c, c->sig2, y2, n0))) return e;
+  c->launches = 0;
+  if ((e = run_job<double>(c, c->job, (const double *)c->sig.p, nullptr, EPI_STORE))) return e;
+  if ((e = run_job<double>(c, c->job, (const double *)c->sig2.p, nullptr, EPI_MULCONJ))) return e;
+  c->job_dsig = nullptr;
+  if (W12_out) return cwtb_get_w(c, W12_out, 1, 0, n_scales);
+  RT(rt_sync(c->stream));
+  return 0;
+}
+
+int cwtb_wct(cwtb_ctx *c, const double *y1, const double *y2, int64_t n0, double dt, double dj,
+             const double *scales, int n_scales, int family, double param, int boxcar_len,
+             double *WCT_out, double *aWCT_out) {
+  (void)dj;
+  if (!c || !y1 || !y2) return fail(c, CWTB_ERR_ARG, "null argument");
+  if (family == CWTB_TABLE) return fail(c, CWTB_ERR_UNSUPPORTED, "wct needs an analytic wavelet family");
+  int e = prepare(c, n0, dt, scales, n_scales, family, param, CWTB_F64, nullptr);
+  if (e) return e;
+  if ((e = upload_signal_f64(c, c->sig, y1, n0))) return e;
+  if ((e = upload_signal_f64(c, c->sig2, y2, n0))) return e;
+  if ((e = upload_window(c, boxcar_len))) return e;
+  if ((e = upload_row_tables(c, c->job))) return e;
+  const size_t cnt = (size_t)n_scales * n0;
+  if ((e = ensure(c, c->aux, 2 * cnt * sizeof(double)))) return e;
+  double *dW = (double *)c->aux.p, *dA = dW + cnt;
+  c->launches = 0;
+  if ((e = wct_core(c, c->job, (const double *)c->sig.p, (const double *)c->sig2.p, boxcar_len, dW,
+                    aWCT_out ? dA : nullptr, nullptr, 0, 0, nullptr)))
+    return e;
+  c->job_dsig = nullptr;
+  if (WCT_out) RT(rt_d2h(WCT_out, dW, cnt * sizeof(double), c->stream));
+  if (aWCT_out) RT(rt_d2h(aWCT_out, dA, cnt * sizeof(double), c->stream));
+  RT(rt_sync(c->stream));
+  return 0;
+}
+
+int cwtb_smooth(cwtb_ctx *c, const void *in, int is_complex, int n_scales, int64_t n, double dt,
+                const double *scales, int boxcar_len, void *out) {
+  if (!c || !in || !out || !scales || n_scales < 1 || n < 1 || !(dt > 0))
+    return fail(c, CWTB_ERR_ARG, "smooth: bad argument");
+  if (n > (1ll << 20)) return fail(c, CWTB_ERR_UNSUPPORTED, "smooth: rows longer than 2^20");
+#ifndef CWTB_HOST_EMU
+  RT(cudaSetDevice(c->device));
+#endif
+  const int S = n_scales;
+  const size_t cnt = (size_t)S * n;
+  const unsigned N = 1u << ilog2((unsigned long long)n);
+  int e = upload_window(c, boxcar_len);
+  if (e) return e;
+  std::vector<double> g(2 * (size_t)S);
+  for (int j = 0; j < S; ++j) { g[j] = scales[j]; double sn = scales[j] / dt; g[S + j] = -0.5 * (sn * sn); }
+  if ((e = upload_doubles(c, c->rowd, g))) return e;
+  if ((e = ensure(c, c->C, cnt * sizeof(double2)))) return e;
+  if ((e = ensure(c, c->A12, cnt * sizeof(double2)))) return e;
+  double2 *X = (double2 *)c->C.p, *Y = (double2 *)c->A12.p;
+  if (is_complex) {
+    RT(rt_h2d(X, in, cnt * sizeof(double2), c->stream));
+  } else {
+    RT(rt_h2d(Y, in, cnt * sizeof(double), c->stream));   // stage the reals in Y, widen into X
+    R2CArgs ra{(const double *)Y, X, (long long)cnt};
+    if ((e = launch<R2CBody>(c, (unsigned)((cnt + NT - 1) / NT), 1, ra))) return e;
+  }
+  if ((e = smooth_time(c, X, S, n, N, (const double *)c->rowd.p + S))) return e;
+  BoxcarArgs ba{X, Y, (const double *)c->win.p, n, S, boxcar_len};
+  if ((e = launch<BoxcarBody>(c, (unsigned)((n + NT - 1) / NT), S, ba))) return e;
+  if (is_complex) {
+    RT(rt_d2h(out, Y, cnt * sizeof(double2), c->stream));
+    RT(rt_sync(c->stream));
+  } else {
+    std::vector<double2> tmp(cnt);
+    RT(rt_d2h(tmp.data(), Y, cnt * sizeof(double2), c->stream));
+    RT(rt_sync(c->stream));
+    double *o = (double *)out;
+    for (size_t i = 0; i < cnt; ++i) o[i] = tmp[i].x;   // .real, mothers.py:95-96
+  }
+  return 0;
+}
+
+int cwtb_wct_mc(cwtb_ctx *c, const double *noise, int n_pairs, int64_t n0, double dt, double dj,
+                const double *scales, int n_scales, int family, double param, int boxcar_len,
+                const uint8_t *mask, int maxscale, int nbins, int64_t *hist) {
+  (void)dj;
+  if (!c || !noise || !mask || !hist || n_pairs < 0 || nbins < 1 || maxscale < 0 || maxscale > n_scales)
+    return fail(c, CWTB_ERR_ARG, "wct_mc: bad argument");
+  if (family == CWTB_TABLE) return fail(c, CWTB_ERR_UNSUPPORTED, "wct_mc needs an analytic wavelet family");
+  int e = prepare(c, n0, dt, scales, n_scales, family, param, CWTB_F64, nullptr);
+  if (e) return e;
+  if ((e = upload_window(c, boxcar_len))) return e;
+  if ((e = upload_row_tables(c, c->job))) return e;
+  const size_t cnt = (size_t)n_scales * n0;
+  if ((e = ensure(c, c->mask, cnt))) return e;
+  RT(rt_h2d(c->mask.p, mask, cnt, c->stream));
+  const size_t hb = (size_t)n_scales * nbins * sizeof(unsigned long long);
+  if ((e = ensure(c, c->hist, hb))) return e;
+  RT(rt_memset(c->hist.p, 0, hb, c->stream));
+  if ((e = ensure(c, c->noise, (size_t)n_pairs * 2 * n0 * sizeof(double)))) return e;
+  RT(rt_h2d(c->noise.p, noise, (size_t)n_pairs * 2 * n0 * sizeof(double), c->stream));
+  RT(rt_sync(c->stream));
+  c->launches = 0;
+  for (int i = 0; i < n_pairs; ++i) {
+    const double *a = (const double *)c->noise.p + (size_t)i * 2 * n0;
+    if ((e = wct_core(c, c->job, a, a + n0, boxcar_len, nullptr, nullptr, (const unsigned char *)c->mask.p,
+                      maxscale, nbins, (unsigned long long *)c->hist.p)))
+      return e;
+  }
+  c->job_dsig = nullptr;
+  std::vector<unsigned long long> h((size_t)n_scales * nbins);
+  RT(rt_d2h(h.data(), c->hist.p, hb, c->stream));
+  RT(rt_sync(c->stream));
+  for (size_t i = 0; i < h.size(); ++i) hist[i] += (int64_t)h[i];
+  return 0;
+}
+
+int cwtb_cwt_batch(cwtb_ctx *c, const void *X, int x_is_f32, int n_chan, int64_t n0, double dt,
+                   const double *scales, int n_scales, int family, double param, int precision,
+                   double *power_out, void *W_out) {
+  if (!c || !X || n_chan < 1) return fail(c, CWTB_ERR_ARG, "cwt_batch: bad argument");
+  const size_t esz_in = x_is_f32 ? 4 : 8;
+  const size_t wsz = (precision == CWTB_F64 ? 16 : 8) * (size_t)n_scales * n0;
+  for (int ch = 0; ch < n_chan; ++ch) {
+    int e = cwtb_cwt(c, (const char *)X + (size_t)ch * n0 * esz_in, x_is_f32, n0, dt, scales, n_scales,
+                     family, param, precision, nullptr);
+    if (e) return e;
+    if (power_out && (e = cwtb_global_power(c, power_out + (size_t)ch * n_scales))) return e;
+    if (W_out && (e = cwtb_get_w(c, (char *)W_out + (size_t)ch * wsz, 0, 0, n_scales))) return e;
+  }
+  return 0;
 }
 
 }  // extern "C"

@@ -72,7 +72,7 @@ template <typename T, int K> struct Lay {
 };
 
 template <typename V> HD V ldg(const V *p) {
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) && !defined(CWTB_HOST_EMU)
   return __ldg(p);
 #else
   return *p;

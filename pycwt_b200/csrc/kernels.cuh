@@ -76,19 +76,46 @@ HD cx<T> band_value(const Fam &fp, const ScaleDesc &d, const cx<T> *spec, unsign
 }
 
 // ---- storers -------------------------------------------------------------------
-// final output: out[row][u + q*U], u = u0 + b, trimmed to n < nout
+// final output: out[row][u + q*U], u = u0 + b, trimmed to n < nout.
+// Epilogues fused into the store:
+//   EPI_STORE      out = x
+//   EPI_MULCONJ    out = out * conj(x)          (cross-wavelet: second transform of xwt)
+//   EPI_GAUSS      out = x * exp(g * k_n^2) * post, k_n = 2 pi fftfreq(nfreq)[n]
+//                  (time-smoothing filter of Morlet.smooth applied to a forward transform)
+enum { EPI_STORE = 0, EPI_MULCONJ = 1, EPI_GAUSS = 2 };
+template <typename T> struct Epilogue {
+  int mode;
+  double g;        // EPI_GAUSS: -0.5 * (s/dt)^2 of this row
+  double invn;     // 1 / nfreq
+  double post;     // extra real factor (1/npad of the following inverse transform)
+  long long nfreq;
+  HD cx<T> apply(cx<T> x, cx<T> old, long long n) const {
+    if (mode == EPI_MULCONJ) return cmul(old, cconj(x));
+    if (mode == EPI_GAUSS) {
+      const long long qs = n < nfreq / 2 ? n : n - nfreq;   // numpy fftfreq ordering
+      const double k = 6.283185307179586 * ((double)qs * invn);
+      const T f = (T)(exp(g * (k * k)) * post);
+      return cscale(x, f);
+    }
+    return x;
+  }
+};
 template <typename T> struct OutStorer {
   using V = cx<T>;
   V *row;          // out + row*pitch
   long long nout;  // keep n < nout
   int u0, U;
+  Epilogue<T> epi;
   template <int R> HD void store(int b, int ql, int qs, V (&x)[R]) const {
     const int u = u0 + b;
     if (u >= U) return;
 #pragma unroll
     for (int c = 0; c < R; ++c) {
       long long n = u + (long long)(ql + c * qs) * U;
-      if (n < nout) row[n] = x[c];
+      if (n < nout) {
+        if (epi.mode == EPI_STORE) row[n] = x[c];
+        else row[n] = epi.apply(x[c], epi.mode == EPI_MULCONJ ? row[n] : x[c], n);
+      }
     }
   }
 };
@@ -126,6 +153,7 @@ template <typename T> struct SingleArgs {
   long long n0;
   unsigned N;
   int first;               // descs[first + blockIdx.y]
+  int epi;                 // EPI_STORE / EPI_MULCONJ
 };
 
 template <typename T, int K> struct SingleBody {
@@ -156,6 +184,7 @@ template <typename T, int K> struct SingleBody {
       st.nout = a.n0;
       st.u0 = p0;
       st.U = M;
+      st.epi.mode = a.epi;
       pass_last<T, K, +1>(sm, st, tid);
     }
   }
@@ -167,9 +196,12 @@ template <typename T> struct PassBArgs {
   cx<T> *out;              // [rows][pitch]
   const cx<T> *tw;
   const ScaleDesc *descs;  // may be null: output row = blockIdx.y + row0
+  const double *grow;      // EPI_GAUSS: per-row coefficient g
   long long pitch, nout;
+  double post;
   unsigned N;
   int first, row0;
+  int epi;
 };
 
 template <typename T, int SIGN> struct PassBBody {
@@ -198,6 +230,13 @@ template <typename T, int SIGN> struct PassBBody {
       st.nout = a.nout;
       st.u0 = u0;
       st.U = U;
+      st.epi.mode = a.epi;
+      if (a.epi == EPI_GAUSS) {
+        st.epi.g = a.grow[row];
+        st.epi.invn = 1.0 / (double)a.N;
+        st.epi.post = a.post;
+        st.epi.nfreq = a.N;
+      }
       pass_last<T, K, SIGN>(sm, st, tid);
     }
   }
@@ -337,9 +376,10 @@ template <typename T> struct RowsArgs {
   const void *in;      // T* if real_in else cx<T>*
   cx<T> *out;
   const cx<T> *tw;
-  const T *mul;        // optional per-(row, q) real multiplier applied to the OUTPUT (may be null)
-  long long in_pitch, out_pitch, n_in, mul_pitch;
-  int nrows, real_in;
+  const double *grow;  // EPI_GAUSS: per-row coefficient (null: plain store)
+  long long in_pitch, out_pitch, n_in, nout;
+  double post;
+  int nrows, real_in, n;
 };
 
 template <typename T, int K> struct RowsLoader {
@@ -369,8 +409,13 @@ template <typename T> struct RowsStorer {
 #pragma unroll
     for (int c = 0; c < R; ++c) {
       const int q = ql + c * qs;
+      if (q >= a->nout) continue;
       V v = x[c];
-      if (a->mul) v = cscale(v, ldg(&a->mul[(size_t)row * a->mul_pitch + q]));
+      if (a->grow) {
+        Epilogue<T> e;
+        e.mode = EPI_GAUSS; e.g = a->grow[row]; e.invn = 1.0 / (double)a->n; e.post = a->post; e.nfreq = a->n;
+        v = e.apply(v, v, q);
+      }
       a->out[(size_t)row * a->out_pitch + q] = v;
     }
   }
@@ -418,6 +463,7 @@ template <typename T> struct TinyArgs {
   long long n0;
   unsigned N;
   int first;
+  int epi;
 };
 template <typename T> struct TinyBody {
   using V = cx<T>;
@@ -437,7 +483,9 @@ template <typename T> struct TinyBody {
       sr += (double)v.x * cs - (double)v.y * sn;
       si += (double)v.x * sn + (double)v.y * cs;
     }
-    a.W[(size_t)d.row * a.n0 + n] = mk<T>((T)sr, (T)si);
+    V *dst = &a.W[(size_t)d.row * a.n0 + n];
+    V val = mk<T>((T)sr, (T)si);
+    *dst = a.epi == EPI_MULCONJ ? cmul(*dst, cconj(val)) : val;
   }
 };
 // forward DFT of a tiny real signal
@@ -461,6 +509,168 @@ template <typename T> struct TinyFwdBody {
       si -= (double)a.sig[n] * sn;
     }
     a.spec[tid] = mk<T>((T)sr, (T)si);
+  }
+};
+
+
+// ---- Body: icwt reduction  out[n] (+)= sum_j Re(W[j,n]) / sqrt(s_j)   (wavelet.py:169-170) ----
+template <typename T> struct IcwtArgs {
+  const cx<T> *W;
+  const double *sqrt_s;   // per row
+  double *out;
+  long long n, pitch;
+  int rows, accumulate;
+};
+template <typename T> struct IcwtBody {
+  using Args = IcwtArgs<T>;
+  static constexpr int NPHASE = 1;
+  static constexpr size_t SMEM = 0;
+  template <int PH> HD static void phase(const Args &a, int bx, int, int tid, void *) {
+    const long long n = (long long)bx * NT + tid;
+    if (n >= a.n) return;
+    double acc = a.accumulate ? a.out[n] : 0.0;
+    for (int j = 0; j < a.rows; ++j) acc += (double)a.W[(size_t)j * a.pitch + n].x / a.sqrt_s[j];
+    a.out[n] = acc;
+  }
+};
+
+// ---- Body: coherence inputs (wavelet.py:506-514) ---------------------------------------
+//   C   = (|W1|^2 + i |W2|^2) / s   (two real fields packed into one complex field: the
+//         smoothing filter is real, so one complex transform smooths both)
+//   A12 = W1 conj(W2) / s,   aWCT = angle(W1 conj(W2))
+struct WctPrepArgs {
+  const double2 *W1, *W2;
+  const double *scale;   // per row
+  double2 *C, *A12;
+  double *aWCT;          // may be null
+  long long n;
+};
+struct WctPrepBody {
+  using Args = WctPrepArgs;
+  static constexpr int NPHASE = 1;
+  static constexpr size_t SMEM = 0;
+  template <int PH> HD static void phase(const Args &a, int bx, int by, int tid, void *) {
+    const long long n = (long long)bx * NT + tid;
+    if (n >= a.n) return;
+    const size_t i = (size_t)by * a.n + n;
+    const double2 w1 = a.W1[i], w2 = a.W2[i];
+    const double s = a.scale[by];
+    const double2 w12 = cmul(w1, cconj(w2));
+    a.C[i] = make_double2((w1.x * w1.x + w1.y * w1.y) / s, (w2.x * w2.x + w2.y * w2.y) / s);
+    a.A12[i] = make_double2(w12.x / s, w12.y / s);
+    if (a.aWCT) a.aWCT[i] = atan2(w12.y, w12.x);
+  }
+};
+
+// ---- Body: scale-axis boxcar (mothers.py:100-102; scipy convolve2d 'same', zero fill) ------
+//   out[i] = sum_t win[t] * in[i - (t - off)],  off = (K-1)//2, rows outside [0, m) are zero
+struct BoxcarArgs {
+  const double2 *in;
+  double2 *out;
+  const double *win;
+  long long n;
+  int rows, K;
+};
+HD double2 boxcar_at(const double2 *in, const double *win, int K, int rows, long long n, int i, long long col) {
+  const int off = (K - 1) / 2;
+  double re = 0, im = 0;
+  for (int t = 0; t < K; ++t) {
+    const int q = i - (t - off);
+    if (q < 0 || q >= rows) continue;
+    const double2 v = in[(size_t)q * n + col];
+    re += win[t] * v.x;
+    im += win[t] * v.y;
+  }
+  return make_double2(re, im);
+}
+struct BoxcarBody {
+  using Args = BoxcarArgs;
+  static constexpr int NPHASE = 1;
+  static constexpr size_t SMEM = 0;
+  template <int PH> HD static void phase(const Args &a, int bx, int by, int tid, void *) {
+    const long long n = (long long)bx * NT + tid;
+    if (n >= a.n) return;
+    a.out[(size_t)by * a.n + n] = boxcar_at(a.in, a.win, a.K, a.rows, a.n, by, n);
+  }
+};
+
+// ---- Body: coherence  WCT = |S12|^2 / (S1 S2)  after the scale boxcar; optional histogram
+// of floor(WCT * nbins) over masked points (wavelet.py:513, 624-630) ---------------------
+struct WctFinalArgs {
+  const double2 *C, *A12;   // time-smoothed fields
+  const double *win;
+  double *WCT;              // may be null (Monte-Carlo mode)
+  const unsigned char *mask;   // [rows][n], may be null
+  unsigned long long *hist;    // [rows][nbins], may be null
+  long long n;
+  int rows, K, maxscale, nbins;
+};
+struct WctFinalBody {
+  using Args = WctFinalArgs;
+  static constexpr int NPHASE = 1;
+  static constexpr size_t SMEM = 0;
+  template <int PH> HD static void phase(const Args &a, int bx, int by, int tid, void *) {
+    const long long n = (long long)bx * NT + tid;
+    if (n >= a.n) return;
+    if (!a.WCT && by >= a.maxscale) return;
+    const double2 c = boxcar_at(a.C, a.win, a.K, a.rows, a.n, by, n);
+    const double2 x = boxcar_at(a.A12, a.win, a.K, a.rows, a.n, by, n);
+    const double r2 = (x.x * x.x + x.y * x.y) / (c.x * c.y);
+    const size_t i = (size_t)by * a.n + n;
+    if (a.WCT) a.WCT[i] = r2;
+    if (a.hist && by < a.maxscale && a.mask[i] && r2 == r2) {
+      int bin = (int)floor(r2 * a.nbins);
+      bin = bin < 0 ? 0 : (bin >= a.nbins ? a.nbins - 1 : bin);
+#if defined(__CUDA_ARCH__) && !defined(CWTB_HOST_EMU)
+      atomicAdd(&a.hist[(size_t)by * a.nbins + bin], 1ull);
+#else
+      a.hist[(size_t)by * a.nbins + bin] += 1ull;
+#endif
+    }
+  }
+};
+
+// ---- Body: |W|^2 and its row means (device-side derived products) ---------------
+template <typename T> struct PowerArgs {
+  const cx<T> *W;
+  double *power;     // [rows][n] or null
+  double *rowsum;    // [rows] accumulated with atomics, or null
+  long long n;
+};
+template <typename T> struct PowerBody {
+  using Args = PowerArgs<T>;
+  static constexpr int NPHASE = 1;
+  static constexpr size_t SMEM = 0;
+  template <int PH> HD static void phase(const Args &a, int bx, int by, int tid, void *) {
+    // each thread covers 8 columns; one atomic per thread for the row sum
+    double acc = 0;
+    for (int i = 0; i < 8; ++i) {
+      const long long n = ((long long)bx * 8 + i) * NT + tid;
+      if (n >= a.n) break;
+      const cx<T> w = a.W[(size_t)by * a.n + n];
+      const double p = (double)w.x * w.x + (double)w.y * w.y;
+      if (a.power) a.power[(size_t)by * a.n + n] = p;
+      acc += p;
+    }
+    if (a.rowsum) {
+#if defined(__CUDA_ARCH__) && !defined(CWTB_HOST_EMU)
+      atomicAdd(&a.rowsum[by], acc);
+#else
+      a.rowsum[by] += acc;
+#endif
+    }
+  }
+};
+
+// ---- Body: real -> complex widening / complex -> real part ---------------------------------
+struct R2CArgs { const double *in; double2 *out; long long count; };
+struct R2CBody {
+  using Args = R2CArgs;
+  static constexpr int NPHASE = 1;
+  static constexpr size_t SMEM = 0;
+  template <int PH> HD static void phase(const Args &a, int bx, int, int tid, void *) {
+    const long long i = (long long)bx * NT + tid;
+    if (i < a.count) a.out[i] = make_double2(a.in[i], 0.0);
   }
 };
 

@@ -81,6 +81,23 @@ def main():
     save("nino3_custom_freqs", x=nino, dt=0.25, freqs_in=fr, W=W, sj=sj, freqs=freqs,
          coi=coi)
 
+    # significance() for the three test kinds + helper functions (host-side O(S) rows)
+    mother = pycwt.Morlet(6)
+    W, sj, freqs, coi, fft, fftfreqs = pycwt.cwt(nino, 0.25, 0.25, 0.5, 28, mother)
+    std = nino.std()
+    dat_norm = nino / std
+    alpha = ar1(nino)[0]
+    s0_, f0_ = pycwt.significance(1.0, 0.25, sj, 0, alpha, significance_level=0.95, wavelet=mother)
+    s1_, f1_ = pycwt.significance(std ** 2, 0.25, sj, 1, alpha, significance_level=0.95,
+                                  dof=nino.size - sj, wavelet=mother)
+    s2_, f2_ = pycwt.significance(std ** 2, 0.25, sj, 2, alpha, significance_level=0.95,
+                                  dof=[sj[3], sj[13]], wavelet=mother)
+    s3_, f3_ = pycwt.significance(dat_norm, 0.25, sj, 0, significance_level=0.9, wavelet=mother)
+    from pycwt.helpers import ar1_spectrum, rect
+    save("significance_nino3", x=nino, sj=sj, alpha=alpha, ar1_full=np.array(ar1(nino)),
+         s0=s0_, f0=f0_, s1=s1_, f1=f1_, s2=s2_, f2=f2_, s3=s3_, f3=f3_,
+         spec=ar1_spectrum(freqs * 0.25, alpha), rect7=rect(7, normalize=True), rect2=rect(2))
+
     # xwt / wct on the AO x Baltic sample (sample_xwt.py preprocessing minus boxpdf,
     # which raises NameError in the reference)
     t1, s1 = np.loadtxt(os.path.join(REF, "pycwt/sample/jao.dat"), unpack=True)

@@ -1,0 +1,69 @@
+"""World-size-2 gloo test (CPU) of the multi-GPU plumbing: channel sharding, gather of the
+reduced per-channel spectra, max-over-ranks timing.  The per-rank GPU transform is replaced
+by a stand-in so the test needs no device; the GPU path of the same code is covered by
+bench.py --gpus N and tests/test_gpu_xwt_wct.py::test_cwt_batch_channels."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from pycwt_b200.distributed import shard_range
+
+
+def test_shard_range_partitions():
+    for n in (0, 1, 7, 8, 8192, 8193):
+        for world in (1, 2, 3, 8):
+            blocks = [shard_range(n, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
+            sizes = [hi - lo for lo, hi in blocks]
+            assert max(sizes) - min(sizes) <= 1
+
+
+class _FakeEngine(object):
+    """Stands in for pycwt_b200.Engine on a box without a GPU: deterministic 'spectra'."""
+
+    def cwt_batch(self, X, dt, scales, family, param, precision, want_power=True, want_w=False):
+        return (X[:, :1] ** 2) * np.asarray(scales)[None, :] + X.sum(axis=1, keepdims=True), None
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from pycwt_b200 import distributed as D
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rs = np.random.RandomState(0)
+        X = rs.randn(7, 32)           # 7 channels over 2 ranks: 4 + 3
+        sj = np.arange(1.0, 6.0)
+        full = D.cwt_batch_sharded(X, 1.0, sj, 0, 6.0, 0, _FakeEngine(), dist)
+        ref, _ = _FakeEngine().cwt_batch(X, 1.0, sj, 0, 6.0, 0)
+        ok = full.shape == (7, 5) and np.array_equal(full, ref)
+        t = D.max_over_ranks(1.0 + rank, dist)
+        q.put((rank, bool(ok), t))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gather_gloo():
+    torch = pytest.importorskip("torch")
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, True, 2.0), (1, True, 2.0)]
