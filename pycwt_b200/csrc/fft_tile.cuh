@@ -63,12 +63,57 @@ template <typename T, int K> struct Lay {
   static constexpr int TILE = TileCfg<T>::TILE;
   static constexpr int P = TILE / K;
   static constexpr int Q = TileCfg<T>::Q;
-  static constexpr bool SKEW = (P < Q);  // last pass mixes b and position lanes
-  static constexpr int KS = SKEW ? K + K / 16 : K;
-  static constexpr int PITCH = SKEW ? (KS - (KS % Q) + 2 + ((KS % Q) > 2 ? Q : 0)) : K + 1;
+  // Rows are contiguous (so a bulk-async copy can fill one).  Pitch K+1 makes the b-lanes of
+  // the last pass hit distinct banks when P >= Q; for P = Q/2 the pitch K+2 spreads the b-lanes
+  // over every second bank group and the two positions sharing a quarter-warp collide 2-way on
+  // the last pass's reads only (shared-memory bandwidth has headroom).
+  static constexpr int PITCH = (P < Q) ? K + 2 : K + 1;
   static constexpr int ELEMS = P * PITCH;
-  static constexpr size_t BYTES = (Plan<K>::NP == 1) ? 0 : (size_t)ELEMS * 2 * sizeof(T);
-  HD static int phys(int b, int pos) { return b * PITCH + pos + (SKEW ? (pos >> 4) : 0); }
+  static constexpr size_t TILE_BYTES = (size_t)ELEMS * 2 * sizeof(T);
+  static constexpr size_t BYTES = (Plan<K>::NP == 1) ? 0 : TILE_BYTES;
+  HD static int phys(int b, int pos) { return b * PITCH + pos; }
+};
+
+// ---- bulk asynchronous copy (TMA, cp.async.bulk) global -> shared with an mbarrier --------
+// One thread arms the barrier with the expected byte count and issues the copies; every
+// thread then waits on the barrier's phase.  Host emulation: plain memcpy, wait is a no-op.
+struct TileBarrier {
+  unsigned long long *bar;  // 8-byte slot in shared memory
+  HD void init_and_expect(unsigned bytes) const {
+#if defined(__CUDA_ARCH__) && !defined(CWTB_HOST_EMU)
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+#else
+    (void)bytes;
+#endif
+  }
+  // dst (shared) and src (global) 16-byte aligned, bytes a multiple of 16
+  HD void copy(void *dst, const void *src, unsigned bytes) const {
+#if defined(__CUDA_ARCH__) && !defined(CWTB_HOST_EMU)
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(d), "l"(src), "r"(bytes), "r"(a) : "memory");
+#else
+    const char *s_ = (const char *)src;
+    char *d_ = (char *)dst;
+    for (unsigned i = 0; i < bytes; ++i) d_[i] = s_[i];
+#endif
+  }
+  HD void wait(unsigned parity) const {
+#if defined(__CUDA_ARCH__) && !defined(CWTB_HOST_EMU)
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned done = 0;
+    while (!done) {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                   "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    }
+#else
+    (void)parity;
+#endif
+  }
 };
 
 template <typename V> HD V ldg(const V *p) {

@@ -210,18 +210,32 @@ template <typename T, int SIGN> struct PassBBody {
   static constexpr int K = K2C;
   using LY = Lay<T, K>;
   static constexpr int NP = Plan<K>::NP;
-  static constexpr int NPHASE = NP;
-  static constexpr size_t SMEM = LY::BYTES;
+  // phase 0: one thread issues the bulk-async (TMA) copies of the tile's rows -- the rows
+  // Z[u0 .. u0+P) are contiguous in global memory -- then the FFT passes run from shared memory
+  static constexpr int NPHASE = NP + 1;
+  static constexpr size_t SMEM = LY::TILE_BYTES + 16;
   template <int PH> HD static void phase(const Args &a, int bx, int by, int tid, void *smraw) {
     V *sm = (V *)smraw;
     const int U = (int)(a.N / K);
     const int u0 = bx * LY::P;
+    TileBarrier tb;
+    tb.bar = (unsigned long long *)((char *)smraw + LY::TILE_BYTES);
     if (PH == 0) {
-      RowLoader<T, K> ld;
-      ld.src = a.Z + (size_t)by * a.N + (size_t)u0 * K;
-      ld.nvalid = U - u0;
+      const int nvalid = (U - u0) < LY::P ? (U - u0) : LY::P;
+      if (tid == 0) {
+        tb.init_and_expect((unsigned)(nvalid * K * sizeof(V)));
+        const V *src = a.Z + (size_t)by * a.N + (size_t)u0 * K;
+        for (int b = 0; b < nvalid; ++b)
+          tb.copy(sm + LY::phys(b, 0), src + (size_t)b * K, (unsigned)(K * sizeof(V)));
+      }
+      for (int b = nvalid; b < LY::P; ++b)
+        for (int i = tid; i < K; i += NT) sm[LY::phys(b, i)] = mk<T>(0, 0);
+    } else if (PH == 1) {
+      tb.wait(0);
+      SmemLoader<T, K> ld;
+      ld.sm = sm;
       tile_first<T, K, SIGN>(sm, a.tw, ld, tid);
-    } else if (PH == 1 && NP == 3) {
+    } else if (PH == 2 && NP == 3) {
       tile_second<T, K, SIGN>(sm, a.tw, tid);
     } else {
       const int row = a.descs ? a.descs[a.first + by].row : a.row0 + by;
