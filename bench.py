@@ -28,6 +28,9 @@ sys.path.insert(0, ROOT)
 N0 = 2 ** 20
 DT, S0, DJ, J = 1.0, 2.0, 1.0 / 16, 255
 F0 = 6.0
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernels, from the
+# `ncu --set full` captures summarised under profiles/ (filled in per round; None = not captured)
+TRAFFIC = {}
 METRIC = "cwt_scale_points_per_sec"
 UNIT = "scale-points/s"
 
@@ -217,10 +220,13 @@ def run_ours(args):
     ms_max = dist_max(dist, local, ms)
     value = world * pts / (ms_max * 1e-3)
 
+    prof = eng.profile_last()    # per-kernel-type event times of one more (untimed) step
     if args.kernels_only:   # for ncu: no e2e leg, no CPU baseline
         if rank == 0:
             print(json.dumps({"kernels_only": True, "ms_per_step": ms_max, "value": value,
-                              "launches_per_step": launches_per_step}))
+                              "launches_per_step": launches_per_step,
+                              "kernels": {k["name"]: [k["launches"], round(k["ms"], 4), k["rows"]]
+                                          for k in prof}}))
         return
 
     # ---- e2e: public API, host buffers, H2D + D2H inside the timed region ----
@@ -243,6 +249,19 @@ def run_ours(args):
         sample = 32
         cores = 1
         cpu_v, cpu_t = cpu_baseline(sample, cores) if world == 1 or True else (None, None)
+        # dominant kernel = the type with the largest share of the step; the kernels that
+        # write W (Single/Direct/PassB) carry 16 B of algorithmic bytes per scale-point,
+        # PassA/Band launches are intermediate work of the same scales (0 algorithmic bytes).
+        writers = [k for k in prof if k["name"].split("<")[0] in ("SingleBody", "DirectBody", "PassBBody")
+                   and not k["name"].endswith("-1>")]
+        dom = max(prof, key=lambda k: k["ms"])
+        domw = max(writers, key=lambda k: k["ms"])
+        kern_ms = sum(k["ms"] for k in prof)
+        dom_bytes = domw["rows"] * N0 * 16
+        dom_rf = {"kernel": domw["name"], "launches_per_step": domw["launches"],
+                  "ms_per_step": domw["ms"], "share_of_step": domw["ms"] / kern_ms,
+                  "rows": domw["rows"], "algorithmic_bytes": dom_bytes,
+                  "achieved": dom_bytes / (domw["ms"] * 1e-3) / 1e9}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max,
@@ -252,10 +271,18 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(pts * 16), "ms_per_step": 1e3 * t_e2e,
                     "steps": e2e_steps},
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "kernel": "whole step (forward FFT + all per-scale inverse transforms)",
-                         "algorithmic_bytes": alg_bytes},
+            "roofline": {"bound": "hbm", "achieved": dom_rf["achieved"], "peak": peak, "unit": "GB/s",
+                         "frac": dom_rf["achieved"] / peak, "traffic": TRAFFIC.get(domw["name"].split("<")[0]),
+                         "peak_source": peak_src, "kernel": dom_rf["kernel"],
+                         "launches_per_step": dom_rf["launches_per_step"],
+                         "ms_per_step": dom_rf["ms_per_step"], "share_of_step": dom_rf["share_of_step"],
+                         "algorithmic_bytes_per_step": dom_bytes,
+                         "largest_kernel_any": dom["name"],
+                         "step": {"achieved": achieved, "frac": achieved / peak,
+                                  "algorithmic_bytes": alg_bytes,
+                                  "note": "whole step: forward FFT + all per-scale inverse transforms"},
+                         "kernels": {k["name"]: {"launches": k["launches"], "ms": round(k["ms"], 4),
+                                                 "rows": k["rows"]} for k in prof}},
             "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": "%d of 256 scales (evenly spread), full N=2^20; "
                                        "%.1f s" % (sample, cpu_t)},

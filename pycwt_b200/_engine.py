@@ -3,6 +3,7 @@ fallback: if the CUDA library or a device is missing, calls raise EngineError.""
 import ctypes
 import os
 import threading
+import weakref
 
 import numpy as np
 
@@ -41,6 +42,7 @@ _SIGNATURES = {
     "cwtb_last_launch_count": (_I, [_P]),
     "cwtb_last_plan": (_I, [_P, _P, _I]),
     "cwtb_bench_last": (_I, [_P, _I, ctypes.POINTER(_D)]),
+    "cwtb_profile_last": (_I, [_P, ctypes.c_char_p, ctypes.c_size_t]),
     "cwtb_dev_alloc": (_I, [_P, ctypes.c_size_t, ctypes.POINTER(_P)]),
     "cwtb_dev_free": (_I, [_P, _P]),
     "cwtb_memcpy_h2d": (_I, [_P, _P, _P, ctypes.c_size_t]),
@@ -92,9 +94,12 @@ class Engine(object):
         self.h = h
         self.device = device
         self.lock = threading.Lock()
+        self._pool = {}          # nbytes -> [pointers of idle pinned buffers]
+        self._pool_bytes = 0
+        self._outstanding = 0    # result arrays still alive that alias pinned memory
 
     def close(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and self._outstanding == 0:
             self.lib.cwtb_destroy(self.h)
             self.h = None
 
@@ -129,6 +134,43 @@ class Engine(object):
     def pinned_free(self, p):
         self.lib.cwtb_host_free(self.h, p)
 
+    #: results at least this large are returned in page-locked memory (D2H at PCIe speed)
+    PINNED_MIN_BYTES = 1 << 20
+    POOL_MAX_BYTES = 12 << 30
+
+    def result_array(self, shape, dtype):
+        """Array for a transform result.  Large results alias pinned host memory taken
+        from a per-engine pool; the buffer returns to the pool when the array (and every
+        view of it) is garbage-collected, so steady-state calls neither allocate nor pin."""
+        dtype = np.dtype(dtype)
+        count = int(np.prod(shape))
+        nbytes = count * dtype.itemsize
+        if nbytes < self.PINNED_MIN_BYTES:
+            return np.empty(shape, dtype=dtype)
+        idle = self._pool.setdefault(nbytes, [])
+        if idle:
+            addr = idle.pop()
+            self._pool_bytes -= nbytes
+        else:
+            p = _P()
+            self._check(self.lib.cwtb_host_alloc(self.h, nbytes, ctypes.byref(p)))
+            addr = p.value
+        buf = (ctypes.c_char * nbytes).from_address(addr)
+        self._outstanding += 1
+        fin = weakref.finalize(buf, self._release, nbytes, addr)
+        fin.atexit = False
+        return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+
+    def _release(self, nbytes, addr):
+        self._outstanding -= 1
+        if self.h is None:
+            return
+        if self._pool_bytes + nbytes <= self.POOL_MAX_BYTES and len(self._pool.get(nbytes, [])) < 2:
+            self._pool.setdefault(nbytes, []).append(addr)
+            self._pool_bytes += nbytes
+        else:
+            self.lib.cwtb_host_free(self.h, _P(addr))
+
     # ---- transform ------------------------------------------------------------------
     def cwt(self, signal, dt, scales, family, param, precision=F64, table=None,
             fetch=True, out_f64=True):
@@ -154,7 +196,7 @@ class Engine(object):
 
     def get_w(self, nrows, n0, precision=F64, out_f64=True):
         dtype = np.complex128 if (precision == F64 or out_f64) else np.complex64
-        W = np.empty((nrows, n0), dtype=dtype)
+        W = self.result_array((nrows, n0), dtype)
         self._check(self.lib.cwtb_get_w(self.h, _ptr(W), 1 if out_f64 else 0, 0, nrows))
         return W
 
@@ -222,7 +264,7 @@ class Engine(object):
         if y1.shape != y2.shape or y1.ndim != 1:
             raise ValueError("xwt: the two series must be 1-D and of equal length")
         sj = np.ascontiguousarray(scales, dtype=np.float64)
-        out = np.empty((sj.size, y1.size), dtype=np.complex128)
+        out = self.result_array((sj.size, y1.size), np.complex128)
         with self.lock:
             self._check(self.lib.cwtb_xwt(self.h, _ptr(y1), _ptr(y2), y1.size, float(dt), _ptr(sj),
                                           sj.size, int(family), float(param), _ptr(out)))
@@ -234,8 +276,8 @@ class Engine(object):
         if y1.shape != y2.shape or y1.ndim != 1:
             raise ValueError("wct: the two series must be 1-D and of equal length")
         sj = np.ascontiguousarray(scales, dtype=np.float64)
-        WCT = np.empty((sj.size, y1.size), dtype=np.float64)
-        aWCT = np.empty((sj.size, y1.size), dtype=np.float64) if want_angle else None
+        WCT = self.result_array((sj.size, y1.size), np.float64)
+        aWCT = self.result_array((sj.size, y1.size), np.float64) if want_angle else None
         with self.lock:
             self._check(self.lib.cwtb_wct(self.h, _ptr(y1), _ptr(y2), y1.size, float(dt), float(dj),
                                           _ptr(sj), sj.size, int(family), float(param),
@@ -311,6 +353,19 @@ class Engine(object):
         ms = _D()
         self._check(self.lib.cwtb_bench_last(self.h, int(iters), ctypes.byref(ms)))
         return ms.value
+
+    def profile_last(self):
+        """Per-kernel-type device times of one pass of the last cwt_dev transform:
+        list of dicts {name, launches, ms, rows}."""
+        buf = ctypes.create_string_buffer(1 << 16)
+        n = self.lib.cwtb_profile_last(self.h, buf, len(buf))
+        if n < 0:
+            self._check(n)
+        out = []
+        for line in buf.value.decode().splitlines():
+            name, nl, ms, rows = line.rsplit("|", 3)
+            out.append({"name": name, "launches": int(nl), "ms": float(ms), "rows": int(rows)})
+        return out
 
     def sync(self):
         self._check(self.lib.cwtb_sync(self.h))

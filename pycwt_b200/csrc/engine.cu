@@ -6,6 +6,7 @@
 // Build (CPU emulation of the kernels, TESTS ONLY, never shipped/loaded by the package):
 //                    nvcc -std=c++17 -O2 -DCWTB_HOST_EMU ... -o libcwtb200_emu.so
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -63,8 +64,16 @@ __device__ __forceinline__ void run_phases(const typename Body::Args &a, void *s
     run_phases<Body, PH + 1>(a, sm);
   }
 }
+template <class Body, int PH>
+__device__ __forceinline__ void run_phases_at(const typename Body::Args &a, int bx, int by, void *sm) {
+  Body::template phase<PH>(a, bx, by, (int)threadIdx.x, sm);
+  if constexpr (PH + 1 < Body::NPHASE) {
+    __syncthreads();
+    run_phases_at<Body, PH + 1>(a, bx, by, sm);
+  }
+}
 template <class Body>
-__global__ void __launch_bounds__(NT) k_run(const __grid_constant__ typename Body::Args a) {
+__global__ void __launch_bounds__(NT, CWTB_MINB) k_run(const __grid_constant__ typename Body::Args a) {
   extern __shared__ __align__(16) unsigned char smraw[];
   run_phases<Body, 0>(a, smraw);
 }
@@ -111,22 +120,36 @@ struct cwtb_ctx {
   rt_stream copy_stream{};
   std::string err;
   double band_eps = 1e-20;
-  int group = 4;  // scales per two-kernel chunk
+  int group = 32;  // scales per two-kernel chunk (unfused path)
+  int l2_persist = 0;
+  int direct_max_log2 = 13;
+  int fused = 0;     // experimental: two-kernel scales through one persistent kernel (CWTB_FUSED=1)
+  int ring = 3;      // Z ring slots of the fused kernel
+  int num_sms = 148;  // K' <= 2^13 handled by one kernel (K' > 1024: DirectBody)
   double2 *tw64 = nullptr;
   float2 *tw32 = nullptr;
   std::map<unsigned, NTabDev> ntabs;
-  Buf sig, sig2, spec, Z, B, W, W2, descs, table, scratch, C, A12, F, aux, rowd, win, mask, hist, noise;
+  Buf ctr, sig, sig2, spec, Z, B, W, W2, descs, table, scratch, C, A12, F, aux, rowd, win, mask, hist, noise;
   Job job;
   const void *job_dsig = nullptr;  // device signal of the last cwt_dev call (not owned)
   double last_ms = 0;
   int launches = 0;
   std::set<const void *> configured;
+  // per-launch event profiling (cwtb_profile_last)
+  bool profiling = false;
+  struct ProfRec { std::string name; unsigned gx, gy; int ev; };
+  std::vector<ProfRec> prof;
+#ifndef CWTB_HOST_EMU
+  std::vector<cudaEvent_t> prof_events;
+#endif
   std::set<void *> pinned, devallocs;
 #ifndef CWTB_HOST_EMU
   cudaEvent_t e0{}, e1{};
 #endif
 };
 
+static int fail(cwtb_ctx *c, int code, const std::string &msg);
+static void apply_l2_policy(cwtb_ctx *c);
 static int fail(cwtb_ctx *c, int code, const std::string &msg) {
   if (c) c->err = msg;
   return code;
@@ -137,6 +160,31 @@ static int fail(cwtb_ctx *c, int code, const std::string &msg) {
     if (e_ != 0) return fail(c, CWTB_ERR_CUDA, std::string(#call) + ": " + rt_errstr(e_));   \
   } while (0)
 
+// Keep the Z buffer (intermediate of the two-kernel scales) resident in L2: persisting access
+// policy window on the engine's stream; everything else keeps the default policy and W is
+// written with streaming stores.  Re-applied whenever Z is (re)allocated.
+static void apply_l2_policy(cwtb_ctx *c) {
+#ifndef CWTB_HOST_EMU
+  if (!c->l2_persist || !c->Z.p) return;
+  int max_persist = 0, max_window = 0;
+  cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, c->device);
+  cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, c->device);
+  if (max_persist <= 0 || max_window <= 0) return;
+  const size_t want = std::min<size_t>(c->Z.bytes, (size_t)max_persist);
+  cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+  cudaStreamAttrValue v{};
+  v.accessPolicyWindow.base_ptr = c->Z.p;
+  v.accessPolicyWindow.num_bytes = std::min<size_t>(c->Z.bytes, (size_t)max_window);
+  v.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)want / (double)v.accessPolicyWindow.num_bytes);
+  v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &v);
+  cudaGetLastError();
+#else
+  (void)c;
+#endif
+}
+
 static int ensure(cwtb_ctx *c, Buf &b, size_t bytes) {
   if (b.bytes >= bytes && b.p) return 0;
   if (b.p) rt_free(b.p);
@@ -144,6 +192,7 @@ static int ensure(cwtb_ctx *c, Buf &b, size_t bytes) {
   b.bytes = 0;
   if (rt_malloc(&b.p, bytes) != 0) return fail(c, CWTB_ERR_NOMEM, "device allocation failed");
   b.bytes = bytes;
+  if (&b == &c->Z) apply_l2_policy(c);
   return 0;
 }
 
@@ -157,6 +206,18 @@ static void emu_phases(const typename Body::Args &a, int bx, int by, void *sm) {
   if constexpr (PH + 1 < Body::NPHASE) emu_phases<Body, PH + 1>(a, bx, by, sm);
 }
 #endif
+
+// "... [with Body = cwtb::PassBBody<double, 1>]"  ->  "PassBBody<double, 1>"
+static std::string body_name(const char *pretty) {
+  std::string s(pretty);
+  size_t i = s.find("Body = ");
+  if (i == std::string::npos) return s;
+  s = s.substr(i + 7);
+  size_t j = s.find_first_of(";]");
+  if (j != std::string::npos) s = s.substr(0, j);
+  if (s.rfind("cwtb::", 0) == 0) s = s.substr(6);
+  return s;
+}
 
 template <class Body>
 static int launch(cwtb_ctx *c, unsigned gx, unsigned gy, const typename Body::Args &a) {
@@ -175,8 +236,20 @@ static int launch(cwtb_ctx *c, unsigned gx, unsigned gy, const typename Body::Ar
   }
   // gridDim.y is limited to 65535
   if (gy > 65535) return fail(c, CWTB_ERR_ARG, "too many rows in one launch");
+  int ev = -1;
+  if (c->profiling) {
+    ev = (int)c->prof.size() * 2;
+    while ((int)c->prof_events.size() < ev + 2) {
+      cudaEvent_t e;
+      RT(cudaEventCreate(&e));
+      c->prof_events.push_back(e);
+    }
+    c->prof.push_back({body_name(__PRETTY_FUNCTION__), gx, gy, ev});
+    RT(cudaEventRecord(c->prof_events[ev], c->stream));
+  }
   k_run<Body><<<dim3(gx, gy), NT, Body::SMEM, c->stream>>>(a);
   RT(cudaGetLastError());
+  if (ev >= 0) RT(cudaEventRecord(c->prof_events[ev + 1], c->stream));
   c->launches++;
   return 0;
 #endif
@@ -191,9 +264,10 @@ static int make_table(cwtb_ctx *c, double2 *o64, float2 *o32, unsigned count, do
 }
 
 static int init_tables(cwtb_ctx *c) {
-  RT(rt_malloc((void **)&c->tw64, sizeof(double2) * KT));
-  RT(rt_malloc((void **)&c->tw32, sizeof(float2) * KT));
-  return make_table(c, c->tw64, c->tw32, KT, 1.0 / KT);
+  RT(rt_malloc((void **)&c->tw64, sizeof(double2) * TW_TOTAL));
+  RT(rt_malloc((void **)&c->tw32, sizeof(float2) * TW_TOTAL));
+  PassTwArgs a{c->tw64, c->tw32};
+  return launch<PassTwBody>(c, (TW_TOTAL + NT - 1) / NT, 1, a);
 }
 
 static int get_ntab(cwtb_ctx *c, unsigned N, int log2N, NTab *out) {
@@ -339,9 +413,9 @@ static int build_job(cwtb_ctx *c, Job &job, long long n0, double dt, const doubl
     long long lo = std::min<long long>(klo, 0), hi = std::max<long long>(khi, 0);
     if (khi < klo) { lo = 0; hi = 0; }
     int lk = std::max(5, ilog2((unsigned long long)(hi - lo + 1)));
-    if (lk > 10) {  // two-kernel path: negative part must be a multiple of K2
+    if (lk > c->direct_max_log2) {  // two-kernel path: negative part must be a multiple of K2
       lo = -((-lo + K2C - 1) / K2C) * K2C;
-      lk = std::max(11, ilog2((unsigned long long)(hi - lo + 1)));
+      lk = std::max(c->direct_max_log2 + 1, ilog2((unsigned long long)(hi - lo + 1)));
     }
     if (lk >= job.log2N) {  // dense
       lk = job.log2N;
@@ -365,7 +439,7 @@ static int build_job(cwtb_ctx *c, Job &job, long long n0, double dt, const doubl
     if (job.classes.empty() || job.classes.back().log2K != d.log2K)
       job.classes.push_back(ClassRun{d.log2K, i, 0});
     job.classes.back().count++;
-    if (d.log2K <= 10) {  // single-kernel scale: own slot in the band buffer
+    if (d.log2K <= 10 || (d.log2K <= c->direct_max_log2 && d.log2K < job.log2N)) {  // single-kernel scale
       d.boff = (long long)boff;
       boff += (size_t)1 << d.log2K;
     }
@@ -455,18 +529,170 @@ static int fft_rows(cwtb_ctx *c, const void *in, int real_in, long long in_pitch
     const int nr = std::min(chunk, nrows - r0);
     PassAArgs<T> a{};
     a.in = in; a.Z = (cx<T> *)c->Z.p; a.tw = Tw<T>::get(c); a.nt = nt;
-    a.in_pitch = in_pitch; a.n_in = n_in; a.N = n; a.first = 0; a.row0 = r0;
+    a.in_pitch = in_pitch; a.n_in = n_in; a.N = n; a.first = 0; a.row0 = r0; a.zmod = 1 << 30;
     e = real_in ? dispatch_passA<T, SIGN, MODE_REAL>(c, l2 - 10, a, nr)
                 : dispatch_passA<T, SIGN, MODE_CPLX>(c, l2 - 10, a, nr);
     if (e) return e;
     PassBArgs<T> b{};
     b.Z = (const cx<T> *)c->Z.p; b.out = out; b.tw = Tw<T>::get(c); b.descs = nullptr;
     b.pitch = out_pitch; b.nout = nout; b.N = n; b.first = 0; b.row0 = r0;
-    b.epi = grow ? EPI_GAUSS : EPI_STORE; b.grow = grow; b.post = post;
+    b.epi = grow ? EPI_GAUSS : EPI_STORE; b.grow = grow; b.post = post; b.zmod = 1 << 30;
     e = launch<PassBBody<T, SIGN>>(c, (n / K2C + Lay<T, K2C>::P - 1) / Lay<T, K2C>::P, nr, b);
     if (e) return e;
   }
   return 0;
+}
+
+// ======================================================================================
+// fused persistent two-pass kernel: PassA and PassB tiles of every scale of one class run in
+// ONE launch.  A global tile queue is consumed in the order
+//     A(0) A(1) B(0) A(2) B(1) ... A(n-1) B(n-2) B(n-1)
+// (A(s)/B(s) = all tiles of scale s); B(s) waits for the A(s) tiles through a global counter,
+// A(s) waits for B(s-ring) before reusing its Z slot.  Z is a ring of `ring` scale buffers
+// (ring * 16 MiB at Np = 2^20) that lives in L2, so the intermediate never goes to HBM and
+// there are no per-scale launch tails.
+// ======================================================================================
+template <typename T> struct FusedArgs {
+  PassAArgs<T> a;
+  PassBArgs<T> b;
+  unsigned *ctr;    // [0] queue head, [1 .. n] doneA, [1+n .. 2n] doneB
+  int nscales, ring;
+  unsigned tilesA, tilesB;
+};
+
+// position t of the queue -> (isB, scale, tile)
+HD void fused_decode(unsigned t, int n, unsigned TA, unsigned TB, int *isB, int *s, unsigned *tile) {
+  if (t < TA) { *isB = 0; *s = 0; *tile = t; return; }
+  t -= TA;
+  const unsigned per = TA + TB;
+  const unsigned blk = t / per, off = t % per;
+  if ((int)blk < n - 1) {
+    if (off < TA) { *isB = 0; *s = (int)blk + 1; *tile = off; }
+    else { *isB = 1; *s = (int)blk; *tile = off - TA; }
+  } else {  // tail: B(n-1)
+    *isB = 1; *s = n - 1; *tile = t - (unsigned)(n - 1) * per;
+  }
+}
+
+#ifndef CWTB_HOST_EMU
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+template <typename T, int K1, int MODE>
+__global__ void __launch_bounds__(NT, 3) k_fused(const __grid_constant__ FusedArgs<T> f) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  __shared__ unsigned s_t;
+  using A = PassABody<T, K1, MODE, +1>;
+  using B = PassBBody<T, +1>;
+  const int n = f.nscales;
+  const unsigned total = (unsigned)n * (f.tilesA + f.tilesB);
+  unsigned *doneA = f.ctr + 1, *doneB = f.ctr + 1 + n;
+  for (;;) {
+    __syncthreads();  // previous tile's shared memory is free
+    if (threadIdx.x == 0) s_t = atomicAdd(f.ctr, 1u);
+    __syncthreads();
+    const unsigned t = s_t;
+    if (t >= total) break;
+    int isB, s;
+    unsigned tile;
+    fused_decode(t, n, f.tilesA, f.tilesB, &isB, &s, &tile);
+    if (threadIdx.x == 0) {
+      if (isB) {
+        while (ld_acquire_u32(&doneA[s]) < f.tilesA) __nanosleep(100);
+      } else if (s >= f.ring) {
+        while (ld_acquire_u32(&doneB[s - f.ring]) < f.tilesB) __nanosleep(100);
+      }
+      asm volatile("fence.proxy.async;" ::: "memory");
+    }
+    __syncthreads();
+    if (isB) run_phases_at<B, 0>(f.b, (int)tile, s, smraw);
+    else run_phases_at<A, 0>(f.a, (int)tile, s, smraw);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      atomicAdd(isB ? &doneB[s] : &doneA[s], 1u);
+    }
+  }
+}
+#endif
+
+template <typename T, int K1, int MODE>
+static int launch_fused(cwtb_ctx *c, const PassAArgs<T> &a, const PassBArgs<T> &b, int nscales) {
+  using A = PassABody<T, K1, MODE, +1>;
+  using B = PassBBody<T, +1>;
+  FusedArgs<T> f;
+  f.a = a; f.b = b;
+  f.nscales = nscales;
+  f.ring = c->ring;
+  f.a.zmod = f.b.zmod = c->ring;
+  const unsigned M = a.N / ((unsigned)K1 * K2C);
+  f.tilesA = M * A::NTILE2;
+  f.tilesB = (a.N / K2C + Lay<T, K2C>::P - 1) / Lay<T, K2C>::P;
+  int e = ensure(c, c->ctr, (size_t)(1 + 2 * nscales) * sizeof(unsigned));
+  if (e) return e;
+  f.ctr = (unsigned *)c->ctr.p;
+  RT(rt_memset(c->ctr.p, 0, (size_t)(1 + 2 * nscales) * sizeof(unsigned), c->stream));
+#ifdef CWTB_HOST_EMU
+  std::vector<unsigned char> sm(std::max(A::SMEM, B::SMEM) + 64);
+  const unsigned total = (unsigned)nscales * (f.tilesA + f.tilesB);
+  for (unsigned t = 0; t < total; ++t) {
+    int isB, s;
+    unsigned tile;
+    fused_decode(t, nscales, f.tilesA, f.tilesB, &isB, &s, &tile);
+    if (isB) emu_phases<B, 0>(f.b, (int)tile, s, sm.data());
+    else emu_phases<A, 0>(f.a, (int)tile, s, sm.data());
+  }
+  c->launches++;
+  return 0;
+#else
+  const size_t smem = std::max(A::SMEM, B::SMEM);
+  auto kern = k_fused<T, K1, MODE>;
+  const void *fn = (const void *)kern;
+  if (!c->configured.count(fn)) {
+    RT(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    c->configured.insert(fn);
+  }
+  int occ = 0;
+  RT(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
+  if (occ < 1) return fail(c, CWTB_ERR_CUDA, "fused kernel does not fit on an SM");
+  const unsigned total = (unsigned)nscales * (f.tilesA + f.tilesB);
+  const unsigned grid = std::min<unsigned>(total, (unsigned)(occ * c->num_sms));
+  int ev = -1;
+  if (c->profiling) {
+    ev = (int)c->prof.size() * 2;
+    while ((int)c->prof_events.size() < ev + 2) {
+      cudaEvent_t e2;
+      RT(cudaEventCreate(&e2));
+      c->prof_events.push_back(e2);
+    }
+    c->prof.push_back({body_name(__PRETTY_FUNCTION__), grid, (unsigned)nscales, ev});
+    RT(cudaEventRecord(c->prof_events[ev], c->stream));
+  }
+  kern<<<grid, NT, smem, c->stream>>>(f);
+  RT(cudaGetLastError());
+  if (ev >= 0) RT(cudaEventRecord(c->prof_events[ev + 1], c->stream));
+  c->launches++;
+  return 0;
+#endif
+}
+
+template <typename T, int MODE>
+static int dispatch_fused(cwtb_ctx *c, int log2K1, const PassAArgs<T> &a, const PassBArgs<T> &b, int n) {
+  switch (log2K1) {
+    case 1: return launch_fused<T, 2, MODE>(c, a, b, n);
+    case 2: return launch_fused<T, 4, MODE>(c, a, b, n);
+    case 3: return launch_fused<T, 8, MODE>(c, a, b, n);
+    case 4: return launch_fused<T, 16, MODE>(c, a, b, n);
+    case 5: return launch_fused<T, 32, MODE>(c, a, b, n);
+    case 6: return launch_fused<T, 64, MODE>(c, a, b, n);
+    case 7: return launch_fused<T, 128, MODE>(c, a, b, n);
+    case 8: return launch_fused<T, 256, MODE>(c, a, b, n);
+    case 9: return launch_fused<T, 512, MODE>(c, a, b, n);
+    case 10: return launch_fused<T, 1024, MODE>(c, a, b, n);
+  }
+  return fail(c, CWTB_ERR_UNSUPPORTED, "transform longer than 2^20 per row is not supported yet");
 }
 
 template <typename T, int K>
@@ -506,13 +732,16 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
   NTab nt;
   if ((e = get_ntab(c, N, job.log2N, &nt))) return e;
   const int G = std::max(1, c->group);
-  const size_t bchunk = (size_t)G * (N / 2);
+  size_t bchunk = 0;   // band products of one chunk of two-kernel scales
+  for (const ClassRun &cl : job.classes)
+    if (cl.log2K > c->direct_max_log2 && cl.log2K < job.log2N)
+      bchunk = std::max(bchunk, (size_t)(c->fused ? cl.count : std::min(G, cl.count)) << cl.log2K);
   if ((e = ensure(c, c->B, (job.b_single + bchunk) * sizeof(V)))) return e;
   V *Bbuf = (V *)c->B.p;
 
   for (const ClassRun &cl : job.classes) {
     const unsigned K = 1u << cl.log2K;
-    if (cl.log2K <= 10) {
+    if (cl.log2K <= 10 || (cl.log2K <= c->direct_max_log2 && cl.log2K < job.log2N)) {
       // ---- single kernel: band product, then pruned K'-point transforms ----
       BandArgs<T> ba{ddesc, spec, Bbuf, fam, N, cl.first};
       if ((e = launch<BandBody<T>>(c, (K + NT * BandBody<T>::PER - 1) / (NT * BandBody<T>::PER), cl.count, ba)))
@@ -525,32 +754,41 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
         case 8: e = launch_single<T, 256>(c, sa, cl.count); break;
         case 9: e = launch_single<T, 512>(c, sa, cl.count); break;
         case 10: e = launch_single<T, 1024>(c, sa, cl.count); break;
+        case 11: e = launch<DirectBody<T, 2>>(c, (N / K2C + Lay<T, K2C>::P - 1) / Lay<T, K2C>::P, cl.count, sa); break;
+        case 12: e = launch<DirectBody<T, 4>>(c, (N / K2C + Lay<T, K2C>::P - 1) / Lay<T, K2C>::P, cl.count, sa); break;
+        case 13: e = launch<DirectBody<T, 8>>(c, (N / K2C + Lay<T, K2C>::P - 1) / Lay<T, K2C>::P, cl.count, sa); break;
         default: e = fail(c, CWTB_ERR_STATE, "bad single-kernel class");
       }
       if (e) return e;
       continue;
     }
-    // ---- two kernels through Z, G scales at a time ----
+    // ---- two kernels through Z ----
     const bool dense = (cl.log2K == job.log2N);
-    if ((e = ensure(c, c->Z, (size_t)G * N * sizeof(V)))) return e;
-    for (int g0 = 0; g0 < cl.count; g0 += G) {
-      const int ng = std::min(G, cl.count - g0);
+    const int chunk = c->fused ? cl.count : G;   // fused: the whole class in one persistent launch
+    if ((e = ensure(c, c->Z, (size_t)(c->fused ? c->ring : G) * N * sizeof(V)))) return e;
+    for (int g0 = 0; g0 < cl.count; g0 += chunk) {
+      const int ng = std::min(chunk, cl.count - g0);
       PassAArgs<T> a{};
       a.descs = ddesc; a.spec = spec; a.Bbuf = Bbuf; a.Z = (V *)c->Z.p; a.tw = Tw<T>::get(c);
-      a.fam = fam; a.nt = nt; a.N = N; a.first = cl.first + g0; a.row0 = 0;
-      if (dense) {
-        e = dispatch_passA<T, +1, MODE_DENSE>(c, cl.log2K - 10, a, ng);
-      } else {
-        BandArgs<T> ba{ddesc, spec, Bbuf, fam, N, cl.first + g0};
-        if ((e = launch<BandBody<T>>(c, (K + NT * BandBody<T>::PER - 1) / (NT * BandBody<T>::PER), ng, ba)))
-          return e;
-        e = dispatch_passA<T, +1, MODE_BAND>(c, cl.log2K - 10, a, ng);
-      }
-      if (e) return e;
+      a.fam = fam; a.nt = nt; a.N = N; a.first = cl.first + g0; a.row0 = 0; a.zmod = 1 << 30;
       PassBArgs<T> b{};
       b.Z = (const V *)c->Z.p; b.out = W; b.tw = Tw<T>::get(c); b.descs = ddesc;
       b.pitch = job.n0; b.nout = job.n0; b.N = N; b.first = cl.first + g0; b.row0 = 0;
-      b.epi = epi; b.grow = nullptr; b.post = 1.0;
+      b.epi = epi; b.grow = nullptr; b.post = 1.0; b.zmod = 1 << 30;
+      if (!dense) {
+        BandArgs<T> ba{ddesc, spec, Bbuf, fam, N, cl.first + g0};
+        if ((e = launch<BandBody<T>>(c, (K + NT * BandBody<T>::PER - 1) / (NT * BandBody<T>::PER), ng, ba)))
+          return e;
+      }
+      if (c->fused) {
+        e = dense ? dispatch_fused<T, MODE_DENSE>(c, cl.log2K - 10, a, b, ng)
+                  : dispatch_fused<T, MODE_BAND>(c, cl.log2K - 10, a, b, ng);
+        if (e) return e;
+        continue;
+      }
+      e = dense ? dispatch_passA<T, +1, MODE_DENSE>(c, cl.log2K - 10, a, ng)
+                : dispatch_passA<T, +1, MODE_BAND>(c, cl.log2K - 10, a, ng);
+      if (e) return e;
       if ((e = launch<PassBBody<T, +1>>(c, (N / K2C + Lay<T, K2C>::P - 1) / Lay<T, K2C>::P, ng, b))) return e;
     }
   }
@@ -561,9 +799,10 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
 static void assign_chunk_offsets(cwtb_ctx *c, Job &job) {
   const int G = std::max(1, c->group);
   for (const ClassRun &cl : job.classes) {
-    if (cl.log2K <= 10 || cl.log2K == job.log2N) continue;
+    if (cl.log2K <= c->direct_max_log2 || cl.log2K == job.log2N) continue;
     for (int i = 0; i < cl.count; ++i)
-      job.descs[cl.first + i].boff = (long long)(job.b_single + (size_t)(i % G) * ((size_t)1 << cl.log2K));
+      job.descs[cl.first + i].boff =
+          (long long)(job.b_single + (size_t)(c->fused ? i : i % G) * ((size_t)1 << cl.log2K));
   }
 }
 
@@ -647,6 +886,13 @@ int cwtb_create(int device, cwtb_ctx **out) {
 #endif
   if (const char *g = getenv("CWTB_GROUP")) c->group = std::max(1, atoi(g));
   if (const char *g = getenv("CWTB_BAND_EPS")) c->band_eps = atof(g);
+  if (const char *g = getenv("CWTB_L2_PERSIST")) c->l2_persist = atoi(g);
+  if (const char *g = getenv("CWTB_FUSED")) c->fused = atoi(g);
+  if (const char *g = getenv("CWTB_RING")) c->ring = std::max(1, atoi(g));
+#ifndef CWTB_HOST_EMU
+  cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
+#endif
+  if (const char *g = getenv("CWTB_DIRECT_MAX")) c->direct_max_log2 = std::min(13, std::max(10, atoi(g)));
   int e = init_tables(c);
   if (e == 0) e = rt_sync(c->stream) ? CWTB_ERR_CUDA : 0;
   if (e) { delete c; return e; }
@@ -660,7 +906,7 @@ void cwtb_destroy(cwtb_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
 #endif
-  for (Buf *b : {&c->sig, &c->sig2, &c->spec, &c->Z, &c->B, &c->W, &c->W2, &c->descs, &c->table, &c->scratch,
+  for (Buf *b : {&c->ctr, &c->sig, &c->sig2, &c->spec, &c->Z, &c->B, &c->W, &c->W2, &c->descs, &c->table, &c->scratch,
                  &c->C, &c->A12, &c->F, &c->aux, &c->rowd, &c->win, &c->mask, &c->hist, &c->noise})
     if (b->p) rt_free(b->p);
   for (auto &kv : c->ntabs) { rt_free(kv.second.hi); rt_free(kv.second.lo); }
@@ -1162,6 +1408,44 @@ int cwtb_wct_mc(cwtb_ctx *c, const double *noise, int n_pairs, int64_t n0, doubl
   RT(rt_sync(c->stream));
   for (size_t i = 0; i < h.size(); ++i) hist[i] += (int64_t)h[i];
   return 0;
+}
+
+// One pass of the last cwtb_cwt_dev transform with a CUDA event pair around every launch.
+// Writes one line per kernel type: "name,launches,total_ms,rows" (rows = sum of gridDim.y, i.e.
+// scale rows processed) into `out`.  Returns the number of bytes written (<= cap-1) or < 0.
+int cwtb_profile_last(cwtb_ctx *c, char *out, size_t cap) {
+  if (!c || !c->job.valid || !c->job_dsig || !out || cap < 2) return fail(c, CWTB_ERR_STATE, "no transform to profile");
+#ifdef CWTB_HOST_EMU
+  out[0] = 0;
+  return 0;
+#else
+  c->prof.clear();
+  c->profiling = true;
+  int e = timed_run(c, c->job_dsig, 1, nullptr);
+  c->profiling = false;
+  if (e) return e;
+  RT(rt_sync(c->stream));
+  std::map<std::string, std::array<double, 3>> agg;
+  std::vector<std::string> order;
+  for (auto &r : c->prof) {
+    float ms = 0;
+    RT(cudaEventElapsedTime(&ms, c->prof_events[r.ev], c->prof_events[r.ev + 1]));
+    if (!agg.count(r.name)) order.push_back(r.name);
+    auto &a = agg[r.name];
+    a[0] += 1; a[1] += ms; a[2] += r.gy;
+  }
+  std::string txt;
+  char line[512];
+  for (auto &n : order) {
+    auto &a = agg[n];
+    snprintf(line, sizeof line, "%s|%d|%.6f|%d\n", n.c_str(), (int)a[0], a[1], (int)a[2]);
+    txt += line;
+  }
+  size_t m = std::min(cap - 1, txt.size());
+  memcpy(out, txt.data(), m);
+  out[m] = 0;
+  return (int)m;
+#endif
 }
 
 int cwtb_cwt_batch(cwtb_ctx *c, const void *X, int x_is_f32, int n_chan, int64_t n0, double dt,

@@ -26,12 +26,33 @@
 
 namespace cwtb {
 
-constexpr int NT = 128;     // threads per CTA
-constexpr int KT = 4096;    // size of the master twiddle table e^{2 pi i t / KT}
+#ifndef CWTB_NT
+#define CWTB_NT 128
+#endif
+#ifndef CWTB_TILE_F64
+#define CWTB_TILE_F64 4096
+#endif
+#ifndef CWTB_TILE_F32
+#define CWTB_TILE_F32 8192
+#endif
+#ifndef CWTB_MINB
+#define CWTB_MINB 1
+#endif
+constexpr int NT = CWTB_NT;  // threads per CTA
+constexpr int KT = 4096;    // (legacy) size of a master table e^{2 pi i t / KT}
+// Pass twiddle tables: for a pass of radix R on sub-transforms of length L the factor
+// w_L^{j c} (c = 1..R-1, j < L/R) is stored at  tw[tw_offset(L) + (c-1)*(L/R) + j], i.e. lanes
+// (consecutive j) read consecutive entries.  Each L has one radix in the plans below.
+HD constexpr int tw_radix(int L) { return L == 32 ? 4 : (L == 256 ? 16 : 8); }
+HD constexpr int tw_count(int L) { return (tw_radix(L) - 1) * (L / tw_radix(L)); }
+HD constexpr int tw_offset(int L) {
+  return L == 32 ? 0 : (L == 64 ? tw_count(32) : tw_offset(L / 2) + tw_count(L / 2));
+}
+constexpr int TW_TOTAL = tw_offset(1024) + tw_count(1024);
 constexpr int K2C = 1024;   // length of the second-pass transform (two-kernel scales)
 
 template <typename T> struct TileCfg {
-  static constexpr int TILE = sizeof(T) == 8 ? 4096 : 8192;  // elements per CTA (64 KiB)
+  static constexpr int TILE = sizeof(T) == 8 ? CWTB_TILE_F64 : CWTB_TILE_F32;  // elements per CTA
   static constexpr int Q = 128 / (2 * (int)sizeof(T));       // lanes per smem conflict domain
 };
 
@@ -102,6 +123,12 @@ struct TileBarrier {
     for (unsigned i = 0; i < bytes; ++i) d_[i] = s_[i];
 #endif
   }
+  HD void inval() const {
+#if defined(__CUDA_ARCH__) && !defined(CWTB_HOST_EMU)
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(a) : "memory");
+#endif
+  }
   HD void wait(unsigned parity) const {
 #if defined(__CUDA_ARCH__) && !defined(CWTB_HOST_EMU)
     const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
@@ -121,6 +148,15 @@ template <typename V> HD V ldg(const V *p) {
   return __ldg(p);
 #else
   return *p;
+#endif
+}
+
+// streaming (evict-first) store for results that are never re-read by the engine
+template <typename V> HD void st_stream(V *p, V v) {
+#if defined(__CUDA_ARCH__) && !defined(CWTB_HOST_EMU)
+  __stcs(p, v);
+#else
+  *p = v;
 #endif
 }
 
@@ -184,14 +220,27 @@ template <typename T, int K, int R> struct GenLoader {
   int rsplit;      // r >= rsplit  ->  k = r - K
   unsigned p0;
   V a[R], d[R];
+  // Phase factors e^{2 pi i k_i p / N} (p = the thread's first index) and the per-step
+  // multipliers e^{2 pi i k_i bstep / N} for the R residues r_i = base + i*stride, signed bins
+  // k_i = r_i - K [r_i >= rsplit].  Only the i = 0 factors need a per-lane table lookup; the
+  // others follow by multiplying with warp-uniform steps (broadcast loads), which keeps the
+  // scattered 16-byte gathers off the LSU pipe.
   HD void begin(int base, int stride, int bstart, int bstep) {
+    const unsigned pp = p0 + (unsigned)bstart;
+    V e = nroot_t<T>(nt, (unsigned)base * pp);
+    V de = nroot_t<T>(nt, (unsigned)base * (unsigned)bstep);
+    const V se = nroot_t<T>(nt, (unsigned)stride * pp);
+    const V sd = nroot_t<T>(nt, (unsigned)stride * (unsigned)bstep);
+    const V ne = nroot_t<T>(nt, (unsigned)(-K) * pp);
+    const V nd = nroot_t<T>(nt, (unsigned)(-K) * (unsigned)bstep);
 #pragma unroll
     for (int i = 0; i < R; ++i) {
-      int r = base + i * stride;
-      int k = r - (r >= rsplit ? K : 0);
-      V e0 = nroot_t<T>(nt, (unsigned)k * (p0 + (unsigned)bstart));
-      d[i] = nroot_t<T>(nt, (unsigned)k * (unsigned)bstep);
-      a[i] = cmul(ldg(&B[r]), e0);
+      const int r = base + i * stride;
+      const bool neg = r >= rsplit;
+      d[i] = neg ? cmul(de, nd) : de;
+      a[i] = cmul(ldg(&B[r]), neg ? cmul(e, ne) : e);
+      e = cmul(e, se);
+      de = cmul(de, sd);
     }
   }
   HD void load(int, V (&x)[R]) {
@@ -214,8 +263,9 @@ HD void pass_mid(cx<T> *sm, const cx<T> *__restrict__ tw, Loader &ld, int tid) {
     const int g = tp / Ln, j = tp % Ln;
     V twv[R];
 #pragma unroll
+    static_assert(tw_radix(L) == R, "pass twiddle table was built for another radix");
     for (int c = 1; c < R; ++c) {
-      V w = ldg(&tw[(j * c) * (KT / L)]);
+      V w = ldg(&tw[tw_offset(L) + (c - 1) * Ln + j]);
       if (SIGN < 0) w.y = -w.y;
       twv[c] = w;
     }

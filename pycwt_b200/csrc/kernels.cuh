@@ -113,7 +113,7 @@ template <typename T> struct OutStorer {
     for (int c = 0; c < R; ++c) {
       long long n = u + (long long)(ql + c * qs) * U;
       if (n < nout) {
-        if (epi.mode == EPI_STORE) row[n] = x[c];
+        if (epi.mode == EPI_STORE) st_stream(&row[n], x[c]);
         else row[n] = epi.apply(x[c], epi.mode == EPI_MULCONJ ? row[n] : x[c], n);
       }
     }
@@ -169,14 +169,14 @@ template <typename T, int K> struct SingleBody {
     const ScaleDesc d = a.descs[a.first + by];
     const int M = (int)(a.N / K);
     const int p0 = bx * LY::P;
-    if (PH == 0) {
+    if constexpr (PH == 0) {
       GenLoader<T, K, Plan<K>::R1> ld;
       ld.B = a.Bbuf + d.boff;
       ld.nt = a.nt;
       ld.rsplit = d.rsplit;
       ld.p0 = (unsigned)p0;
       tile_first<T, K, +1>(sm, a.tw, ld, tid);
-    } else if (PH == 1 && NP == 3) {
+    } else if constexpr (PH == 1 && NP == 3) {
       tile_second<T, K, +1>(sm, a.tw, tid);
     } else {
       OutStorer<T> st;
@@ -184,6 +184,84 @@ template <typename T, int K> struct SingleBody {
       st.nout = a.n0;
       st.u0 = p0;
       st.U = M;
+      st.epi.mode = a.epi;
+      pass_last<T, K, +1>(sm, st, tid);
+    }
+  }
+};
+
+
+// ---- Body: K' = K1*1024 with small K1 (2, 4, 8) in ONE kernel -------------------------------
+// The K1-point transform over r1 is evaluated as a direct sum while the tile is filled, so the
+// Z round trip of the two-kernel path disappears:
+//   in[u][r2] = e^{2 pi i r2 u / N} * sum_{r1 < K1} B[r1*1024 + r2] * w_u^{k1},  w_u = e^{2 pi i u / U},
+//   W[u + q2*U] = sum_{r2} in[u][r2] e^{2 pi i r2 q2 / 1024}
+// (k1 = r1 - K1 [r >= rsplit] is the signed row of residue r; no alignment of the window needed).
+template <typename T, int K1> struct DirectBody {
+  using V = cx<T>;
+  using Args = SingleArgs<T>;
+  static constexpr int K = K2C;
+  using LY = Lay<T, K>;
+  static constexpr int NP = Plan<K>::NP;
+  static constexpr int P = LY::P;
+  static constexpr int NPHASE = 2 + NP;
+  static constexpr int NW = 2 * K1 * P;   // w_u^{k1} for k1 = r1 and r1 - K1, per b
+  static constexpr size_t SMEM = LY::TILE_BYTES + NW * sizeof(V);
+  template <int PH> HD static void phase(const Args &a, int bx, int by, int tid, void *smraw) {
+    V *sm = (V *)smraw;
+    V *wt = (V *)((char *)smraw + LY::TILE_BYTES);   // [b][2][K1]
+    const ScaleDesc d = a.descs[a.first + by];
+    const int U = (int)(a.N / K);
+    const int u0 = bx * P;
+    if constexpr (PH == 0) {
+      for (int i = tid; i < NW; i += NT) {
+        const int b = i / (2 * K1), s = (i / K1) & 1, r1 = i % K1;
+        const int k1 = r1 - (s ? K1 : 0);
+        wt[i] = nroot_t<T>(a.nt, (unsigned)k1 * (unsigned)(u0 + b) * (unsigned)K);
+      }
+    } else if constexpr (PH == 1) {
+      const V *B = a.Bbuf + d.boff;
+      // r2 = tid + NT*it; phase e^{2 pi i r2 u0 / N} by recurrence over it, advanced over b
+      V e = nroot_t<T>(a.nt, (unsigned)tid * (unsigned)u0);
+      const V se = nroot_t<T>(a.nt, (unsigned)NT * (unsigned)u0);
+      V dr = nroot_t<T>(a.nt, (unsigned)tid);          // e^{2 pi i r2 / N}
+      const V sdr = nroot_t<T>(a.nt, (unsigned)NT);
+      for (int it = 0; it < K / NT; ++it) {
+        const int r2 = tid + NT * it;
+        V bv[K1];
+        bool neg[K1];
+#pragma unroll
+        for (int r1 = 0; r1 < K1; ++r1) {
+          bv[r1] = ldg(&B[r1 * K + r2]);
+          neg[r1] = (r1 * K + r2) >= d.rsplit;
+        }
+        V t = e;
+#pragma unroll
+        for (int b = 0; b < P; ++b) {
+          V acc = mk<T>(0, 0);
+#pragma unroll
+          for (int r1 = 0; r1 < K1; ++r1) {
+            const V w = wt[(b * 2 + (neg[r1] ? 1 : 0)) * K1 + r1];
+            acc = cadd(acc, cmul(bv[r1], w));
+          }
+          sm[LY::phys(b, r2)] = cmul(acc, t);
+          t = cmul(t, dr);
+        }
+        e = cmul(e, se);
+        dr = cmul(dr, sdr);
+      }
+    } else if constexpr (PH == 2) {
+      SmemLoader<T, K> ld;
+      ld.sm = sm;
+      tile_first<T, K, +1>(sm, a.tw, ld, tid);
+    } else if constexpr (PH == 3 && NP == 3) {
+      tile_second<T, K, +1>(sm, a.tw, tid);
+    } else {
+      OutStorer<T> st;
+      st.row = a.W + (size_t)d.row * a.n0;
+      st.nout = a.n0;
+      st.u0 = u0;
+      st.U = U;
       st.epi.mode = a.epi;
       pass_last<T, K, +1>(sm, st, tid);
     }
@@ -202,6 +280,7 @@ template <typename T> struct PassBArgs {
   unsigned N;
   int first, row0;
   int epi;
+  int zmod;                // Z slot of row `by` is by % zmod
 };
 
 template <typename T, int SIGN> struct PassBBody {
@@ -220,22 +299,22 @@ template <typename T, int SIGN> struct PassBBody {
     const int u0 = bx * LY::P;
     TileBarrier tb;
     tb.bar = (unsigned long long *)((char *)smraw + LY::TILE_BYTES);
-    if (PH == 0) {
+    if constexpr (PH == 0) {
       const int nvalid = (U - u0) < LY::P ? (U - u0) : LY::P;
       if (tid == 0) {
         tb.init_and_expect((unsigned)(nvalid * K * sizeof(V)));
-        const V *src = a.Z + (size_t)by * a.N + (size_t)u0 * K;
+        const V *src = a.Z + (size_t)(by % a.zmod) * a.N + (size_t)u0 * K;
         for (int b = 0; b < nvalid; ++b)
           tb.copy(sm + LY::phys(b, 0), src + (size_t)b * K, (unsigned)(K * sizeof(V)));
       }
       for (int b = nvalid; b < LY::P; ++b)
         for (int i = tid; i < K; i += NT) sm[LY::phys(b, i)] = mk<T>(0, 0);
-    } else if (PH == 1) {
+    } else if constexpr (PH == 1) {
       tb.wait(0);
       SmemLoader<T, K> ld;
       ld.sm = sm;
       tile_first<T, K, SIGN>(sm, a.tw, ld, tid);
-    } else if (PH == 2 && NP == 3) {
+    } else if constexpr (PH == 2 && NP == 3) {
       tile_second<T, K, SIGN>(sm, a.tw, tid);
     } else {
       const int row = a.descs ? a.descs[a.first + by].row : a.row0 + by;
@@ -252,6 +331,7 @@ template <typename T, int SIGN> struct PassBBody {
         st.epi.nfreq = a.N;
       }
       pass_last<T, K, SIGN>(sm, st, tid);
+      if (tid == 0) tb.inval();   // every thread passed wait() two barriers ago
     }
   }
 };
@@ -271,6 +351,7 @@ template <typename T> struct PassAArgs {
   long long in_pitch, n_in;
   unsigned N;
   int first, row0;
+  int zmod;            // Z slot of row `by` is by % zmod (ring of Z buffers in the fused kernel)
 };
 
 template <typename T, int K1, int MODE, int SIGN> struct PassABody {
@@ -321,13 +402,13 @@ template <typename T, int K1, int MODE, int SIGN> struct PassABody {
     const int r20 = (bx % NTILE2) * T2;
     const int M = (int)(a.N / ((unsigned)K1 * K2C));
     ZStorer<T, SIGN> st;
-    st.Z = a.Z + (size_t)by * a.N;
+    st.Z = a.Z + (size_t)(by % a.zmod) * a.N;
     st.nt = a.nt;
     st.p = p;
     st.M = M;
     st.r20 = r20;
     st.bmax = T2;
-    if (NP == 1) {
+    if constexpr (NP == 1) {
       Src src(a, by, p);
       for (int b = tid; b < T2; b += NT) {
         V x[K1];
@@ -336,17 +417,17 @@ template <typename T, int K1, int MODE, int SIGN> struct PassABody {
         dftR<K1, SIGN, T>(x);
         st.store(b, 0, 1, x);
       }
-    } else if (PH == 0) {
+    } else if constexpr (PH == 0) {
       Src src(a, by, p);
       for (int idx = tid; idx < K1 * T2; idx += NT) {
         const int b = idx % T2, pos = idx / T2;
         sm[LY::phys(b, pos)] = src.get(pos, r20 + b);
       }
-    } else if (PH == 1) {
+    } else if constexpr (PH == 1) {
       SmemLoader<T, K1> ld;
       ld.sm = sm;
       tile_first<T, K1, SIGN>(sm, a.tw, ld, tid);
-    } else if (PH == 2 && NP == 3) {
+    } else if constexpr (PH == 2 && NP == 3) {
       tile_second<T, K1, SIGN>(sm, a.tw, tid);
     } else {
       pass_last<T, K1, SIGN>(sm, st, tid);
@@ -450,7 +531,7 @@ template <typename T, int K, int SIGN> struct RowsBody {
     RowsLoader<T, K> ld;
     ld.a = &a;
     ld.row0 = row0;
-    if (NP == 1) {
+    if constexpr (NP == 1) {
       for (int b = tid; b < LY::P; b += NT) {
         V x[K];
 #pragma unroll
@@ -458,9 +539,9 @@ template <typename T, int K, int SIGN> struct RowsBody {
         dftR<K, SIGN, T>(x);
         st.store(b, 0, 1, x);
       }
-    } else if (PH == 0) {
+    } else if constexpr (PH == 0) {
       tile_first<T, K, SIGN>(sm, a.tw, ld, tid);
-    } else if (PH == 1 && NP == 3) {
+    } else if constexpr (PH == 1 && NP == 3) {
       tile_second<T, K, SIGN>(sm, a.tw, tid);
     } else {
       pass_last<T, K, SIGN>(sm, st, tid);
@@ -685,6 +766,31 @@ struct R2CBody {
   template <int PH> HD static void phase(const Args &a, int bx, int, int tid, void *) {
     const long long i = (long long)bx * NT + tid;
     if (i < a.count) a.out[i] = make_double2(a.in[i], 0.0);
+  }
+};
+
+// ---- Body: pass twiddle tables in [c][j] layout (see fft_tile.cuh: tw_offset) -------------
+struct PassTwArgs {
+  double2 *out64;
+  float2 *out32;
+};
+struct PassTwBody {
+  using Args = PassTwArgs;
+  static constexpr int NPHASE = 1;
+  static constexpr size_t SMEM = 0;
+  template <int PH> HD static void phase(const Args &a, int bx, int, int tid, void *) {
+    const int idx = bx * NT + tid;
+    if (idx >= TW_TOTAL) return;
+    int L = 32;
+    while (L < 1024 && idx >= tw_offset(2 * L)) L *= 2;
+    const int R = tw_radix(L), Ln = L / R;
+    const int rel = idx - tw_offset(L);
+    const int c = rel / Ln + 1, j = rel % Ln;
+    double sn, cs;
+    sincospi_hd(2.0 * (double)(j * c) / (double)L, &sn, &cs);
+    (void)R;
+    a.out64[idx] = make_double2(cs, sn);
+    a.out32[idx] = make_float2((float)cs, (float)sn);
   }
 };
 

@@ -23,28 +23,32 @@ def find(condition):
 
 
 def ar1(x):
-    """Allen & Smith (1996) lag-1 autocorrelation estimate (helpers.py:43-104).
+    """Allen & Smith (1996) estimate of the lag-1 autocorrelation of a series, with the
+    finite-sample bias correction used by the reference (helpers.py:43-104).
 
-    Returns (g, a, mu2): lag-one autocorrelation, noise amplitude, and the squared mean
-    of a finite AR(1) segment normalised by the process variance."""
-    x = np.asarray(x)
-    N = x.size
-    x = x - x.mean()
-    c0 = x.transpose().dot(x) / N
-    c1 = x[0:N - 1].transpose().dot(x[1:N]) / (N - 1)
-    B = -c1 * N - c0 * N ** 2 - 2 * c0 + 2 * c1 - c1 * N ** 2 + c0 * N
-    A = c0 * N ** 2
-    C = N * (c0 + c1 * N - c1)
-    D = B ** 2 - 4 * A * C
-    if D > 0:
-        g = (-B - D ** 0.5) / (2 * A)
-    else:
+    Returns ``(g, a, mu2)``: lag-one autocorrelation, white-noise amplitude of the AR(1)
+    model ``x_t - <x> = g (x_{t-1} - <x>) + a z_t`` and the (normalised) squared mean of a
+    finite AR(1) segment.  Raises ``Warning`` when no upper bound can be placed on g
+    (series too short or dominated by a trend), like the reference."""
+    series = np.asarray(x)
+    n = series.size
+    dev = series - series.mean()
+    cov0 = np.dot(dev, dev) / n                     # lag-0 covariance
+    cov1 = np.dot(dev[:-1], dev[1:]) / (n - 1)      # lag-1 covariance
+
+    # unbiased estimate: smaller root of  qa*g^2 + qb*g + qc = 0
+    qa = cov0 * n ** 2
+    qb = -cov1 * n - cov0 * n ** 2 - 2 * cov0 + 2 * cov1 - cov1 * n ** 2 + cov0 * n
+    qc = n * (cov0 + cov1 * n - cov1)
+    disc = qb ** 2 - 4 * qa * qc
+    if not disc > 0:
         raise Warning('Cannot place an upperbound on the unbiased AR(1). '
                       'Series is too short or trend is to large.')
-    mu2 = -1 / N + (2 / N ** 2) * ((N - g ** N) / (1 - g) -
-                                   g * (1 - g ** (N - 1)) / (1 - g) ** 2)
-    c0t = c0 / (1 - mu2)
-    a = ((1 - g ** 2) * c0t) ** 0.5
+    g = (-qb - disc ** 0.5) / (2 * qa)
+
+    # Allen & Smith footnote 4: expected squared mean of a length-n AR(1) segment
+    mu2 = (2 / n ** 2) * ((n - g ** n) / (1 - g) - g * (1 - g ** (n - 1)) / (1 - g) ** 2) - 1 / n
+    a = np.sqrt((1 - g ** 2) * cov0 / (1 - mu2))
     return g, a, mu2
 
 
@@ -71,19 +75,20 @@ def rednoise(N, g, a=1.):
 
 
 def rect(x, normalize=False):
-    """Boxcar window with half-weight end taps (helpers.py:176-191)."""
-    if type(x) in [int, float]:
-        shape = [x, ]
-    elif type(x) in [list, dict]:
-        shape = x
-    elif type(x) in [np.ndarray, np.ma.core.MaskedArray]:
+    """Boxcar window whose two end taps carry half weight (helpers.py:176-191).  `x` is the
+    length (int/float), a shape list, or an array whose shape is used."""
+    if isinstance(x, (np.ndarray, np.ma.core.MaskedArray)):
         shape = x.shape
-    X = np.zeros(shape)
-    X[0] = X[-1] = 0.5
-    X[1:-1] = 1
+    elif type(x) in (list, dict):
+        shape = x
+    else:
+        shape = [x, ]
+    win = np.ones(shape)
+    win[0] = 0.5
+    win[-1] = 0.5          # a single-tap window ends up as [0.5], like the reference
     if normalize:
-        X /= X.sum()
-    return X
+        win /= win.sum()
+    return win
 
 
 def boxpdf(x):
