@@ -169,6 +169,13 @@ int cwtb_cwt_batch(cwtb_ctx *ctx, const void *X, int x_is_f32, int n_chan,
                    int family, double param, int precision, double *power_out,
                    void *W_out);
 
+/* Device-resident variant: d_X [n_chan][n0] already on the device in the engine's real type;
+ * one chunk (n_chan * n_scales rows <= 60000); W [n_chan][n_scales][n0] stays resident
+ * (cwtb_w_device_ptr); power_out (may be NULL): host [n_chan][n_scales] mean |W|^2. */
+int cwtb_cwt_batch_dev(cwtb_ctx *ctx, const void *d_X, int n_chan, int64_t n0, double dt,
+                       const double *scales, int n_scales, int family, double param,
+                       int precision, double *power_out);
+
 /* ---- timing / introspection (bench.py, tests) ----------------------------- */
 /* Device time (ms, CUDA events on the context's stream) of the kernels of the
  * last cwtb_cwt* call, excluding H2D/D2H; and the number of kernel launches. */

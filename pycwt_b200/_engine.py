@@ -59,6 +59,7 @@ _SIGNATURES = {
     "cwtb_smooth": (_I, [_P, _P, _I, _I, _I64, _D, _P, _I, _P]),
     "cwtb_wct_mc": (_I, [_P, _P, _I, _I64, _D, _D, _P, _I, _I, _D, _I, _P, _I, _I, _P]),
     "cwtb_cwt_batch": (_I, [_P, _P, _I, _I, _I64, _D, _P, _I, _I, _D, _I, _P, _P]),
+    "cwtb_cwt_batch_dev": (_I, [_P, _P, _I, _I64, _D, _P, _I, _I, _D, _I, _P]),
 }
 
 
@@ -348,6 +349,15 @@ class Engine(object):
         self._check(self.lib.cwtb_cwt_dev(self.h, dptr, int(is_f32), int(n0), float(dt),
                                           _ptr(sj), sj.size, int(family), float(param),
                                           int(precision)))
+
+    def cwt_batch_dev(self, dptr, n_chan, n0, dt, scales, family, param, precision=F64,
+                      want_power=False):
+        sj = np.ascontiguousarray(scales, dtype=np.float64)
+        power = np.empty((n_chan, sj.size), dtype=np.float64) if want_power else None
+        self._check(self.lib.cwtb_cwt_batch_dev(self.h, dptr, int(n_chan), int(n0), float(dt),
+                                                _ptr(sj), sj.size, int(family), float(param),
+                                                int(precision), _ptr(power) if want_power else None))
+        return power
 
     def bench_last(self, iters):
         ms = _D()

@@ -98,7 +98,8 @@ struct Job {
   long long n0 = 0;
   unsigned N = 0;
   int log2N = 0;
-  int S = 0;
+  int S = 0;          // scales per channel
+  int nbatch = 1;     // channels transformed together (rows = nbatch * S)
   double dt = 0;
   Fam fam{};
   std::vector<ScaleDesc> descs;   // sorted by class
@@ -125,7 +126,8 @@ struct cwtb_ctx {
   int direct_max_log2 = 13;
   int fused = 0;     // experimental: two-kernel scales through one persistent kernel (CWTB_FUSED=1)
   int ring = 3;      // Z ring slots of the fused kernel
-  int num_sms = 148;  // K' <= 2^13 handled by one kernel (K' > 1024: DirectBody)
+  int num_sms = 148;
+  size_t batch_bytes = (size_t)4 << 30;   // coefficients per chunk of cwtb_cwt_batch  // K' <= 2^13 handled by one kernel (K' > 1024: DirectBody)
   double2 *tw64 = nullptr;
   float2 *tw32 = nullptr;
   std::map<unsigned, NTabDev> ntabs;
@@ -340,7 +342,7 @@ static void family_band(int family, double param, double eps, double *flo, doubl
 }
 
 static int build_job(cwtb_ctx *c, Job &job, long long n0, double dt, const double *scales, int S,
-                     int family, double param, int precision, bool have_table) {
+                     int family, double param, int precision, bool have_table, int nbatch = 1) {
   if (n0 < 1 || S < 1 || !(dt > 0)) return fail(c, CWTB_ERR_ARG, "bad n0 / n_scales / dt");
   if (family < 0 || family > 3) return fail(c, CWTB_ERR_ARG, "unknown wavelet family");
   if (family == CWTB_TABLE && !have_table) return fail(c, CWTB_ERR_ARG, "CWTB_TABLE needs a table");
@@ -353,6 +355,7 @@ static int build_job(cwtb_ctx *c, Job &job, long long n0, double dt, const doubl
   job.log2N = ilog2((unsigned long long)n0);   // pycwt/helpers.py:27-30
   job.N = 1u << job.log2N;
   job.S = S;
+  job.nbatch = nbatch;
   job.dt = dt;
   const unsigned N = job.N;
   Fam &fam = job.fam;
@@ -394,6 +397,8 @@ static int build_job(cwtb_ctx *c, Job &job, long long n0, double dt, const doubl
     d.s = s;
     d.row = j;
     d.trow = j;
+    d.chan = 0;
+    d.pad_ = 0;
     d.boff = 0;
     const double norm = std::sqrt(s * w1 * (double)N);  // wavelet.py:103
     d.amp = (family == CWTB_TABLE ? 1.0 : norm * fconst) / (double)N;
@@ -427,13 +432,25 @@ static int build_job(cwtb_ctx *c, Job &job, long long n0, double dt, const doubl
     d.log2K = lk;
     job.plan_log2K[j] = (N < 32) ? 0 : lk;
   }
+  // one descriptor per (channel, scale) row; rows of channel ch are ch*S .. ch*S+S-1
+  if (nbatch > 1) {
+    ds.resize((size_t)S * nbatch);
+    for (int ch = 1; ch < nbatch; ++ch)
+      for (int j = 0; j < S; ++j) {
+        ScaleDesc d = ds[j];
+        d.chan = ch;
+        d.row = ch * S + j;
+        ds[(size_t)ch * S + j] = d;
+      }
+  }
+  const int R = S * nbatch;
   // sort by class (descending K': small scales first), stable
-  std::vector<int> order(S);
-  for (int j = 0; j < S; ++j) order[j] = j;
+  std::vector<int> order(R);
+  for (int j = 0; j < R; ++j) order[j] = j;
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return ds[a].log2K > ds[b].log2K; });
-  job.descs.resize(S);
+  job.descs.resize(R);
   size_t boff = 0;
-  for (int i = 0; i < S; ++i) {
+  for (int i = 0; i < R; ++i) {
     job.descs[i] = ds[order[i]];
     ScaleDesc &d = job.descs[i];
     if (job.classes.empty() || job.classes.back().log2K != d.log2K)
@@ -707,9 +724,9 @@ template <typename T>
 static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nullptr, int epi = EPI_STORE) {
   using V = cx<T>;
   const unsigned N = job.N;
-  const int S = job.S;
+  const int S = job.S * job.nbatch;   // rows: one per (channel, scale)
   int e;
-  if ((e = ensure(c, c->spec, (size_t)N * sizeof(V)))) return e;
+  if ((e = ensure(c, c->spec, (size_t)job.nbatch * N * sizeof(V)))) return e;
   if (!Wout) {
     if ((e = ensure(c, c->W, (size_t)S * job.n0 * sizeof(V)))) return e;
     Wout = (V *)c->W.p;
@@ -722,12 +739,13 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
 
   // ---- forward transform of the zero-padded signal (wavelet.py:91) ----
   if (N < 32) {
+    if (job.nbatch != 1) return fail(c, CWTB_ERR_UNSUPPORTED, "batched transform needs n0 > 16");
     TinyFwdArgs<T> fa{dsig, spec, job.n0, N};
     if ((e = launch<TinyFwdBody<T>>(c, 1, 1, fa))) return e;
     TinyArgs<T> ta{ddesc, spec, W, fam, job.n0, N, 0, epi};
     return launch<TinyBody<T>>(c, (unsigned)((job.n0 + NT - 1) / NT), S, ta);
   }
-  if ((e = fft_rows<T, -1>(c, dsig, 1, job.n0, job.n0, spec, N, N, 1))) return e;
+  if ((e = fft_rows<T, -1>(c, dsig, 1, job.n0, job.n0, spec, N, N, job.nbatch))) return e;
 
   NTab nt;
   if ((e = get_ntab(c, N, job.log2N, &nt))) return e;
@@ -739,13 +757,26 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
   if ((e = ensure(c, c->B, (job.b_single + bchunk) * sizeof(V)))) return e;
   V *Bbuf = (V *)c->B.p;
 
+  // band products of every single-kernel scale in one launch (their descriptors are the tail
+  // of the class-sorted array; blocks beyond a scale's K' exit immediately)
+  {
+    int first = -1, maxlk = 0;
+    for (const ClassRun &cl : job.classes)
+      if (cl.log2K <= 10 || (cl.log2K <= c->direct_max_log2 && cl.log2K < job.log2N)) {
+        if (first < 0) first = cl.first;
+        maxlk = std::max(maxlk, cl.log2K);
+      }
+    if (first >= 0) {
+      BandArgs<T> ba{ddesc, spec, Bbuf, fam, N, first};
+      const unsigned Kmax = 1u << maxlk;
+      if ((e = launch<BandBody<T>>(c, (Kmax + NT * BandBody<T>::PER - 1) / (NT * BandBody<T>::PER), S - first, ba)))
+        return e;
+    }
+  }
   for (const ClassRun &cl : job.classes) {
     const unsigned K = 1u << cl.log2K;
     if (cl.log2K <= 10 || (cl.log2K <= c->direct_max_log2 && cl.log2K < job.log2N)) {
-      // ---- single kernel: band product, then pruned K'-point transforms ----
-      BandArgs<T> ba{ddesc, spec, Bbuf, fam, N, cl.first};
-      if ((e = launch<BandBody<T>>(c, (K + NT * BandBody<T>::PER - 1) / (NT * BandBody<T>::PER), cl.count, ba)))
-        return e;
+      // ---- single kernel: pruned K'-point transforms from the band products ----
       SingleArgs<T> sa{ddesc, Bbuf, W, Tw<T>::get(c), nt, job.n0, N, cl.first, epi};
       switch (cl.log2K) {
         case 5: e = launch_single<T, 32>(c, sa, cl.count); break;
@@ -888,6 +919,7 @@ int cwtb_create(int device, cwtb_ctx **out) {
   if (const char *g = getenv("CWTB_BAND_EPS")) c->band_eps = atof(g);
   if (const char *g = getenv("CWTB_L2_PERSIST")) c->l2_persist = atoi(g);
   if (const char *g = getenv("CWTB_FUSED")) c->fused = atoi(g);
+  if (const char *g = getenv("CWTB_BATCH_MB")) c->batch_bytes = (size_t)std::max(1, atoi(g)) << 20;
   if (const char *g = getenv("CWTB_RING")) c->ring = std::max(1, atoi(g));
 #ifndef CWTB_HOST_EMU
   cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
@@ -971,14 +1003,15 @@ int cwtb_sync(cwtb_ctx *c) {
 }
 
 static int prepare(cwtb_ctx *c, long long n0, double dt, const double *scales, int S, int family,
-                   double param, int precision, const void *table) {
+                   double param, int precision, const void *table, int nbatch = 1) {
   if (!c) return CWTB_ERR_ARG;
   if (precision != CWTB_F64 && precision != CWTB_F32) return fail(c, CWTB_ERR_ARG, "bad precision");
   if (!scales) return fail(c, CWTB_ERR_ARG, "null scales");
 #ifndef CWTB_HOST_EMU
   RT(cudaSetDevice(c->device));
 #endif
-  int e = build_job(c, c->job, n0, dt, scales, S, family, param, precision, table != nullptr);
+  if (nbatch < 1 || (long long)nbatch * S > 60000) return fail(c, CWTB_ERR_ARG, "batch too large for one launch");
+  int e = build_job(c, c->job, n0, dt, scales, S, family, param, precision, table != nullptr, nbatch);
   if (e) return e;
   if (family == CWTB_TABLE) {
     size_t bytes = (size_t)S * c->job.N * sizeof(double2);
@@ -1059,7 +1092,7 @@ int cwtb_last_plan(cwtb_ctx *c, int *out, int n) {
 int cwtb_get_w(cwtb_ctx *c, void *out, int out_f64, int row0, int nrows) {
   if (!c || !c->job.valid || !out) return fail(c, CWTB_ERR_STATE, "no transform resident");
   const Job &job = c->job;
-  if (row0 < 0 || nrows < 0 || row0 + nrows > job.S) return fail(c, CWTB_ERR_ARG, "row range");
+  if (row0 < 0 || nrows < 0 || row0 + nrows > job.S * job.nbatch) return fail(c, CWTB_ERR_ARG, "row range");
   const size_t cnt = (size_t)nrows * job.n0;
   if (job.precision == CWTB_F64) {
     RT(rt_d2h(out, (const double2 *)c->W.p + (size_t)row0 * job.n0, cnt * sizeof(double2), c->stream));
@@ -1222,6 +1255,7 @@ int cwtb_cwt_to_host(cwtb_ctx *c, const void *signal, int signal_is_f32, int64_t
 int cwtb_icwt_sum(cwtb_ctx *c, double *out) {
   if (!c || !c->job.valid || !out) return fail(c, CWTB_ERR_STATE, "no transform resident");
   const Job &job = c->job;
+  if (job.nbatch != 1) return fail(c, CWTB_ERR_UNSUPPORTED, "icwt of a batched transform: fetch rows per channel");
   std::vector<double> rs(job.S);
   for (int j = 0; j < job.S; ++j) rs[j] = std::sqrt(job.scales[j]);
   int e = upload_doubles(c, c->rowd, rs);
@@ -1266,25 +1300,26 @@ int cwtb_icwt_sum_host(cwtb_ctx *c, const void *W, const double *scales, int n_s
 static int power_common(cwtb_ctx *c, double *power_out, double *mean_out) {
   if (!c || !c->job.valid) return fail(c, CWTB_ERR_STATE, "no transform resident");
   const Job &job = c->job;
-  const size_t cnt = (size_t)job.S * job.n0;
-  int e = ensure(c, c->aux, (power_out ? cnt : 0) * sizeof(double) + (size_t)job.S * sizeof(double));
+  const int R = job.S * job.nbatch;
+  const size_t cnt = (size_t)R * job.n0;
+  int e = ensure(c, c->aux, (power_out ? cnt : 0) * sizeof(double) + (size_t)R * sizeof(double));
   if (e) return e;
   double *dsum = (double *)c->aux.p;
-  double *dpow = power_out ? dsum + job.S : nullptr;
-  RT(rt_memset(dsum, 0, (size_t)job.S * sizeof(double), c->stream));
+  double *dpow = power_out ? dsum + R : nullptr;
+  RT(rt_memset(dsum, 0, (size_t)R * sizeof(double), c->stream));
   const unsigned gx = (unsigned)((job.n0 + 8 * NT - 1) / (8 * NT));
   if (job.precision == CWTB_F64) {
     PowerArgs<double> a{(const double2 *)c->W.p, dpow, dsum, job.n0};
-    e = launch<PowerBody<double>>(c, gx, job.S, a);
+    e = launch<PowerBody<double>>(c, gx, R, a);
   } else {
     PowerArgs<float> a{(const float2 *)c->W.p, dpow, dsum, job.n0};
-    e = launch<PowerBody<float>>(c, gx, job.S, a);
+    e = launch<PowerBody<float>>(c, gx, R, a);
   }
   if (e) return e;
   if (power_out) RT(rt_d2h(power_out, dpow, cnt * sizeof(double), c->stream));
-  if (mean_out) RT(rt_d2h(mean_out, dsum, (size_t)job.S * sizeof(double), c->stream));
+  if (mean_out) RT(rt_d2h(mean_out, dsum, (size_t)R * sizeof(double), c->stream));
   RT(rt_sync(c->stream));
-  if (mean_out) for (int j = 0; j < job.S; ++j) mean_out[j] /= (double)job.n0;
+  if (mean_out) for (int j = 0; j < R; ++j) mean_out[j] /= (double)job.n0;
   return 0;
 }
 int cwtb_get_power(cwtb_ctx *c, double *out) { return power_common(c, out, nullptr); }
@@ -1448,19 +1483,59 @@ int cwtb_profile_last(cwtb_ctx *c, char *out, size_t cap) {
 #endif
 }
 
+// Batched transform of independent channels: chunks of channels share every kernel launch
+// (one descriptor row per (channel, scale)).  X: host [n_chan][n0].
 int cwtb_cwt_batch(cwtb_ctx *c, const void *X, int x_is_f32, int n_chan, int64_t n0, double dt,
                    const double *scales, int n_scales, int family, double param, int precision,
                    double *power_out, void *W_out) {
-  if (!c || !X || n_chan < 1) return fail(c, CWTB_ERR_ARG, "cwt_batch: bad argument");
-  const size_t esz_in = x_is_f32 ? 4 : 8;
-  const size_t wsz = (precision == CWTB_F64 ? 16 : 8) * (size_t)n_scales * n0;
-  for (int ch = 0; ch < n_chan; ++ch) {
-    int e = cwtb_cwt(c, (const char *)X + (size_t)ch * n0 * esz_in, x_is_f32, n0, dt, scales, n_scales,
-                     family, param, precision, nullptr);
+  if (!c || !X || n_chan < 1 || n0 < 1 || n_scales < 1) return fail(c, CWTB_ERR_ARG, "cwt_batch: bad argument");
+  if (family == CWTB_TABLE) return fail(c, CWTB_ERR_UNSUPPORTED, "cwt_batch needs an analytic wavelet family");
+  const bool f32 = (precision == CWTB_F32);
+  const size_t esz_in = x_is_f32 ? 4 : 8, esz = f32 ? 4 : 8;
+  const size_t wrow = (f32 ? 8 : 16) * (size_t)n0;
+  // channels per chunk: coefficients of a chunk <= batch_bytes, rows <= 32768
+  size_t per_chan = wrow * n_scales;
+  int nb = (int)std::max<size_t>(1, std::min<size_t>(c->batch_bytes / std::max<size_t>(per_chan, 1), 32768 / n_scales));
+  nb = std::max(1, std::min(nb, n_chan));
+  std::vector<unsigned char> conv;
+  for (int ch0 = 0; ch0 < n_chan; ch0 += nb) {
+    const int nc = std::min(nb, n_chan - ch0);
+    int e = prepare(c, n0, dt, scales, n_scales, family, param, precision, nullptr, nc);
     if (e) return e;
-    if (power_out && (e = cwtb_global_power(c, power_out + (size_t)ch * n_scales))) return e;
-    if (W_out && (e = cwtb_get_w(c, (char *)W_out + (size_t)ch * wsz, 0, 0, n_scales))) return e;
+    if ((e = ensure(c, c->sig, (size_t)nc * n0 * esz))) return e;
+    const char *src = (const char *)X + (size_t)ch0 * n0 * esz_in;
+    if ((x_is_f32 != 0) == f32) {
+      RT(rt_h2d(c->sig.p, src, (size_t)nc * n0 * esz, c->stream));
+    } else {
+      conv.resize((size_t)nc * n0 * esz);
+      const size_t cnt = (size_t)nc * n0;
+      if (f32) for (size_t i = 0; i < cnt; ++i) ((float *)conv.data())[i] = (float)((const double *)src)[i];
+      else for (size_t i = 0; i < cnt; ++i) ((double *)conv.data())[i] = (double)((const float *)src)[i];
+      RT(rt_h2d(c->sig.p, conv.data(), conv.size(), c->stream));
+    }
+    RT(rt_sync(c->stream));
+    c->job_dsig = c->sig.p;
+    c->job.sig_is_f32 = f32;
+    if ((e = timed_run(c, c->sig.p, 1, &c->last_ms))) return e;
+    if (power_out && (e = cwtb_global_power(c, power_out + (size_t)ch0 * n_scales))) return e;
+    if (W_out && (e = cwtb_get_w(c, (char *)W_out + (size_t)ch0 * per_chan, 0, 0, nc * n_scales))) return e;
   }
+  return 0;
+}
+
+// Device-resident batched transform for benchmarks: d_X [n_chan][n0] of the engine's real
+// type; all channels in one chunk (rows = n_chan * n_scales <= 60000).  W stays on the device
+// (cwtb_w_device_ptr), per-row mean power is optionally copied to power_out.
+int cwtb_cwt_batch_dev(cwtb_ctx *c, const void *d_X, int n_chan, int64_t n0, double dt, const double *scales,
+                       int n_scales, int family, double param, int precision, double *power_out) {
+  if (!c || !d_X || n_chan < 1) return fail(c, CWTB_ERR_ARG, "cwt_batch_dev: bad argument");
+  if (family == CWTB_TABLE) return fail(c, CWTB_ERR_UNSUPPORTED, "cwt_batch needs an analytic wavelet family");
+  int e = prepare(c, n0, dt, scales, n_scales, family, param, precision, nullptr, n_chan);
+  if (e) return e;
+  c->job_dsig = d_X;
+  c->job.sig_is_f32 = (precision == CWTB_F32);
+  if ((e = timed_run(c, d_X, 1, &c->last_ms))) return e;
+  if (power_out) return cwtb_global_power(c, power_out);
   return 0;
 }
 

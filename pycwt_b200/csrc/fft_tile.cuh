@@ -38,12 +38,21 @@ namespace cwtb {
 #ifndef CWTB_MINB
 #define CWTB_MINB 1
 #endif
+#ifndef CWTB_UNROLL_B
+#define CWTB_UNROLL_B 1
+#endif
+#define CWTB_STR_(x) #x
+#define CWTB_STR(x) CWTB_STR_(x)
+#define CWTB_PRAGMA_UNROLL_B _Pragma(CWTB_STR(unroll CWTB_UNROLL_B))
 constexpr int NT = CWTB_NT;  // threads per CTA
 constexpr int KT = 4096;    // (legacy) size of a master table e^{2 pi i t / KT}
 // Pass twiddle tables: for a pass of radix R on sub-transforms of length L the factor
 // w_L^{j c} (c = 1..R-1, j < L/R) is stored at  tw[tw_offset(L) + (c-1)*(L/R) + j], i.e. lanes
 // (consecutive j) read consecutive entries.  Each L has one radix in the plans below.
-HD constexpr int tw_radix(int L) { return L == 32 ? 4 : (L == 256 ? 16 : 8); }
+#ifndef CWTB_PLAN256_3PASS
+#define CWTB_PLAN256_3PASS 1
+#endif
+HD constexpr int tw_radix(int L) { return L == 32 ? 4 : (L == 256 ? (CWTB_PLAN256_3PASS ? 4 : 16) : 8); }
 HD constexpr int tw_count(int L) { return (tw_radix(L) - 1) * (L / tw_radix(L)); }
 HD constexpr int tw_offset(int L) {
   return L == 32 ? 0 : (L == 64 ? tw_count(32) : tw_offset(L / 2) + tw_count(L / 2));
@@ -73,7 +82,11 @@ CWTB_PLAN(16, 16, 1, 1)
 CWTB_PLAN(32, 4, 8, 1)
 CWTB_PLAN(64, 8, 8, 1)
 CWTB_PLAN(128, 8, 16, 1)
+#if CWTB_PLAN256_3PASS
+CWTB_PLAN(256, 4, 8, 8)
+#else
 CWTB_PLAN(256, 16, 16, 1)
+#endif
 CWTB_PLAN(512, 8, 8, 8)
 CWTB_PLAN(1024, 8, 8, 16)
 #undef CWTB_PLAN
@@ -192,6 +205,35 @@ template <typename T, int K> struct SmemLoader {
   }
 };
 
+// shared-memory tile whose rows still need the first-kernel twist
+//   e^{2 pi i k1 p / (K1 M)} = e^{2 pi i (k1 p K2) / N},  k1 = pos - K [pos*K2 >= rsplit],
+// applied while loading: the R factors of a thread do not depend on b, so they live in registers
+// (one per-lane table lookup, the rest by multiplying with warp-uniform steps).
+template <typename T, int K, int R> struct SmemTwistLoader {
+  using V = cx<T>;
+  const V *sm;
+  NTab nt;
+  int rsplit_row;   // first row (pos) whose residues are >= rsplit  (rsplit is a multiple of K2)
+  unsigned pk2;     // p * K2
+  int base, stride;
+  V tw[R];
+  HD void begin(int base_, int stride_, int, int) {
+    base = base_; stride = stride_;
+    V e = nroot_t<T>(nt, (unsigned)base * pk2);
+    const V se = nroot_t<T>(nt, (unsigned)stride * pk2);
+    const V ne = nroot_t<T>(nt, (unsigned)(-K) * pk2);
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      tw[i] = (base + i * stride >= rsplit_row) ? cmul(e, ne) : e;
+      e = cmul(e, se);
+    }
+  }
+  HD void load(int b, V (&x)[R]) const {
+#pragma unroll
+    for (int i = 0; i < R; ++i) x[i] = cmul(sm[Lay<T, K>::phys(b, base + i * stride)], tw[i]);
+  }
+};
+
 // rows of a [rows][K] global array (second-pass kernel: Z[u][r2])
 template <typename T, int K> struct RowLoader {
   using V = cx<T>;
@@ -270,6 +312,7 @@ HD void pass_mid(cx<T> *sm, const cx<T> *__restrict__ tw, Loader &ld, int tid) {
       twv[c] = w;
     }
     ld.begin(g * L + j, Ln, bg, GROUPS);
+    CWTB_PRAGMA_UNROLL_B
     for (int b = bg; b < P; b += GROUPS) {
       V x[R];
       ld.load(b, x);

@@ -17,6 +17,8 @@ struct ScaleDesc {
   int log2K;       // pruned transform length K' = 1 << log2K  (K' == Np: dense)
   int rsplit;      // residue r >= rsplit  <->  signed bin k = r - K'
   int trow;        // row in the caller's psi_ft table (CWTB_TABLE family)
+  int chan;        // channel of a batched transform: spectrum at spec + chan*Np
+  int pad_;
   long long boff;  // offset of this scale's band product B[] in the band buffer
 };
 
@@ -64,8 +66,8 @@ template <typename T> HD cx<T> rot_unit(cx<T> v, int unit) {
 
 // value of x^[bin] * conj(psi_ft)(s, k) * norm / Np  for one scale
 template <typename T>
-HD cx<T> band_value(const Fam &fp, const ScaleDesc &d, const cx<T> *spec, unsigned bin, int k) {
-  cx<T> v = ldg(&spec[bin]);
+HD cx<T> band_value(const Fam &fp, const ScaleDesc &d, const cx<T> *spec, unsigned bin, int k, unsigned N) {
+  cx<T> v = ldg(&spec[(size_t)d.chan * N + bin]);
   if (fp.family == 3) {
     double2 t = ldg(&fp.table[(size_t)d.trow * fp.tpitch + bin]);
     cx<T> tt = mk<T>((T)(t.x * d.amp), (T)(t.y * d.amp));
@@ -126,14 +128,21 @@ template <typename T, int SIGN> struct ZStorer {
   V *Z;
   NTab nt;
   int p, M, r20, bmax;
-  template <int R> HD void store(int b, int ql, int qs, V (&x)[R]) const {
+  int cached_b = -1;   // the step factor depends on b only: looked up once per thread
+  V cached_st;
+  template <int R> HD void store(int b, int ql, int qs, V (&x)[R]) {
     if (b >= bmax) return;
     const unsigned r2 = (unsigned)(r20 + b);
     const unsigned u = (unsigned)(p + ql * M);
     const unsigned du = (unsigned)(qs * M);
     V t = nroot_t<T>(nt, r2 * u);
-    V st = nroot_t<T>(nt, r2 * du);
-    if (SIGN < 0) { t.y = -t.y; st.y = -st.y; }
+    if (b != cached_b) {
+      cached_st = nroot_t<T>(nt, r2 * du);
+      if (SIGN < 0) cached_st.y = -cached_st.y;
+      cached_b = b;
+    }
+    const V st = cached_st;
+    if (SIGN < 0) t.y = -t.y;
     V *dst = Z + (size_t)u * K2C + r2;
 #pragma unroll
     for (int c = 0; c < R; ++c) {
@@ -378,10 +387,10 @@ template <typename T, int K1, int MODE, int SIGN> struct PassABody {
       const unsigned r = (unsigned)pos * K2C + (unsigned)r2;
       if (MODE == MODE_DENSE) {
         const int k = (int)r - (r >= a.N / 2 ? (int)a.N : 0);
-        return band_value<T>(a.fam, d, a.spec, r, k);
+        return band_value<T>(a.fam, d, a.spec, r, k, a.N);
       } else if (MODE == MODE_BAND) {
         V v = ldg(&a.Bbuf[d.boff + r]);
-        if (p == 0) return v;
+        if (p == 0 || NP > 1) return v;   // multi-pass plans apply the twist in pass 1
         const int k1 = pos - ((int)r >= d.rsplit ? K1 : 0);
         // e^{2 pi i k1 p / (K1 M)} = e^{2 pi i (k1 p K2) / N}
         V w = nroot_t<T>(a.nt, (unsigned)k1 * (unsigned)p * (unsigned)K2C);
@@ -424,9 +433,18 @@ template <typename T, int K1, int MODE, int SIGN> struct PassABody {
         sm[LY::phys(b, pos)] = src.get(pos, r20 + b);
       }
     } else if constexpr (PH == 1) {
-      SmemLoader<T, K1> ld;
-      ld.sm = sm;
-      tile_first<T, K1, SIGN>(sm, a.tw, ld, tid);
+      if (MODE == MODE_BAND && p != 0) {
+        SmemTwistLoader<T, K1, Plan<K1>::R1> ld;
+        ld.sm = sm;
+        ld.nt = a.nt;
+        ld.rsplit_row = a.descs[a.first + by].rsplit / K2C;
+        ld.pk2 = (unsigned)p * (unsigned)K2C;
+        tile_first<T, K1, SIGN>(sm, a.tw, ld, tid);
+      } else {
+        SmemLoader<T, K1> ld;
+        ld.sm = sm;
+        tile_first<T, K1, SIGN>(sm, a.tw, ld, tid);
+      }
     } else if constexpr (PH == 2 && NP == 3) {
       tile_second<T, K1, SIGN>(sm, a.tw, tid);
     } else {
@@ -459,7 +477,7 @@ template <typename T> struct BandBody {
       if (r >= K) return;
       const int k = r - (r >= d.rsplit ? K : 0);
       V v = mk<T>(0, 0);
-      if (k >= d.k_lo && k <= d.k_hi) v = band_value<T>(a.fam, d, a.spec, (unsigned)k & (a.N - 1), k);
+      if (k >= d.k_lo && k <= d.k_hi) v = band_value<T>(a.fam, d, a.spec, (unsigned)k & (a.N - 1), k, a.N);
       a.Bbuf[d.boff + r] = v;
     }
   }
@@ -572,7 +590,7 @@ template <typename T> struct TinyBody {
     double sr = 0, si = 0;
     for (unsigned r = 0; r < a.N; ++r) {
       const int k = (int)r - (r >= a.N / 2 && a.N > 1 ? (int)a.N : 0);
-      V v = band_value<T>(a.fam, d, a.spec, r, k);
+      V v = band_value<T>(a.fam, d, a.spec, r, k, a.N);
       double sn, cs;
       sincospi_hd(2.0 * (double)((r * (unsigned)n) % a.N) / (double)a.N, &sn, &cs);
       sr += (double)v.x * cs - (double)v.y * sn;

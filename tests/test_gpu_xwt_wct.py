@@ -164,14 +164,39 @@ def test_xwt_wct_config4_properties(pycwt):
 
 
 def test_cwt_batch_channels(pycwt):
-    """Config 5 flavour: independent float32 channels, fp32 engine, power spectra + W."""
+    """Config 5 flavour: independent float32 channels, fp32 engine, power spectra + W.  All
+    channels of a chunk share every kernel launch (one descriptor row per channel x scale)."""
     rs = np.random.RandomState(1)
     X = rs.randn(6, 4096).astype(np.float32)
     sj = 2.0 * 2 ** (np.arange(0, 40) / 4.0)
     eng = pycwt.default_engine()
     power, W = eng.cwt_batch(X, 1.0, sj, 0, 6.0, precision=1, want_w=True)
-    for ch in (0, 5):
+    for ch in (0, 3, 5):
         Wr = orc.cwt(X[ch].astype(np.float64), 1.0, wavelet=orc.Morlet(6),
                      freqs=1 / (orc.Morlet(6).flambda() * sj))[0]
         assert relerr(W[ch], Wr) < 1e-5
         assert relerr(power[ch], (np.abs(Wr) ** 2).mean(axis=1)) < 1e-5
+
+
+def test_cwt_batch_fp64_two_kernel_sizes_and_device_variant(pycwt):
+    """Batched fp64 channels long enough for the direct and two-kernel classes; the batched
+    result must equal the per-channel transform bit for bit (same kernels, same order)."""
+    rs = np.random.RandomState(2)
+    n0, nch = 2 ** 15, 3
+    X = rs.randn(nch, n0)
+    sj = 2.0 * 2 ** (np.arange(0, 26) / 2.0)
+    eng = pycwt.default_engine()
+    power, W = eng.cwt_batch(X, 1.0, sj, 0, 6.0, precision=0, want_w=True)
+    for ch in range(nch):
+        Wc = eng.cwt(X[ch], 1.0, sj, 0, 6.0)
+        assert np.array_equal(W[ch], Wc)
+    Wr = orc.cwt(X[1], 1.0, wavelet=orc.Morlet(6), freqs=1 / (orc.Morlet(6).flambda() * sj))[0]
+    assert relerr(W[1], Wr) < TOL
+    # device-resident entry point
+    d = eng.dev_alloc(X.nbytes)
+    eng.h2d(d, X)
+    p2 = eng.cwt_batch_dev(d, nch, n0, 1.0, sj, 0, 6.0, precision=0, want_power=True)
+    eng.dev_free(d)
+    assert relerr(p2, power) < 1e-13
+    W2 = eng.get_w(nch * len(sj), n0).reshape(nch, len(sj), n0)
+    assert np.array_equal(W2, W)
