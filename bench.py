@@ -30,7 +30,10 @@ DT, S0, DJ, J = 1.0, 2.0, 1.0 / 16, 255
 F0 = 6.0
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernels, from the
 # `ncu --set full` captures summarised under profiles/ (filled in per round; None = not captured)
-TRAFFIC = {}
+# r1: PassBBody<double,1>, 16-row launch: 268.5 MB read + 215.5 MB written = 30.25 MB per row
+# (algorithmic 16.78 MB per row: the Z intermediate of the two-kernel scales is read back from
+# DRAM); scaled to the 32-row launches of the bench step.
+TRAFFIC = {"PassBBody": 32 * 30.25e6, "SingleBody": 16 * 13.56e6, "DirectBody": 16 * 13.51e6}
 METRIC = "cwt_scale_points_per_sec"
 UNIT = "scale-points/s"
 

@@ -1,0 +1,78 @@
+"""CPU-only logic tests of the CUDA kernel bodies through the host-emulation build.
+
+tests/_emu/libcwtb200_emu.so is the SAME kernel source compiled with -DCWTB_HOST_EMU, where
+every CTA runs as a plain C++ loop over (phase, thread).  It exists so that index maths,
+plans, pruning and epilogues can be checked where no GPU is present (the build container).
+It is test infrastructure only: the package never loads it (pycwt_b200._engine.LIB_PATH is the
+sm_100a library) and these tests patch the loader path only for their own duration."""
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden, relerr, golden_cwt_kwargs
+from oracle import cwt_oracle as orc
+
+
+@pytest.fixture(scope="module")
+def emu():
+    import os
+    from pycwt_b200 import build as _build, _engine
+    lib = _build.build_emulation(os.path.join(ROOT, "tests", "_emu"))
+    eng = _engine.Engine(0, lib_path=lib)
+    assert "emulation" in eng.version()
+    yield eng
+    eng.close()
+
+
+def test_fft_plans_all_lengths(emu):
+    rs = np.random.RandomState(0)
+    for n in [2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 8192]:
+        x = rs.randn(2, n) + 1j * rs.randn(2, n)
+        assert relerr(emu.fft_c2c(x, -1), np.fft.fft(x, axis=1)) < 1e-13
+        assert relerr(emu.fft_c2c(x, +1, precision=1), np.fft.ifft(x, axis=1) * n) < 5e-6
+
+
+@pytest.mark.parametrize("name", ["nino3_morlet_tutorial", "nino3_paul_default", "nino3_dog3_odd",
+                                  "chirp4000_morlet"])
+def test_cwt_kernels_vs_reference_fixture(emu, name):
+    g = load_golden(name)
+    fam = {"morlet": 0, "paul": 1, "dog": 2}[str(g["wavelet"])]
+    W = emu.cwt(g["x"], float(g["dt"]), g["sj"], fam, float(g["param"]))
+    st = int(g["stride"])
+    assert relerr(W[:, ::st], g["W"]) < 1e-10
+
+
+def test_every_pruned_class_and_dense_path(emu):
+    n = 2 ** 15
+    t = np.arange(n) / n
+    x = np.sin(2 * np.pi * (50 * t + (n / 8) * t ** 2)) + 0.1 * np.random.RandomState(1).randn(n)
+    sj = 2.0 * 2 ** (np.arange(0, 27) / 2.0)
+    W = emu.cwt(x, 1.0, sj, 0, 6.0)
+    plan = emu.last_plan(len(sj))
+    assert set(plan) >= set(range(5, 16)), plan   # single, direct (11..13), two-kernel, dense
+    Wr = orc.cwt(x, 1.0, wavelet=orc.Morlet(6), freqs=1 / (orc.Morlet(6).flambda() * sj))[0]
+    assert relerr(W, Wr) < 1e-10
+    W32 = emu.cwt(x.astype(np.float32), 1.0, sj, 0, 6.0, precision=1)
+    assert relerr(W32, Wr) < 1e-5
+
+
+def test_xwt_wct_smooth_kernels(emu):
+    g = load_golden("ao_baltic_xwt_wct")
+    y1 = (g["y1"] - g["y1"].mean()) / g["y1"].std()
+    y2 = (g["y2"] - g["y2"].mean()) / g["y2"].std()
+    m = orc.Morlet(6)
+    sj = 2 * float(g["dt"]) / m.flambda() * 2 ** (np.arange(76) / 12.0)
+    assert relerr(emu.xwt(y1, y2, float(g["dt"]), sj, 0, 6.0), g["W12"]) < 1e-10
+    WCT, aWCT = emu.wct(y1, y2, float(g["dt"]), 1 / 12, sj, 0, 6.0, 14)
+    assert relerr(WCT, g["WCT"]) < 1e-10 and relerr(aWCT, g["aWCT"]) < 1e-10
+    s = load_golden("smooth_cases")
+    assert relerr(emu.smooth(s["Wc"], 1.0, s["sj"], 5), s["Sc"]) < 1e-10
+    assert relerr(emu.smooth(s["Wr"], 1.0, s["sj"], 5), s["Sr"]) < 1e-10
+
+
+def test_batched_rows_equal_single_channel(emu):
+    rs = np.random.RandomState(3)
+    X = rs.randn(3, 5000)
+    sj = 2.0 * 2 ** (np.arange(0, 20) / 2.0)
+    power, W = emu.cwt_batch(X, 1.0, sj, 0, 6.0, want_w=True)
+    for ch in range(3):
+        assert np.array_equal(W[ch], emu.cwt(X[ch], 1.0, sj, 0, 6.0))
