@@ -117,11 +117,46 @@ template <int SIGN, typename T, typename V> HD void dft16(V *x) {
   for (int i = 0; i < 8; ++i) { x[i] = cadd(e[i], o[i]); x[i + 8] = csub(e[i], o[i]); }
 }
 
+// radix-32: two radix-16 halves (even / odd inputs) + w32^c twiddles
+template <int SIGN, typename T, typename V> HD void dft32(V *x) {
+  V e[16], o[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { e[i] = x[2 * i]; o[i] = x[2 * i + 1]; }
+  dft16<SIGN, T>(e);
+  dft16<SIGN, T>(o);
+  // cos(k pi/16), sin(k pi/16), k = 1..7
+  const T c1 = (T)0.98078528040323044913, s1 = (T)0.19509032201612826785;
+  const T c2 = (T)0.92387953251128675613, s2 = (T)0.38268343236508977173;
+  const T c3 = (T)0.83146961230254523708, s3 = (T)0.55557023301960222474;
+  const T c5 = s3, s5 = c3, c6 = s2, s6 = c2, c7 = s1, s7 = c1;
+  V w;
+#define CWTB_TW32(k, cr, sr) w.x = (cr); w.y = SIGN * (sr); o[k] = cmul(o[k], w);
+  CWTB_TW32(1, c1, s1)
+  CWTB_TW32(2, c2, s2)
+  CWTB_TW32(3, c3, s3)
+  o[4] = mul_w8_1<SIGN, T>(o[4]);
+  CWTB_TW32(5, c5, s5)
+  CWTB_TW32(6, c6, s6)
+  CWTB_TW32(7, c7, s7)
+  o[8] = mul_si<SIGN>(o[8]);
+  CWTB_TW32(9, -s1, c1)
+  CWTB_TW32(10, -s2, c2)
+  CWTB_TW32(11, -s3, c3)
+  o[12] = mul_w8_3<SIGN, T>(o[12]);
+  CWTB_TW32(13, -c3, s3)
+  CWTB_TW32(14, -c2, s2)
+  CWTB_TW32(15, -c1, s1)
+#undef CWTB_TW32
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { x[i] = cadd(e[i], o[i]); x[i + 16] = csub(e[i], o[i]); }
+}
+
 template <int R, int SIGN, typename T, typename V> HD void dftR(V *x) {
   if (R == 2) dft2<SIGN>(x[0], x[1]);
   else if (R == 4) dft4<SIGN>(x[0], x[1], x[2], x[3]);
   else if (R == 8) dft8<SIGN, T>(x);
   else if (R == 16) dft16<SIGN, T>(x);
+  else if (R == 32) dft32<SIGN, T>(x);
 }
 
 }  // namespace cwtb

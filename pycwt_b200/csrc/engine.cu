@@ -127,6 +127,8 @@ struct cwtb_ctx {
   int fused = 0;     // experimental: two-kernel scales through one persistent kernel (CWTB_FUSED=1)
   int ring = 3;      // Z ring slots of the fused kernel
   int num_sms = 148;
+  int pf_dist = 148;   // PassB: L2 prefetch distance in tiles (CWTB_PF_DIST)
+  int pf_dist_a = 148;  // PassA (band): L2 prefetch distance in tiles (CWTB_PF_DIST_A)
   size_t batch_bytes = (size_t)4 << 30;   // coefficients per chunk of cwtb_cwt_batch  // K' <= 2^13 handled by one kernel (K' > 1024: DirectBody)
   double2 *tw64 = nullptr;
   float2 *tw32 = nullptr;
@@ -554,6 +556,7 @@ static int fft_rows(cwtb_ctx *c, const void *in, int real_in, long long in_pitch
     b.Z = (const cx<T> *)c->Z.p; b.out = out; b.tw = Tw<T>::get(c); b.descs = nullptr;
     b.pitch = out_pitch; b.nout = nout; b.N = n; b.first = 0; b.row0 = r0;
     b.epi = grow ? EPI_GAUSS : EPI_STORE; b.grow = grow; b.post = post; b.zmod = 1 << 30;
+    b.pf_dist = 0; b.ny = nr;
     e = launch<PassBBody<T, SIGN>>(c, (n / K2C + Lay<T, K2C>::P - 1) / Lay<T, K2C>::P, nr, b);
     if (e) return e;
   }
@@ -802,10 +805,12 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
       PassAArgs<T> a{};
       a.descs = ddesc; a.spec = spec; a.Bbuf = Bbuf; a.Z = (V *)c->Z.p; a.tw = Tw<T>::get(c);
       a.fam = fam; a.nt = nt; a.N = N; a.first = cl.first + g0; a.row0 = 0; a.zmod = 1 << 30;
+      a.pf_dist = c->pf_dist_a;
       PassBArgs<T> b{};
       b.Z = (const V *)c->Z.p; b.out = W; b.tw = Tw<T>::get(c); b.descs = ddesc;
       b.pitch = job.n0; b.nout = job.n0; b.N = N; b.first = cl.first + g0; b.row0 = 0;
       b.epi = epi; b.grow = nullptr; b.post = 1.0; b.zmod = 1 << 30;
+      b.pf_dist = c->pf_dist; b.ny = ng;
       if (!dense) {
         BandArgs<T> ba{ddesc, spec, Bbuf, fam, N, cl.first + g0};
         if ((e = launch<BandBody<T>>(c, (K + NT * BandBody<T>::PER - 1) / (NT * BandBody<T>::PER), ng, ba)))
@@ -919,6 +924,8 @@ int cwtb_create(int device, cwtb_ctx **out) {
   if (const char *g = getenv("CWTB_BAND_EPS")) c->band_eps = atof(g);
   if (const char *g = getenv("CWTB_L2_PERSIST")) c->l2_persist = atoi(g);
   if (const char *g = getenv("CWTB_FUSED")) c->fused = atoi(g);
+  if (const char *g = getenv("CWTB_PF_DIST")) c->pf_dist = std::max(0, atoi(g));
+  if (const char *g = getenv("CWTB_PF_DIST_A")) c->pf_dist_a = std::max(0, atoi(g));
   if (const char *g = getenv("CWTB_BATCH_MB")) c->batch_bytes = (size_t)std::max(1, atoi(g)) << 20;
   if (const char *g = getenv("CWTB_RING")) c->ring = std::max(1, atoi(g));
 #ifndef CWTB_HOST_EMU

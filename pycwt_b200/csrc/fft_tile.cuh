@@ -49,10 +49,15 @@ constexpr int KT = 4096;    // (legacy) size of a master table e^{2 pi i t / KT}
 // Pass twiddle tables: for a pass of radix R on sub-transforms of length L the factor
 // w_L^{j c} (c = 1..R-1, j < L/R) is stored at  tw[tw_offset(L) + (c-1)*(L/R) + j], i.e. lanes
 // (consecutive j) read consecutive entries.  Each L has one radix in the plans below.
+#ifndef CWTB_PLAN1024_R32
+#define CWTB_PLAN1024_R32 0
+#endif
 #ifndef CWTB_PLAN256_3PASS
 #define CWTB_PLAN256_3PASS 1
 #endif
-HD constexpr int tw_radix(int L) { return L == 32 ? 4 : (L == 256 ? (CWTB_PLAN256_3PASS ? 4 : 16) : 8); }
+HD constexpr int tw_radix(int L) {
+  return L == 32 ? 4 : (L == 256 ? (CWTB_PLAN256_3PASS ? 4 : 16) : ((L == 1024 && CWTB_PLAN1024_R32) ? 32 : 8));
+}
 HD constexpr int tw_count(int L) { return (tw_radix(L) - 1) * (L / tw_radix(L)); }
 HD constexpr int tw_offset(int L) {
   return L == 32 ? 0 : (L == 64 ? tw_count(32) : tw_offset(L / 2) + tw_count(L / 2));
@@ -88,7 +93,11 @@ CWTB_PLAN(256, 4, 8, 8)
 CWTB_PLAN(256, 16, 16, 1)
 #endif
 CWTB_PLAN(512, 8, 8, 8)
+#if CWTB_PLAN1024_R32
+CWTB_PLAN(1024, 32, 32, 1)
+#else
 CWTB_PLAN(1024, 8, 8, 16)
+#endif
 #undef CWTB_PLAN
 
 // Shared-memory layout of the tile: [b][pos] with a row pitch chosen so that both
@@ -134,6 +143,14 @@ struct TileBarrier {
     const char *s_ = (const char *)src;
     char *d_ = (char *)dst;
     for (unsigned i = 0; i < bytes; ++i) d_[i] = s_[i];
+#endif
+  }
+  // fire-and-forget prefetch of a global range into L2 (no barrier involved)
+  HD static void prefetch_l2(const void *src, unsigned bytes) {
+#if defined(__CUDA_ARCH__) && !defined(CWTB_HOST_EMU)
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+#else
+    (void)src; (void)bytes;
 #endif
   }
   HD void inval() const {
@@ -257,18 +274,26 @@ template <typename T, int K> struct RowLoader {
 // recurrence over b (a <- a * delta, delta = e^{2 pi i k bstep / N}).
 template <typename T, int K, int R> struct GenLoader {
   using V = cx<T>;
+  static constexpr int P = Lay<T, K>::P;
+  static constexpr int I = K / R;
+  static constexpr int GROUPS = (I >= NT) ? 1 : NT / I;
+  static constexpr bool ONE_SHOT = (P / GROUPS <= 1);   // one batch index per thread: no recurrence
   const V *B;      // K entries, residue order
   NTab nt;
   int rsplit;      // r >= rsplit  ->  k = r - K
   unsigned p0;
-  V a[R], d[R];
+  V a[ONE_SHOT ? 1 : R], d[ONE_SHOT ? 1 : R];
+  int base, stride;
+  unsigned pp;
   // Phase factors e^{2 pi i k_i p / N} (p = the thread's first index) and the per-step
   // multipliers e^{2 pi i k_i bstep / N} for the R residues r_i = base + i*stride, signed bins
   // k_i = r_i - K [r_i >= rsplit].  Only the i = 0 factors need a per-lane table lookup; the
   // others follow by multiplying with warp-uniform steps (broadcast loads), which keeps the
   // scattered 16-byte gathers off the LSU pipe.
-  HD void begin(int base, int stride, int bstart, int bstep) {
-    const unsigned pp = p0 + (unsigned)bstart;
+  HD void begin(int base_, int stride_, int bstart, int bstep) {
+    base = base_; stride = stride_;
+    pp = p0 + (unsigned)bstart;
+    if (ONE_SHOT) return;
     V e = nroot_t<T>(nt, (unsigned)base * pp);
     V de = nroot_t<T>(nt, (unsigned)base * (unsigned)bstep);
     const V se = nroot_t<T>(nt, (unsigned)stride * pp);
@@ -279,15 +304,27 @@ template <typename T, int K, int R> struct GenLoader {
     for (int i = 0; i < R; ++i) {
       const int r = base + i * stride;
       const bool neg = r >= rsplit;
-      d[i] = neg ? cmul(de, nd) : de;
-      a[i] = cmul(ldg(&B[r]), neg ? cmul(e, ne) : e);
+      d[ONE_SHOT ? 0 : i] = neg ? cmul(de, nd) : de;
+      a[ONE_SHOT ? 0 : i] = cmul(ldg(&B[r]), neg ? cmul(e, ne) : e);
       e = cmul(e, se);
       de = cmul(de, sd);
     }
   }
   HD void load(int, V (&x)[R]) {
+    if (ONE_SHOT) {
+      V e = nroot_t<T>(nt, (unsigned)base * pp);
+      const V se = nroot_t<T>(nt, (unsigned)stride * pp);
+      const V ne = nroot_t<T>(nt, (unsigned)(-K) * pp);
 #pragma unroll
-    for (int i = 0; i < R; ++i) { x[i] = a[i]; a[i] = cmul(a[i], d[i]); }
+      for (int i = 0; i < R; ++i) {
+        const int r = base + i * stride;
+        x[i] = cmul(ldg(&B[r]), (r >= rsplit) ? cmul(e, ne) : e);
+        e = cmul(e, se);
+      }
+      return;
+    }
+#pragma unroll
+    for (int i = 0; i < R; ++i) { x[i] = a[ONE_SHOT ? 0 : i]; a[ONE_SHOT ? 0 : i] = cmul(a[ONE_SHOT ? 0 : i], d[ONE_SHOT ? 0 : i]); }
   }
 };
 

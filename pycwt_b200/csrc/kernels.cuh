@@ -111,12 +111,20 @@ template <typename T> struct OutStorer {
   template <int R> HD void store(int b, int ql, int qs, V (&x)[R]) const {
     const int u = u0 + b;
     if (u >= U) return;
+    const size_t step = (size_t)qs * (size_t)U;
+    size_t n = (size_t)u + (size_t)ql * (size_t)U;
+    if (epi.mode == EPI_STORE && (long long)(n + (R - 1) * step) < nout) {
+      // common case: every output of this butterfly is kept -> pointer walk, no per-element test
+      V *p = row + n;
 #pragma unroll
-    for (int c = 0; c < R; ++c) {
-      long long n = u + (long long)(ql + c * qs) * U;
-      if (n < nout) {
+      for (int c = 0; c < R; ++c) { st_stream(p, x[c]); p += step; }
+      return;
+    }
+#pragma unroll
+    for (int c = 0; c < R; ++c, n += step) {
+      if ((long long)n < nout) {
         if (epi.mode == EPI_STORE) st_stream(&row[n], x[c]);
-        else row[n] = epi.apply(x[c], epi.mode == EPI_MULCONJ ? row[n] : x[c], n);
+        else row[n] = epi.apply(x[c], epi.mode == EPI_MULCONJ ? row[n] : x[c], (long long)n);
       }
     }
   }
@@ -230,34 +238,80 @@ template <typename T, int K1> struct DirectBody {
       }
     } else if constexpr (PH == 1) {
       const V *B = a.Bbuf + d.boff;
-      // r2 = tid + NT*it; phase e^{2 pi i r2 u0 / N} by recurrence over it, advanced over b
-      V e = nroot_t<T>(a.nt, (unsigned)tid * (unsigned)u0);
+      // Positions r2 = tid + NT*it are handled IB at a time: the K1*IB band values stay in
+      // registers while the K1 weights of each batch index b are read from shared memory once
+      // (they depend on (b, r1) only, except on the single row r1s that the signed-bin split
+      // cuts, where the sign is chosen per position).
+      constexpr int NIT = K / NT;
+      constexpr int IB = (8 / K1) < 1 ? 1 : ((8 / K1) < NIT ? (8 / K1) : NIT);
+      const int r1s = d.rsplit / K, r2s = d.rsplit % K;   // residues >= rsplit are "negative"
+      V e = nroot_t<T>(a.nt, (unsigned)tid * (unsigned)u0);    // e^{2 pi i r2 u0 / N}
       const V se = nroot_t<T>(a.nt, (unsigned)NT * (unsigned)u0);
-      V dr = nroot_t<T>(a.nt, (unsigned)tid);          // e^{2 pi i r2 / N}
+      V dr = nroot_t<T>(a.nt, (unsigned)tid);                  // e^{2 pi i r2 / N}
       const V sdr = nroot_t<T>(a.nt, (unsigned)NT);
-      for (int it = 0; it < K / NT; ++it) {
-        const int r2 = tid + NT * it;
-        V bv[K1];
-        bool neg[K1];
-#pragma unroll
-        for (int r1 = 0; r1 < K1; ++r1) {
-          bv[r1] = ldg(&B[r1 * K + r2]);
-          neg[r1] = (r1 * K + r2) >= d.rsplit;
-        }
-        V t = e;
-#pragma unroll
-        for (int b = 0; b < P; ++b) {
-          V acc = mk<T>(0, 0);
+      if constexpr (K1 >= 8) {
+        // many terms per position: one position at a time, weights straight from shared memory
+        for (int it = 0; it < NIT; ++it) {
+          const int r2 = tid + NT * it;
+          V bv[K1];
+          bool neg[K1];
 #pragma unroll
           for (int r1 = 0; r1 < K1; ++r1) {
-            const V w = wt[(b * 2 + (neg[r1] ? 1 : 0)) * K1 + r1];
-            acc = cadd(acc, cmul(bv[r1], w));
+            bv[r1] = ldg(&B[r1 * K + r2]);
+            neg[r1] = (r1 * K + r2) >= d.rsplit;
           }
-          sm[LY::phys(b, r2)] = cmul(acc, t);
-          t = cmul(t, dr);
+          V t = e;
+#pragma unroll
+          for (int b = 0; b < P; ++b) {
+            V acc = mk<T>(0, 0);
+#pragma unroll
+            for (int r1 = 0; r1 < K1; ++r1)
+              acc = cadd(acc, cmul(bv[r1], wt[(b * 2 + (neg[r1] ? 1 : 0)) * K1 + r1]));
+            sm[LY::phys(b, r2)] = cmul(acc, t);
+            t = cmul(t, dr);
+          }
+          e = cmul(e, se);
+          dr = cmul(dr, sdr);
         }
-        e = cmul(e, se);
-        dr = cmul(dr, sdr);
+      } else
+      for (int it0 = 0; it0 < NIT; it0 += IB) {
+        V bv[IB][K1], t[IB], dd[IB];
+#pragma unroll
+        for (int q = 0; q < IB; ++q) {
+          const int r2 = tid + NT * (it0 + q);
+#pragma unroll
+          for (int r1 = 0; r1 < K1; ++r1) bv[q][r1] = ldg(&B[r1 * K + r2]);
+          t[q] = e;
+          dd[q] = dr;
+          e = cmul(e, se);
+          dr = cmul(dr, sdr);
+        }
+#pragma unroll
+        for (int b = 0; b < P; ++b) {
+          V acc[IB];
+#pragma unroll
+          for (int q = 0; q < IB; ++q) acc[q] = mk<T>(0, 0);
+#pragma unroll
+          for (int r1 = 0; r1 < K1; ++r1) {
+            if (r1 != r1s) {   // warp-uniform: one weight for the whole row
+              const V w = wt[(b * 2 + (r1 > r1s ? 1 : 0)) * K1 + r1];
+#pragma unroll
+              for (int q = 0; q < IB; ++q) acc[q] = cadd(acc[q], cmul(bv[q][r1], w));
+            } else {
+              const V wp = wt[(b * 2 + 0) * K1 + r1], wn = wt[(b * 2 + 1) * K1 + r1];
+#pragma unroll
+              for (int q = 0; q < IB; ++q) {
+                const bool neg = (tid + NT * (it0 + q)) >= r2s;
+                acc[q] = cadd(acc[q], cmul(bv[q][r1], neg ? wn : wp));
+              }
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < IB; ++q) {
+            sm[LY::phys(b, tid + NT * (it0 + q))] = cmul(acc[q], t[q]);
+            t[q] = cmul(t[q], dd[q]);
+          }
+        }
       }
     } else if constexpr (PH == 2) {
       SmemLoader<T, K> ld;
@@ -290,6 +344,8 @@ template <typename T> struct PassBArgs {
   int first, row0;
   int epi;
   int zmod;                // Z slot of row `by` is by % zmod
+  int pf_dist;             // L2 prefetch distance in tiles (0 = off)
+  int ny;                  // gridDim.y of this launch (rows)
 };
 
 template <typename T, int SIGN> struct PassBBody {
@@ -315,6 +371,17 @@ template <typename T, int SIGN> struct PassBBody {
         const V *src = a.Z + (size_t)(by % a.zmod) * a.N + (size_t)u0 * K;
         for (int b = 0; b < nvalid; ++b)
           tb.copy(sm + LY::phys(b, 0), src + (size_t)b * K, (unsigned)(K * sizeof(V)));
+        // warm L2 with the tile a CTA `pf_dist` blocks ahead will load (same row of the grid,
+        // or the next row when this one is exhausted): its TMA copies then hit L2
+        if (a.pf_dist > 0) {
+          long long t = (long long)bx + a.pf_dist;
+          int py = by;
+          const int tiles = (U + LY::P - 1) / LY::P;
+          while (t >= tiles && py + 1 < a.ny) { t -= tiles; ++py; }
+          if (t < tiles && t * LY::P + LY::P <= U)
+            TileBarrier::prefetch_l2(a.Z + (size_t)(py % a.zmod) * a.N + (size_t)t * LY::P * K,
+                                     (unsigned)(LY::P * K * sizeof(V)));
+        }
       }
       for (int b = nvalid; b < LY::P; ++b)
         for (int i = tid; i < K; i += NT) sm[LY::phys(b, i)] = mk<T>(0, 0);
@@ -361,6 +428,7 @@ template <typename T> struct PassAArgs {
   unsigned N;
   int first, row0;
   int zmod;            // Z slot of row `by` is by % zmod (ring of Z buffers in the fused kernel)
+  int pf_dist;         // L2 prefetch distance in tiles for the band-product rows (0 = off)
 };
 
 template <typename T, int K1, int MODE, int SIGN> struct PassABody {
@@ -428,6 +496,17 @@ template <typename T, int K1, int MODE, int SIGN> struct PassABody {
       }
     } else if constexpr (PH == 0) {
       Src src(a, by, p);
+      // warm L2 with the band-product rows of the tile `pf_dist` blocks ahead (same scale)
+      if (MODE == MODE_BAND && a.pf_dist > 0 && T2 * sizeof(V) >= 256) {
+        const int tiles = M * NTILE2;
+        const int t = bx + a.pf_dist;
+        if (t < tiles) {
+          const int r20n = (t % NTILE2) * T2;
+          const V *base = a.Bbuf + src.d.boff + r20n;
+          for (int pos = tid; pos < K1; pos += NT)
+            TileBarrier::prefetch_l2(base + (size_t)pos * K2C, (unsigned)(T2 * sizeof(V)));
+        }
+      }
       for (int idx = tid; idx < K1 * T2; idx += NT) {
         const int b = idx % T2, pos = idx / T2;
         sm[LY::phys(b, pos)] = src.get(pos, r20 + b);
