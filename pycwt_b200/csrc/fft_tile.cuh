@@ -102,19 +102,24 @@ CWTB_PLAN(1024, 8, 8, 16)
 
 // Shared-memory layout of the tile: [b][pos] with a row pitch chosen so that both
 // access patterns (lanes over pos, lanes over b) are bank-conflict free.
-template <typename T, int K> struct Lay {
+template <typename T, int K, bool ROWS = false> struct Lay {
   static constexpr int TILE = TileCfg<T>::TILE;
   static constexpr int P = TILE / K;
   static constexpr int Q = TileCfg<T>::Q;
-  // Rows are contiguous (so a bulk-async copy can fill one).  Pitch K+1 makes the b-lanes of
-  // the last pass hit distinct banks when P >= Q; for P = Q/2 the pitch K+2 spreads the b-lanes
-  // over every second bank group and the two positions sharing a quarter-warp collide 2-way on
-  // the last pass's reads only (shared-memory bandwidth has headroom).
-  static constexpr int PITCH = (P < Q) ? K + 2 : K + 1;
+  // ROWS = true: every row is one contiguous run (a bulk-async copy fills it).  Pitch K+1 makes
+  // the b-lanes of the last pass hit distinct banks when P >= Q; for P = Q/2 the pitch K+2
+  // spreads the b-lanes over every second bank group and the two positions sharing a
+  // quarter-warp collide 2-way on the last pass's reads.
+  // ROWS = false (default): for P < Q one pad element is inserted after every 16 positions
+  // (pos + pos/16), which shifts the second position of a quarter-warp onto the free bank
+  // groups -> conflict-free in every pass.
+  static constexpr bool SKEW = (P < Q) && !ROWS;
+  static constexpr int KS = SKEW ? K + K / 16 : K;
+  static constexpr int PITCH = (P < Q) ? (KS - (KS % Q) + 2 + ((KS % Q) > 2 ? Q : 0)) : K + 1;
   static constexpr int ELEMS = P * PITCH;
   static constexpr size_t TILE_BYTES = (size_t)ELEMS * 2 * sizeof(T);
   static constexpr size_t BYTES = (Plan<K>::NP == 1) ? 0 : TILE_BYTES;
-  HD static int phys(int b, int pos) { return b * PITCH + pos; }
+  HD static int phys(int b, int pos) { return b * PITCH + pos + (SKEW ? (pos >> 4) : 0); }
 };
 
 // ---- bulk asynchronous copy (TMA, cp.async.bulk) global -> shared with an mbarrier --------
@@ -211,14 +216,14 @@ template <typename T> HD cx<T> nroot_t(const NTab &t, unsigned e) {
 // Interface:  begin(base, stride, bstart, bstep);  load(b, x[R])
 //   the R inputs of the butterfly sit at positions base + i*stride.
 
-template <typename T, int K> struct SmemLoader {
+template <typename T, int K, bool ROWS = false> struct SmemLoader {
   using V = cx<T>;
   const V *sm;
   int base, stride;
   HD void begin(int base_, int stride_, int, int) { base = base_; stride = stride_; }
   template <int R> HD void load(int b, V (&x)[R]) const {
 #pragma unroll
-    for (int i = 0; i < R; ++i) x[i] = sm[Lay<T, K>::phys(b, base + i * stride)];
+    for (int i = 0; i < R; ++i) x[i] = sm[Lay<T, K, ROWS>::phys(b, base + i * stride)];
   }
 };
 
@@ -330,10 +335,10 @@ template <typename T, int K, int R> struct GenLoader {
 
 // ---- passes --------------------------------------------------------------------
 // One non-final pass on sub-transforms of length L (K/L of them per row).
-template <typename T, int K, int L, int R, int SIGN, class Loader>
+template <typename T, int K, int L, int R, int SIGN, class Loader, bool ROWS = false>
 HD void pass_mid(cx<T> *sm, const cx<T> *__restrict__ tw, Loader &ld, int tid) {
   using V = cx<T>;
-  using LY = Lay<T, K>;
+  using LY = Lay<T, K, ROWS>;
   constexpr int Ln = L / R, I = K / R, P = LY::P;
   constexpr int LANES = (I >= NT) ? NT : I;
   constexpr int GROUPS = NT / LANES;
@@ -364,10 +369,10 @@ HD void pass_mid(cx<T> *sm, const cx<T> *__restrict__ tw, Loader &ld, int tid) {
 
 // Final pass: radix R = Plan<K>::RL on K/R sub-transforms per row, lanes over b.
 // Storer interface: store(b, qlow, qstride, x[R])  with output index q = qlow + c*qstride.
-template <typename T, int K, int SIGN, class Storer>
+template <typename T, int K, int SIGN, class Storer, bool ROWS = false>
 HD void pass_last(const cx<T> *sm, Storer &st, int tid) {
   using V = cx<T>;
-  using LY = Lay<T, K>;
+  using LY = Lay<T, K, ROWS>;
   constexpr int R = Plan<K>::RL, G = K / R, P = LY::P;
   for (int idx = tid; idx < G * P; idx += NT) {
     const int b = idx % P, g = idx / P;
@@ -386,15 +391,15 @@ template <typename T, int K> struct TilePhases {
   static constexpr int NP = Plan<K>::NP;  // number of phases of the multi-pass core
 };
 
-template <typename T, int K, int SIGN, class Loader>
+template <typename T, int K, int SIGN, class Loader, bool ROWS = false>
 HD void tile_first(cx<T> *sm, const cx<T> *tw, Loader &ld, int tid) {
-  pass_mid<T, K, K, Plan<K>::R1, SIGN>(sm, tw, ld, tid);
+  pass_mid<T, K, K, Plan<K>::R1, SIGN, Loader, ROWS>(sm, tw, ld, tid);
 }
-template <typename T, int K, int SIGN>
+template <typename T, int K, int SIGN, bool ROWS = false>
 HD void tile_second(cx<T> *sm, const cx<T> *tw, int tid) {  // only for 3-pass plans
-  SmemLoader<T, K> ld;
+  SmemLoader<T, K, ROWS> ld;
   ld.sm = sm;
-  pass_mid<T, K, K / Plan<K>::R1, Plan<K>::R2, SIGN>(sm, tw, ld, tid);
+  pass_mid<T, K, K / Plan<K>::R1, Plan<K>::R2, SIGN, SmemLoader<T, K, ROWS>, ROWS>(sm, tw, ld, tid);
 }
 
 }  // namespace cwtb

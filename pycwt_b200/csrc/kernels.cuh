@@ -352,7 +352,7 @@ template <typename T, int SIGN> struct PassBBody {
   using V = cx<T>;
   using Args = PassBArgs<T>;
   static constexpr int K = K2C;
-  using LY = Lay<T, K>;
+  using LY = Lay<T, K, true>;   // rows are filled by bulk-async copies: no skew
   static constexpr int NP = Plan<K>::NP;
   // phase 0: one thread issues the bulk-async (TMA) copies of the tile's rows -- the rows
   // Z[u0 .. u0+P) are contiguous in global memory -- then the FFT passes run from shared memory
@@ -387,11 +387,11 @@ template <typename T, int SIGN> struct PassBBody {
         for (int i = tid; i < K; i += NT) sm[LY::phys(b, i)] = mk<T>(0, 0);
     } else if constexpr (PH == 1) {
       tb.wait(0);
-      SmemLoader<T, K> ld;
+      SmemLoader<T, K, true> ld;
       ld.sm = sm;
-      tile_first<T, K, SIGN>(sm, a.tw, ld, tid);
+      tile_first<T, K, SIGN, SmemLoader<T, K, true>, true>(sm, a.tw, ld, tid);
     } else if constexpr (PH == 2 && NP == 3) {
-      tile_second<T, K, SIGN>(sm, a.tw, tid);
+      tile_second<T, K, SIGN, true>(sm, a.tw, tid);
     } else {
       const int row = a.descs ? a.descs[a.first + by].row : a.row0 + by;
       OutStorer<T> st;
@@ -406,7 +406,7 @@ template <typename T, int SIGN> struct PassBBody {
         st.epi.post = a.post;
         st.epi.nfreq = a.N;
       }
-      pass_last<T, K, SIGN>(sm, st, tid);
+      pass_last<T, K, SIGN, OutStorer<T>, true>(sm, st, tid);
       if (tid == 0) tb.inval();   // every thread passed wait() two barriers ago
     }
   }
@@ -455,6 +455,9 @@ template <typename T, int K1, int MODE, int SIGN> struct PassABody {
       const unsigned r = (unsigned)pos * K2C + (unsigned)r2;
       if (MODE == MODE_DENSE) {
         const int k = (int)r - (r >= a.N / 2 ? (int)a.N : 0);
+        // outside the scale's band the response is below the pruning threshold: same rule as
+        // the pruned classes (their band product is exactly zero there); skips the exp
+        if (a.fam.family != 3 && (k < d.k_lo || k > d.k_hi)) return mk<T>(0, 0);
         return band_value<T>(a.fam, d, a.spec, r, k, a.N);
       } else if (MODE == MODE_BAND) {
         V v = ldg(&a.Bbuf[d.boff + r]);
