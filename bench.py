@@ -33,7 +33,7 @@ F0 = 6.0
 # r1: PassBBody<double,1>, 16-row launch: 268.5 MB read + 215.5 MB written = 30.25 MB per row
 # (algorithmic 16.78 MB per row: the Z intermediate of the two-kernel scales is read back from
 # DRAM); scaled to the 32-row launches of the bench step.
-TRAFFIC = {"PassBBody": 32 * 30.25e6, "SingleBody": 16 * 13.56e6, "DirectBody": 16 * 13.51e6}
+TRAFFIC = {"PassBBody": 32 * 30.21e6, "SingleBody": 16 * 13.44e6, "DirectBody": 16 * 13.68e6}
 METRIC = "cwt_scale_points_per_sec"
 UNIT = "scale-points/s"
 
