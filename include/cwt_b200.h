@@ -105,9 +105,10 @@ int64_t cwtb_padded_length(cwtb_ctx *ctx);
  * consumers (DLPack / __cuda_array_interface__ wrappers). */
 void *cwtb_w_device_ptr(cwtb_ctx *ctx);
 
-/* Pipelined whole call for host callers: H2D signal, transform in groups of
- * scales, D2H of each group overlapped with the next group's kernels.
- * `out` should come from cwtb_host_alloc.  Equivalent to cwtb_cwt + cwtb_get_w. */
+/* Whole call for host callers: H2D signal, transform, one D2H of W into `out`
+ * (page-locked memory from cwtb_host_alloc makes the copy run at PCIe speed; the
+ * kernels take ~2 % of the copy time at the north-star size, so there is nothing
+ * to overlap).  Equivalent to cwtb_cwt + cwtb_get_w. */
 int cwtb_cwt_to_host(cwtb_ctx *ctx, const void *signal, int signal_is_f32,
                      int64_t n0, double dt, const double *scales, int n_scales,
                      int family, double param, int precision, void *out,

@@ -51,5 +51,7 @@ sj = 2.0 * 2 ** (np.arange(128) / 8.0)
 d = eng.dev_alloc(X.nbytes); eng.h2d(d, X)
 eng.cwt_batch_dev(d, nch, 2 ** 16, 1.0, sj, 0, 6.0, precision=1)
 ms = eng.bench_last(10)
+for k in sorted(eng.profile_last(), key=lambda k: -k["ms"])[:12]:
+    print("   %-40s launches %2d  ms %.4f  rows %5d  us/row %.3f" % (k["name"][:40], k["launches"], k["ms"], k["rows"], 1e3 * k["ms"] / max(k["rows"], 1)))
 print("config5 slice: %d channels x 128 scales x 2^16, fp32: %.3f ms -> %.3e scale-points/s, %.0f GB/s algorithmic (8192 ch on 8 GPUs = 16 such chunks per GPU)"
       % (nch, ms, nch * 128 * 65536 / ms * 1e3, nch * 128 * 65536 * 8 / ms / 1e6))

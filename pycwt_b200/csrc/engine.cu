@@ -29,7 +29,6 @@ using namespace cwtb;
 // ======================================================================================
 #ifdef CWTB_HOST_EMU
 typedef int rt_stream;
-typedef double rt_event;
 static inline int rt_malloc(void **p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 1; }
 static inline int rt_free(void *p) { free(p); return 0; }
 static inline int rt_host_alloc(void **p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 1; }
@@ -41,7 +40,6 @@ static inline int rt_sync(rt_stream) { return 0; }
 static inline const char *rt_errstr(int) { return "emulation error"; }
 #else
 typedef cudaStream_t rt_stream;
-typedef cudaEvent_t rt_event;
 static inline int rt_malloc(void **p, size_t n) { return (int)cudaMalloc(p, n ? n : 1); }
 static inline int rt_free(void *p) { return (int)cudaFree(p); }
 static inline int rt_host_alloc(void **p, size_t n) { return (int)cudaHostAlloc(p, n ? n : 1, cudaHostAllocDefault); }
@@ -118,10 +116,10 @@ struct NTabDev {
 struct cwtb_ctx {
   int device = 0;
   rt_stream stream{};
-  rt_stream copy_stream{};
   std::string err;
   double band_eps = 1e-20;
-  int group = 32;  // scales per two-kernel chunk (unfused path)
+  int group = 0;   // rows per two-kernel chunk; 0 = as many as fit in group_bytes of Z (CWTB_GROUP)
+  size_t group_bytes = (size_t)512 << 20;
   int l2_persist = 0;
   int direct_max_log2 = 13;
   int fused = 0;     // experimental: two-kernel scales through one persistent kernel (CWTB_FUSED=1)
@@ -722,6 +720,14 @@ static int launch_single(cwtb_ctx *c, const SingleArgs<T> &a, int count) {
   return launch<SingleBody<T, K>>(c, (M + P - 1) / P, count, a);
 }
 
+// rows (scale x channel) per chunk of the two-kernel path: the Z intermediate of a chunk is
+// rows * Np elements
+static int chunk_rows(const cwtb_ctx *c, unsigned N, size_t elem_bytes) {
+  if (c->group > 0) return c->group;
+  size_t g = c->group_bytes / ((size_t)N * elem_bytes);
+  return (int)std::max<size_t>(1, std::min<size_t>(g, 32768));
+}
+
 // all kernels of one transform: forward FFT of the (device, type T) signal, then every scale
 template <typename T>
 static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nullptr, int epi = EPI_STORE) {
@@ -752,7 +758,7 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
 
   NTab nt;
   if ((e = get_ntab(c, N, job.log2N, &nt))) return e;
-  const int G = std::max(1, c->group);
+  const int G = chunk_rows(c, N, sizeof(V));
   size_t bchunk = 0;   // band products of one chunk of two-kernel scales
   for (const ClassRun &cl : job.classes)
     if (cl.log2K > c->direct_max_log2 && cl.log2K < job.log2N)
@@ -833,7 +839,7 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
 
 // band-buffer offsets of the two-kernel scales depend on the chunk position; set them here
 static void assign_chunk_offsets(cwtb_ctx *c, Job &job) {
-  const int G = std::max(1, c->group);
+  const int G = chunk_rows(c, job.N, job.precision == CWTB_F64 ? sizeof(double2) : sizeof(float2));
   for (const ClassRun &cl : job.classes) {
     if (cl.log2K <= c->direct_max_log2 || cl.log2K == job.log2N) continue;
     for (int i = 0; i < cl.count; ++i)
@@ -916,11 +922,11 @@ int cwtb_create(int device, cwtb_ctx **out) {
 #ifndef CWTB_HOST_EMU
   if (cudaSetDevice(device) != cudaSuccess) { delete c; return CWTB_ERR_CUDA; }
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return CWTB_ERR_CUDA; }
-  if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return CWTB_ERR_CUDA; }
   cudaEventCreate(&c->e0);
   cudaEventCreate(&c->e1);
 #endif
-  if (const char *g = getenv("CWTB_GROUP")) c->group = std::max(1, atoi(g));
+  if (const char *g = getenv("CWTB_GROUP")) c->group = std::max(0, atoi(g));
+  if (const char *g = getenv("CWTB_GROUP_MB")) c->group_bytes = (size_t)std::max(1, atoi(g)) << 20;
   if (const char *g = getenv("CWTB_BAND_EPS")) c->band_eps = atof(g);
   if (const char *g = getenv("CWTB_L2_PERSIST")) c->l2_persist = atoi(g);
   if (const char *g = getenv("CWTB_FUSED")) c->fused = atoi(g);
@@ -957,7 +963,6 @@ void cwtb_destroy(cwtb_ctx *c) {
   cudaEventDestroy(c->e0);
   cudaEventDestroy(c->e1);
   cudaStreamDestroy(c->stream);
-  cudaStreamDestroy(c->copy_stream);
 #endif
   delete c;
 }

@@ -45,7 +45,6 @@ namespace cwtb {
 #define CWTB_STR(x) CWTB_STR_(x)
 #define CWTB_PRAGMA_UNROLL_B _Pragma(CWTB_STR(unroll CWTB_UNROLL_B))
 constexpr int NT = CWTB_NT;  // threads per CTA
-constexpr int KT = 4096;    // (legacy) size of a master table e^{2 pi i t / KT}
 // Pass twiddle tables: for a pass of radix R on sub-transforms of length L the factor
 // w_L^{j c} (c = 1..R-1, j < L/R) is stored at  tw[tw_offset(L) + (c-1)*(L/R) + j], i.e. lanes
 // (consecutive j) read consecutive entries.  Each L has one radix in the plans below.

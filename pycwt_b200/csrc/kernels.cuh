@@ -165,7 +165,7 @@ template <typename T> struct SingleArgs {
   const ScaleDesc *descs;  // device
   const cx<T> *Bbuf;       // band products
   cx<T> *W;                // [rows][n0]
-  const cx<T> *tw;         // master twiddle table (KT entries)
+  const cx<T> *tw;         // pass twiddle tables (fft_tile.cuh: tw_offset)
   NTab nt;
   long long n0;
   unsigned N;

@@ -76,3 +76,41 @@ def test_batched_rows_equal_single_channel(emu):
     power, W = emu.cwt_batch(X, 1.0, sj, 0, 6.0, want_w=True)
     for ch in range(3):
         assert np.array_equal(W[ch], emu.cwt(X[ch], 1.0, sj, 0, 6.0))
+
+
+def test_error_paths_report_status_and_message(emu):
+    """The C ABI never throws: bad calls return a negative status + message, which the
+    ctypes layer turns into EngineError."""
+    from pycwt_b200._engine import EngineError
+    x = np.random.RandomState(0).randn(64)
+    with pytest.raises(EngineError, match="family"):
+        emu.cwt(x, 1.0, np.array([2.0, 4.0]), 7, 6.0)
+    with pytest.raises(EngineError, match="order"):
+        emu.cwt(x, 1.0, np.array([2.0, 4.0]), 1, 2.5)          # Paul order must be an integer
+    with pytest.raises(EngineError, match="dt"):
+        emu.cwt(x, -1.0, np.array([2.0]), 0, 6.0)
+    with pytest.raises(EngineError, match="table"):
+        emu.cwt(x, 1.0, np.array([2.0]), 3, 0.0)                # CWTB_TABLE without a table
+    with pytest.raises(EngineError, match="2\\^20"):
+        emu.cwt(np.zeros(2 ** 20 + 1), 1.0, np.array([2.0]), 0, 6.0)   # Np = 2^21: not built yet
+    with pytest.raises(EngineError):
+        emu.set_band_eps(0.5)
+    with pytest.raises(ValueError):
+        emu.xwt(np.zeros(10), np.zeros(11), 1.0, np.array([2.0]), 0, 6.0)
+    # a failed call leaves the context usable
+    W = emu.cwt(x, 1.0, np.array([2.0, 4.0]), 0, 6.0)
+    assert W.shape == (2, 64) and np.isfinite(W).all()
+
+
+def test_table_family_matches_analytic(emu):
+    """CWTB_TABLE (duck-typed wavelets: host-evaluated response) == analytic Morlet path."""
+    rs = np.random.RandomState(2)
+    for n0 in (300, 3000):
+        x = rs.randn(n0)
+        sj = 2.0 * 2 ** (np.arange(12) / 2.0)
+        npad = orc.next_pow2(n0)
+        om = 2 * np.pi * np.fft.fftfreq(npad, 1.0)
+        table = (sj[:, None] * om[1] * npad) ** .5 * np.conj(orc.Morlet(6).psi_ft(sj[:, None] * om))
+        Wt = emu.cwt(x, 1.0, sj, 3, 0.0, table=table)
+        Wa = emu.cwt(x, 1.0, sj, 0, 6.0)
+        assert relerr(Wt, Wa) < 1e-13
