@@ -24,7 +24,7 @@ lo, hi = D.shard_range(nch_total, rank, world)
 X = np.random.RandomState(1000 + rank).randn(hi - lo, n0).astype(np.float32)   # this rank's channels
 eng = _engine.Engine(local)
 dev = torch.device("cuda", local)
-power, _ = eng.cwt_batch(X[:8], 1.0, sj, 0, 6.0, precision=1)                  # warm-up
+power, _ = eng.cwt_batch(X[:64], 1.0, sj, 0, 6.0, precision=1)                 # warm-up (same chunk shape: buffers allocated)
 if world > 1:
     dist.barrier(device_ids=[local])
 torch.cuda.synchronize()
