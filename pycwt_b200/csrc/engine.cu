@@ -131,7 +131,7 @@ struct cwtb_ctx {
   double2 *tw64 = nullptr;
   float2 *tw32 = nullptr;
   std::map<unsigned, NTabDev> ntabs;
-  Buf ctr, sig, sig2, spec, Z, B, W, W2, descs, table, scratch, C, A12, F, aux, rowd, win, mask, hist, noise;
+  Buf ctr, sig, sig2, spec, Z, Y, B, W, W2, descs, table, scratch, C, A12, F, aux, rowd, win, mask, hist, noise;
   Job job;
   const void *job_dsig = nullptr;  // device signal of the last cwt_dev call (not owned)
   double last_ms = 0;
@@ -422,6 +422,7 @@ static int build_job(cwtb_ctx *c, Job &job, long long n0, double dt, const doubl
       lo = -((-lo + K2C - 1) / K2C) * K2C;
       lk = std::max(c->direct_max_log2 + 1, ilog2((unsigned long long)(hi - lo + 1)));
     }
+    if (lk > 20) lk = job.log2N;   // pruned lengths above 2^20 are not built: treat as dense
     if (lk >= job.log2N) {  // dense
       lk = job.log2N;
       d.rsplit = (int)half;
@@ -489,8 +490,8 @@ static int fft_rows_small(cwtb_ctx *c, const RowsArgs<T> &a) {
 template <typename T, int SIGN, int K1, int MODE>
 static int launch_passA(cwtb_ctx *c, const PassAArgs<T> &a, int ny) {
   using B = PassABody<T, K1, MODE, SIGN>;
-  const unsigned M = a.N / ((unsigned)K1 * K2C);
-  return launch<B>(c, M * B::NTILE2, ny, a);
+  const unsigned M = a.N / ((unsigned)K1 * a.K2);
+  return launch<B>(c, M * (a.K2 / B::T2), ny, a);
 }
 
 template <typename T, int SIGN, int MODE>
@@ -508,6 +509,41 @@ static int dispatch_passA(cwtb_ctx *c, int log2K1, const PassAArgs<T> &a, int ny
     case 10: return launch_passA<T, SIGN, 1024, MODE>(c, a, ny);
   }
   return fail(c, CWTB_ERR_UNSUPPORTED, "transform longer than 2^20 per row is not supported yet");
+}
+
+// Rows of length n (1024 < n <= 2^20) through PassA<REAL|CPLX> + PassB, in chunks that fit the
+// Z buffer.  Input row g becomes sub-transform g % ileave of output row out_row0 + g / ileave
+// (ileave = 1: plain rows).  Output rows are renamed through descs[first + outer].row if given.
+template <typename T, int SIGN>
+static int two_kernel_rows(cwtb_ctx *c, const void *in, int real_in, long long in_pitch, long long n_in,
+                           cx<T> *out, long long out_pitch, unsigned n, int nrows, long long nout,
+                           const double *grow, double post, int ileave, const ScaleDesc *descs, int first,
+                           int out_row0, int epi) {
+  const int l2 = ilog2(n);
+  NTab nt;
+  int e = get_ntab(c, n, l2, &nt);
+  if (e) return e;
+  const int chunk = std::max(1, std::min(nrows, (int)std::max<size_t>(1, ((size_t)64 << 20) / ((size_t)n * sizeof(cx<T>)))));
+  if ((e = ensure(c, c->Z, (size_t)chunk * n * sizeof(cx<T>)))) return e;
+  for (int r0 = 0; r0 < nrows; r0 += chunk) {
+    const int nr = std::min(chunk, nrows - r0);
+    PassAArgs<T> a{};
+    a.in = in; a.Z = (cx<T> *)c->Z.p; a.tw = Tw<T>::get(c); a.nt = nt;
+    a.in_pitch = in_pitch; a.n_in = n_in; a.N = n; a.first = 0; a.zmod = 1 << 30; a.K2 = K2C;
+    a.row0 = (ileave > 1 ? 0 : out_row0) + r0;   // interleaved input rows are numbered from 0
+    e = real_in ? dispatch_passA<T, SIGN, MODE_REAL>(c, l2 - 10, a, nr)
+                : dispatch_passA<T, SIGN, MODE_CPLX>(c, l2 - 10, a, nr);
+    if (e) return e;
+    PassBArgs<T> b{};
+    b.Z = (const cx<T> *)c->Z.p; b.out = out; b.tw = Tw<T>::get(c); b.descs = descs;
+    b.pitch = out_pitch; b.nout = nout; b.N = n; b.first = first;
+    b.epi = grow ? EPI_GAUSS : epi; b.grow = grow; b.post = post; b.zmod = 1 << 30;
+    b.pf_dist = 0; b.ny = nr; b.ileave = ileave;
+    if (ileave > 1) { b.row0 = out_row0; b.by0 = r0; } else { b.row0 = out_row0 + r0; b.by0 = 0; }
+    e = launch<PassBBody<T, SIGN>>(c, (n / K2C + Lay<T, K2C>::P - 1) / Lay<T, K2C>::P, nr, b);
+    if (e) return e;
+  }
+  return 0;
 }
 
 template <typename T, int SIGN>
@@ -535,28 +571,30 @@ static int fft_rows(cwtb_ctx *c, const void *in, int real_in, long long in_pitch
     }
     return fail(c, CWTB_ERR_ARG, "fft_rows: bad length");
   }
-  // two kernels through Z, in chunks of rows
+  if (n <= (1u << 20))
+    return two_kernel_rows<T, SIGN>(c, in, real_in, in_pitch, n_in, out, out_pitch, n, nrows, nout, grow, post,
+                                    1, nullptr, 0, 0, EPI_STORE);
+  // ---- Np > 2^20: three levels.  A pre-pass (PassA with K1 = K0 = n / 2^20 and rows of 2^20)
+  // turns each row into K0 twiddled sequences y_c[j]; output bin K0*q + c is bin q of the
+  // 2^20-point transform of y_c, computed by the two-kernel path with interleaved stores.
+  const int l0 = l2 - 20;
+  const unsigned K0 = 1u << l0, Nsub = 1u << 20;
   NTab nt;
   int e = get_ntab(c, n, l2, &nt);
   if (e) return e;
-  const int chunk = std::max(1, std::min(nrows, (int)std::max<size_t>(1, (64u << 20) / ((size_t)n * sizeof(cx<T>)))));
-  e = ensure(c, c->Z, (size_t)chunk * n * sizeof(cx<T>));
-  if (e) return e;
+  const int chunk = std::max(1, std::min(nrows, (int)std::max<size_t>(1, ((size_t)512 << 20) / ((size_t)n * sizeof(cx<T>)))));
+  if ((e = ensure(c, c->Y, (size_t)chunk * n * sizeof(cx<T>)))) return e;
   for (int r0 = 0; r0 < nrows; r0 += chunk) {
     const int nr = std::min(chunk, nrows - r0);
     PassAArgs<T> a{};
-    a.in = in; a.Z = (cx<T> *)c->Z.p; a.tw = Tw<T>::get(c); a.nt = nt;
-    a.in_pitch = in_pitch; a.n_in = n_in; a.N = n; a.first = 0; a.row0 = r0; a.zmod = 1 << 30;
-    e = real_in ? dispatch_passA<T, SIGN, MODE_REAL>(c, l2 - 10, a, nr)
-                : dispatch_passA<T, SIGN, MODE_CPLX>(c, l2 - 10, a, nr);
+    a.in = in; a.Z = (cx<T> *)c->Y.p; a.tw = Tw<T>::get(c); a.nt = nt;
+    a.in_pitch = in_pitch; a.n_in = n_in; a.N = n; a.first = 0; a.row0 = r0; a.zmod = 1 << 30; a.K2 = Nsub;
+    e = real_in ? dispatch_passA<T, SIGN, MODE_REAL>(c, l0, a, nr)
+                : dispatch_passA<T, SIGN, MODE_CPLX>(c, l0, a, nr);
     if (e) return e;
-    PassBArgs<T> b{};
-    b.Z = (const cx<T> *)c->Z.p; b.out = out; b.tw = Tw<T>::get(c); b.descs = nullptr;
-    b.pitch = out_pitch; b.nout = nout; b.N = n; b.first = 0; b.row0 = r0;
-    b.epi = grow ? EPI_GAUSS : EPI_STORE; b.grow = grow; b.post = post; b.zmod = 1 << 30;
-    b.pf_dist = 0; b.ny = nr;
-    e = launch<PassBBody<T, SIGN>>(c, (n / K2C + Lay<T, K2C>::P - 1) / Lay<T, K2C>::P, nr, b);
-    if (e) return e;
+    if ((e = two_kernel_rows<T, SIGN>(c, c->Y.p, 0, Nsub, Nsub, out, out_pitch, Nsub, nr * (int)K0, nout, grow, post,
+                                      (int)K0, nullptr, 0, r0, EPI_STORE)))
+      return e;
   }
   return 0;
 }
@@ -646,7 +684,7 @@ static int launch_fused(cwtb_ctx *c, const PassAArgs<T> &a, const PassBArgs<T> &
   f.ring = c->ring;
   f.a.zmod = f.b.zmod = c->ring;
   const unsigned M = a.N / ((unsigned)K1 * K2C);
-  f.tilesA = M * A::NTILE2;
+  f.tilesA = M * (K2C / A::T2);
   f.tilesB = (a.N / K2C + Lay<T, K2C>::P - 1) / Lay<T, K2C>::P;
   int e = ensure(c, c->ctr, (size_t)(1 + 2 * nscales) * sizeof(unsigned));
   if (e) return e;
@@ -804,6 +842,26 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
     }
     // ---- two kernels through Z ----
     const bool dense = (cl.log2K == job.log2N);
+    if (dense && job.log2N > 20) {
+      // ---- Np > 2^20: pre-pass (K0-point transforms over rows of 2^20, response generated
+      // in-kernel) into Y, then the K0 interleaved 2^20-point transforms of every scale ----
+      const int l0 = job.log2N - 20;
+      const unsigned Nsub = 1u << 20;
+      const int gy = std::max<int>(1, (int)std::min<size_t>((size_t)cl.count, ((size_t)512 << 20) / ((size_t)N * sizeof(V))));
+      if ((e = ensure(c, c->Y, (size_t)gy * N * sizeof(V)))) return e;
+      for (int g0 = 0; g0 < cl.count; g0 += gy) {
+        const int ng = std::min(gy, cl.count - g0);
+        PassAArgs<T> a{};
+        a.descs = ddesc; a.spec = spec; a.Bbuf = Bbuf; a.Z = (V *)c->Y.p; a.tw = Tw<T>::get(c);
+        a.fam = fam; a.nt = nt; a.N = N; a.first = cl.first + g0; a.row0 = 0; a.zmod = 1 << 30;
+        a.pf_dist = 0; a.K2 = Nsub;
+        if ((e = dispatch_passA<T, +1, MODE_DENSE>(c, l0, a, ng))) return e;
+        if ((e = two_kernel_rows<T, +1>(c, c->Y.p, 0, Nsub, Nsub, W, job.n0, Nsub, ng << l0, job.n0, nullptr, 1.0,
+                                         1 << l0, ddesc, cl.first + g0, 0, epi)))
+          return e;
+      }
+      continue;
+    }
     const int chunk = c->fused ? cl.count : G;   // fused: the whole class in one persistent launch
     if ((e = ensure(c, c->Z, (size_t)(c->fused ? c->ring : G) * N * sizeof(V)))) return e;
     for (int g0 = 0; g0 < cl.count; g0 += chunk) {
@@ -811,7 +869,7 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
       PassAArgs<T> a{};
       a.descs = ddesc; a.spec = spec; a.Bbuf = Bbuf; a.Z = (V *)c->Z.p; a.tw = Tw<T>::get(c);
       a.fam = fam; a.nt = nt; a.N = N; a.first = cl.first + g0; a.row0 = 0; a.zmod = 1 << 30;
-      a.pf_dist = c->pf_dist_a;
+      a.pf_dist = c->pf_dist_a; a.K2 = K2C;
       PassBArgs<T> b{};
       b.Z = (const V *)c->Z.p; b.out = W; b.tw = Tw<T>::get(c); b.descs = ddesc;
       b.pitch = job.n0; b.nout = job.n0; b.N = N; b.first = cl.first + g0; b.row0 = 0;
@@ -951,7 +1009,7 @@ void cwtb_destroy(cwtb_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
 #endif
-  for (Buf *b : {&c->ctr, &c->sig, &c->sig2, &c->spec, &c->Z, &c->B, &c->W, &c->W2, &c->descs, &c->table, &c->scratch,
+  for (Buf *b : {&c->ctr, &c->sig, &c->sig2, &c->spec, &c->Z, &c->Y, &c->B, &c->W, &c->W2, &c->descs, &c->table, &c->scratch,
                  &c->C, &c->A12, &c->F, &c->aux, &c->rowd, &c->win, &c->mask, &c->hist, &c->noise})
     if (b->p) rt_free(b->p);
   for (auto &kv : c->ntabs) { rt_free(kv.second.hi); rt_free(kv.second.lo); }
@@ -1145,7 +1203,7 @@ int cwtb_get_signal_fft(cwtb_ctx *c, void *out) {
 int cwtb_fft_c2c(cwtb_ctx *c, const void *in, void *out, int64_t n, int batch, int sign, int precision) {
   if (!c || !in || !out || n < 2 || (n & (n - 1)) || batch < 1 || (sign != 1 && sign != -1))
     return fail(c, CWTB_ERR_ARG, "fft_c2c: bad argument");
-  if (n > (1ll << 20)) return fail(c, CWTB_ERR_UNSUPPORTED, "fft_c2c: n > 2^20");
+  if (n > (1ll << 26)) return fail(c, CWTB_ERR_UNSUPPORTED, "fft_c2c: n > 2^26");
   const size_t cnt = (size_t)n * batch;
   void *din = nullptr, *dout = nullptr;
   const size_t esz = precision == CWTB_F64 ? sizeof(double2) : sizeof(float2);
@@ -1384,7 +1442,7 @@ int cwtb_smooth(cwtb_ctx *c, const void *in, int is_complex, int n_scales, int64
                 const double *scales, int boxcar_len, void *out) {
   if (!c || !in || !out || !scales || n_scales < 1 || n < 1 || !(dt > 0))
     return fail(c, CWTB_ERR_ARG, "smooth: bad argument");
-  if (n > (1ll << 20)) return fail(c, CWTB_ERR_UNSUPPORTED, "smooth: rows longer than 2^20");
+  if (n > (1ll << 26)) return fail(c, CWTB_ERR_UNSUPPORTED, "smooth: rows longer than 2^26");
 #ifndef CWTB_HOST_EMU
   RT(cudaSetDevice(c->device));
 #endif

@@ -105,14 +105,16 @@ template <typename T> struct Epilogue {
 template <typename T> struct OutStorer {
   using V = cx<T>;
   V *row;          // out + row*pitch
-  long long nout;  // keep n < nout
+  long long nout;  // keep final index < nout
   int u0, U;
   Epilogue<T> epi;
+  int ostride = 1, ooff = 0;   // final index = n*ostride + ooff (interleaved sub-transforms, Np > 2^20)
   template <int R> HD void store(int b, int ql, int qs, V (&x)[R]) const {
     const int u = u0 + b;
     if (u >= U) return;
-    const size_t step = (size_t)qs * (size_t)U;
+    size_t step = (size_t)qs * (size_t)U;
     size_t n = (size_t)u + (size_t)ql * (size_t)U;
+    if (ostride != 1) { n = n * (size_t)ostride + (size_t)ooff; step *= (size_t)ostride; }
     if (epi.mode == EPI_STORE && (long long)(n + (R - 1) * step) < nout) {
       // common case: every output of this butterfly is kept -> pointer walk, no per-element test
       V *p = row + n;
@@ -136,6 +138,7 @@ template <typename T, int SIGN> struct ZStorer {
   V *Z;
   NTab nt;
   int p, M, r20, bmax;
+  unsigned K2 = K2C;   // row length of Z
   int cached_b = -1;   // the step factor depends on b only: looked up once per thread
   V cached_st;
   template <int R> HD void store(int b, int ql, int qs, V (&x)[R]) {
@@ -151,10 +154,10 @@ template <typename T, int SIGN> struct ZStorer {
     }
     const V st = cached_st;
     if (SIGN < 0) t.y = -t.y;
-    V *dst = Z + (size_t)u * K2C + r2;
+    V *dst = Z + (size_t)u * K2 + r2;
 #pragma unroll
     for (int c = 0; c < R; ++c) {
-      dst[(size_t)c * du * K2C] = cmul(x[c], t);
+      dst[(size_t)c * du * K2] = cmul(x[c], t);
       t = cmul(t, st);
     }
   }
@@ -346,6 +349,9 @@ template <typename T> struct PassBArgs {
   int zmod;                // Z slot of row `by` is by % zmod
   int pf_dist;             // L2 prefetch distance in tiles (0 = off)
   int ny;                  // gridDim.y of this launch (rows)
+  int by0;                 // global index of this launch's first Z row (interleave bookkeeping)
+  int ileave;              // > 1: Z row `by` is sub-transform by % ileave of output row by / ileave
+                           // (final index n*ileave + by % ileave): three-level path, Np > 2^20
 };
 
 template <typename T, int SIGN> struct PassBBody {
@@ -393,18 +399,22 @@ template <typename T, int SIGN> struct PassBBody {
     } else if constexpr (PH == 2 && NP == 3) {
       tile_second<T, K, SIGN, true>(sm, a.tw, tid);
     } else {
-      const int row = a.descs ? a.descs[a.first + by].row : a.row0 + by;
+      const int il = a.ileave > 1 ? a.ileave : 1;
+      const int outer = (a.by0 + by) / il;
+      const int row = a.descs ? a.descs[a.first + outer].row : a.row0 + outer;
       OutStorer<T> st;
       st.row = a.out + (size_t)row * a.pitch;
       st.nout = a.nout;
       st.u0 = u0;
       st.U = U;
+      st.ostride = il;
+      st.ooff = (a.by0 + by) % il;
       st.epi.mode = a.epi;
       if (a.epi == EPI_GAUSS) {
         st.epi.g = a.grow[row];
-        st.epi.invn = 1.0 / (double)a.N;
+        st.epi.invn = 1.0 / ((double)a.N * il);
         st.epi.post = a.post;
-        st.epi.nfreq = a.N;
+        st.epi.nfreq = (long long)a.N * il;
       }
       pass_last<T, K, SIGN, OutStorer<T>, true>(sm, st, tid);
       if (tid == 0) tb.inval();   // every thread passed wait() two barriers ago
@@ -429,6 +439,8 @@ template <typename T> struct PassAArgs {
   int first, row0;
   int zmod;            // Z slot of row `by` is by % zmod (ring of Z buffers in the fused kernel)
   int pf_dist;         // L2 prefetch distance in tiles for the band-product rows (0 = off)
+  unsigned K2;         // row length of Z: 1024 (second kernel = PassB) or 2^20 (pre-pass of the
+                       // three-level path for Np > 2^20, where the rows are transformed again)
 };
 
 template <typename T, int K1, int MODE, int SIGN> struct PassABody {
@@ -437,8 +449,7 @@ template <typename T, int K1, int MODE, int SIGN> struct PassABody {
   using LY = Lay<T, K1>;
   static constexpr int NP = Plan<K1>::NP;
   static constexpr int P = LY::P;
-  static constexpr int T2 = P < K2C ? P : K2C;  // r2 values per tile
-  static constexpr int NTILE2 = K2C / T2;
+  static constexpr int T2 = P < K2C ? P : K2C;  // r2 values per tile (a.K2 is a multiple of it)
   static constexpr int NPHASE = NP == 1 ? 1 : NP + 1;
   static constexpr size_t SMEM = LY::BYTES;
 
@@ -452,7 +463,7 @@ template <typename T, int K1, int MODE, int SIGN> struct PassABody {
     }
     // element r = pos*K2 + r2 of the K'-point input
     HD V get(int pos, int r2) const {
-      const unsigned r = (unsigned)pos * K2C + (unsigned)r2;
+      const unsigned r = (unsigned)pos * a.K2 + (unsigned)r2;
       if (MODE == MODE_DENSE) {
         const int k = (int)r - (r >= a.N / 2 ? (int)a.N : 0);
         // outside the scale's band the response is below the pruning threshold: same rule as
@@ -464,7 +475,7 @@ template <typename T, int K1, int MODE, int SIGN> struct PassABody {
         if (p == 0 || NP > 1) return v;   // multi-pass plans apply the twist in pass 1
         const int k1 = pos - ((int)r >= d.rsplit ? K1 : 0);
         // e^{2 pi i k1 p / (K1 M)} = e^{2 pi i (k1 p K2) / N}
-        V w = nroot_t<T>(a.nt, (unsigned)k1 * (unsigned)p * (unsigned)K2C);
+        V w = nroot_t<T>(a.nt, (unsigned)k1 * (unsigned)p * a.K2);
         return cmul(v, w);
       } else if (MODE == MODE_REAL) {
         const T *row = (const T *)a.in + (size_t)(a.row0 + by) * a.in_pitch;
@@ -478,9 +489,10 @@ template <typename T, int K1, int MODE, int SIGN> struct PassABody {
 
   template <int PH> HD static void phase(const Args &a, int bx, int by, int tid, void *smraw) {
     V *sm = (V *)smraw;
+    const int NTILE2 = (int)(a.K2 / T2);
     const int p = bx / NTILE2;
     const int r20 = (bx % NTILE2) * T2;
-    const int M = (int)(a.N / ((unsigned)K1 * K2C));
+    const int M = (int)(a.N / ((unsigned)K1 * a.K2));
     ZStorer<T, SIGN> st;
     st.Z = a.Z + (size_t)(by % a.zmod) * a.N;
     st.nt = a.nt;
@@ -488,6 +500,7 @@ template <typename T, int K1, int MODE, int SIGN> struct PassABody {
     st.M = M;
     st.r20 = r20;
     st.bmax = T2;
+    st.K2 = a.K2;
     if constexpr (NP == 1) {
       Src src(a, by, p);
       for (int b = tid; b < T2; b += NT) {
@@ -507,7 +520,7 @@ template <typename T, int K1, int MODE, int SIGN> struct PassABody {
           const int r20n = (t % NTILE2) * T2;
           const V *base = a.Bbuf + src.d.boff + r20n;
           for (int pos = tid; pos < K1; pos += NT)
-            TileBarrier::prefetch_l2(base + (size_t)pos * K2C, (unsigned)(T2 * sizeof(V)));
+            TileBarrier::prefetch_l2(base + (size_t)pos * a.K2, (unsigned)(T2 * sizeof(V)));
         }
       }
       for (int idx = tid; idx < K1 * T2; idx += NT) {
@@ -519,8 +532,8 @@ template <typename T, int K1, int MODE, int SIGN> struct PassABody {
         SmemTwistLoader<T, K1, Plan<K1>::R1> ld;
         ld.sm = sm;
         ld.nt = a.nt;
-        ld.rsplit_row = a.descs[a.first + by].rsplit / K2C;
-        ld.pk2 = (unsigned)p * (unsigned)K2C;
+        ld.rsplit_row = a.descs[a.first + by].rsplit / (int)a.K2;
+        ld.pk2 = (unsigned)p * a.K2;
         tile_first<T, K1, SIGN>(sm, a.tw, ld, tid);
       } else {
         SmemLoader<T, K1> ld;

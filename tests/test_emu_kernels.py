@@ -91,8 +91,6 @@ def test_error_paths_report_status_and_message(emu):
         emu.cwt(x, -1.0, np.array([2.0]), 0, 6.0)
     with pytest.raises(EngineError, match="table"):
         emu.cwt(x, 1.0, np.array([2.0]), 3, 0.0)                # CWTB_TABLE without a table
-    with pytest.raises(EngineError, match="2\\^20"):
-        emu.cwt(np.zeros(2 ** 20 + 1), 1.0, np.array([2.0]), 0, 6.0)   # Np = 2^21: not built yet
     with pytest.raises(EngineError):
         emu.set_band_eps(0.5)
     with pytest.raises(ValueError):
@@ -114,3 +112,19 @@ def test_table_family_matches_analytic(emu):
         Wt = emu.cwt(x, 1.0, sj, 3, 0.0, table=table)
         Wa = emu.cwt(x, 1.0, sj, 0, 6.0)
         assert relerr(Wt, Wa) < 1e-13
+
+
+def test_three_level_path_beyond_2_20(emu):
+    """Np = 2^21: pre-pass + interleaved 2^20-point transforms (forward FFT and dense scales),
+    pruned classes unchanged."""
+    rs = np.random.RandomState(4)
+    y = rs.randn(1, 2 ** 21) + 1j * rs.randn(1, 2 ** 21)
+    assert relerr(emu.fft_c2c(y, -1), np.fft.fft(y, axis=1)) < 1e-13
+    n0 = 2 ** 20 + 777
+    x = rs.randn(n0)
+    sj = np.array([2.0, 7.0, 300.0, 5e4])
+    W = emu.cwt(x, 1.0, sj, 0, 6.0)
+    assert emu.last_plan(4)[0] == 21
+    m = orc.Morlet(6)
+    Wr = orc.cwt(x, 1.0, wavelet=m, freqs=1 / (m.flambda() * sj))[0]
+    assert relerr(W, Wr) < 1e-10

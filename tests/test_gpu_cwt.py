@@ -196,10 +196,26 @@ def test_linearity_and_parseval_full_size(pycwt):
     assert relerr(Wb[rows], Wr) < TOL64
 
 
+def test_signal_longer_than_2_20(pycwt):
+    """n0 > 2^20 (Np = 2^21, 2^22): three-level path for the forward FFT and the dense scales."""
+    rs = np.random.RandomState(8)
+    for n0 in (2 ** 20 + 4321, 2 ** 22):
+        x = chirp(n0) + 0.2 * rs.randn(n0)
+        sj = np.array([2.0, 4.5, 20.0, 900.0, 3e4, 4e5])
+        eng = pycwt.default_engine()
+        W = eng.cwt(x, 1.0, sj, 0, 6.0)
+        m = orc.Morlet(6)
+        Wr = orc.cwt(x, 1.0, wavelet=m, freqs=1 / (m.flambda() * sj))[0]
+        assert relerr(W, Wr) < TOL64
+    W, sj, freqs, coi, fft, fftfreqs = pycwt.cwt(x[:2 ** 20 + 9], 1.0, dj=2.0, wavelet="dog")
+    Wr, sjr, _, _, fftr, _ = orc.cwt(x[:2 ** 20 + 9], 1.0, dj=2.0, wavelet=orc.DOG(2))
+    assert relerr(W, Wr) < TOL64 and relerr(fft, fftr) < 1e-12
+
+
 def test_engine_c2c_hook(pycwt):
     eng = pycwt.default_engine()
     rs = np.random.RandomState(4)
-    for n in (2, 8, 64, 512, 1024, 4096, 2 ** 15, 2 ** 20):
+    for n in (2, 8, 64, 512, 1024, 4096, 2 ** 15, 2 ** 20, 2 ** 22):
         x = rs.randn(2, n) + 1j * rs.randn(2, n)
         assert relerr(eng.fft_c2c(x, -1), np.fft.fft(x, axis=1)) < 1e-13
         assert relerr(eng.fft_c2c(x, +1), np.fft.ifft(x, axis=1) * n) < 1e-13
