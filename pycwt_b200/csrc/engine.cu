@@ -116,6 +116,8 @@ struct NTabDev {
 struct cwtb_ctx {
   int device = 0;
   rt_stream stream{};
+  rt_stream copy_streams[4]{};   // large D2H copies are split over several streams / copy engines
+  int d2h_split = 1;             // CWTB_D2H_SPLIT
   std::string err;
   double band_eps = 1e-20;
   int group = 0;   // rows per two-kernel chunk; 0 = as many as fit in group_bytes of Z (CWTB_GROUP)
@@ -982,6 +984,8 @@ int cwtb_create(int device, cwtb_ctx **out) {
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return CWTB_ERR_CUDA; }
   cudaEventCreate(&c->e0);
   cudaEventCreate(&c->e1);
+  for (auto &st : c->copy_streams) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+  if (const char *g = getenv("CWTB_D2H_SPLIT")) c->d2h_split = std::min(4, std::max(1, atoi(g)));
 #endif
   if (const char *g = getenv("CWTB_GROUP")) c->group = std::max(0, atoi(g));
   if (const char *g = getenv("CWTB_GROUP_MB")) c->group_bytes = (size_t)std::max(1, atoi(g)) << 20;
@@ -1021,6 +1025,7 @@ void cwtb_destroy(cwtb_ctx *c) {
   cudaEventDestroy(c->e0);
   cudaEventDestroy(c->e1);
   cudaStreamDestroy(c->stream);
+  for (auto &st : c->copy_streams) cudaStreamDestroy(st);
 #endif
   delete c;
 }
@@ -1165,7 +1170,23 @@ int cwtb_get_w(cwtb_ctx *c, void *out, int out_f64, int row0, int nrows) {
   if (row0 < 0 || nrows < 0 || row0 + nrows > job.S * job.nbatch) return fail(c, CWTB_ERR_ARG, "row range");
   const size_t cnt = (size_t)nrows * job.n0;
   if (job.precision == CWTB_F64) {
-    RT(rt_d2h(out, (const double2 *)c->W.p + (size_t)row0 * job.n0, cnt * sizeof(double2), c->stream));
+    const char *src = (const char *)((const double2 *)c->W.p + (size_t)row0 * job.n0);
+    const size_t bytes = cnt * sizeof(double2);
+#ifndef CWTB_HOST_EMU
+    if (c->d2h_split > 1 && bytes >= ((size_t)64 << 20)) {
+      RT(rt_sync(c->stream));   // kernels done
+      const int ns = c->d2h_split;
+      const size_t piece = ((bytes / ns) + 255) & ~(size_t)255;
+      for (int i = 0; i < ns; ++i) {
+        const size_t off = (size_t)i * piece;
+        if (off >= bytes) break;
+        RT(rt_d2h((char *)out + off, src + off, std::min(piece, bytes - off), c->copy_streams[i]));
+      }
+      for (int i = 0; i < ns; ++i) RT(rt_sync(c->copy_streams[i]));
+      return 0;
+    }
+#endif
+    RT(rt_d2h(out, src, bytes, c->stream));
     RT(rt_sync(c->stream));
   } else if (!out_f64) {
     RT(rt_d2h(out, (const float2 *)c->W.p + (size_t)row0 * job.n0, cnt * sizeof(float2), c->stream));
