@@ -15,6 +15,7 @@
 #include <map>
 #include <set>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -23,6 +24,12 @@
 #include "kernels.cuh"
 
 using namespace cwtb;
+
+// threads per CTA of a kernel body: Body::NTB if it declares one (tile kernels: per precision),
+// else the global NT
+template <class B, class = void> struct BodyNT { static constexpr int value = NT; };
+template <class B> struct BodyNT<B, std::void_t<decltype(B::NTB)>> { static constexpr int value = B::NTB; };
+
 
 // ======================================================================================
 // runtime abstraction
@@ -71,7 +78,7 @@ __device__ __forceinline__ void run_phases_at(const typename Body::Args &a, int 
   }
 }
 template <class Body>
-__global__ void __launch_bounds__(NT, CWTB_MINB) k_run(const __grid_constant__ typename Body::Args a) {
+__global__ void __launch_bounds__(BodyNT<Body>::value, CWTB_MINB) k_run(const __grid_constant__ typename Body::Args a) {
   extern __shared__ __align__(16) unsigned char smraw[];
   run_phases<Body, 0>(a, smraw);
 }
@@ -206,7 +213,7 @@ static int ensure(cwtb_ctx *c, Buf &b, size_t bytes) {
 #ifdef CWTB_HOST_EMU
 template <class Body, int PH>
 static void emu_phases(const typename Body::Args &a, int bx, int by, void *sm) {
-  for (int tid = 0; tid < NT; ++tid) Body::template phase<PH>(a, bx, by, tid, sm);
+  for (int tid = 0; tid < BodyNT<Body>::value; ++tid) Body::template phase<PH>(a, bx, by, tid, sm);
   if constexpr (PH + 1 < Body::NPHASE) emu_phases<Body, PH + 1>(a, bx, by, sm);
 }
 #endif
@@ -251,7 +258,7 @@ static int launch(cwtb_ctx *c, unsigned gx, unsigned gy, const typename Body::Ar
     c->prof.push_back({body_name(__PRETTY_FUNCTION__), gx, gy, ev});
     RT(cudaEventRecord(c->prof_events[ev], c->stream));
   }
-  k_run<Body><<<dim3(gx, gy), NT, Body::SMEM, c->stream>>>(a);
+  k_run<Body><<<dim3(gx, gy), BodyNT<Body>::value, Body::SMEM, c->stream>>>(a);
   RT(cudaGetLastError());
   if (ev >= 0) RT(cudaEventRecord(c->prof_events[ev + 1], c->stream));
   c->launches++;
@@ -639,7 +646,7 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
   return v;
 }
 template <typename T, int K1, int MODE>
-__global__ void __launch_bounds__(NT, 3) k_fused(const __grid_constant__ FusedArgs<T> f) {
+__global__ void __launch_bounds__(TileCfg<T>::NT, 3) k_fused(const __grid_constant__ FusedArgs<T> f) {
   extern __shared__ __align__(16) unsigned char smraw[];
   __shared__ unsigned s_t;
   using A = PassABody<T, K1, MODE, +1>;
@@ -713,7 +720,7 @@ static int launch_fused(cwtb_ctx *c, const PassAArgs<T> &a, const PassBArgs<T> &
     c->configured.insert(fn);
   }
   int occ = 0;
-  RT(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
+  RT(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TileCfg<T>::NT, smem));
   if (occ < 1) return fail(c, CWTB_ERR_CUDA, "fused kernel does not fit on an SM");
   const unsigned total = (unsigned)nscales * (f.tilesA + f.tilesB);
   const unsigned grid = std::min<unsigned>(total, (unsigned)(occ * c->num_sms));
@@ -728,7 +735,7 @@ static int launch_fused(cwtb_ctx *c, const PassAArgs<T> &a, const PassBArgs<T> &
     c->prof.push_back({body_name(__PRETTY_FUNCTION__), grid, (unsigned)nscales, ev});
     RT(cudaEventRecord(c->prof_events[ev], c->stream));
   }
-  kern<<<grid, NT, smem, c->stream>>>(f);
+  kern<<<grid, TileCfg<T>::NT, smem, c->stream>>>(f);
   RT(cudaGetLastError());
   if (ev >= 0) RT(cudaEventRecord(c->prof_events[ev + 1], c->stream));
   c->launches++;

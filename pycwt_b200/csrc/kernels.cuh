@@ -177,6 +177,8 @@ template <typename T> struct SingleArgs {
 };
 
 template <typename T, int K> struct SingleBody {
+  static constexpr int NTB = TileCfg<T>::NT;   // threads per CTA of this kernel
+  static constexpr int NT = NTB;
   using V = cx<T>;
   using Args = SingleArgs<T>;
   using LY = Lay<T, K>;
@@ -218,6 +220,8 @@ template <typename T, int K> struct SingleBody {
 //   W[u + q2*U] = sum_{r2} in[u][r2] e^{2 pi i r2 q2 / 1024}
 // (k1 = r1 - K1 [r >= rsplit] is the signed row of residue r; no alignment of the window needed).
 template <typename T, int K1> struct DirectBody {
+  static constexpr int NTB = TileCfg<T>::NT;   // threads per CTA of this kernel
+  static constexpr int NT = NTB;
   using V = cx<T>;
   using Args = SingleArgs<T>;
   static constexpr int K = K2C;
@@ -355,6 +359,8 @@ template <typename T> struct PassBArgs {
 };
 
 template <typename T, int SIGN> struct PassBBody {
+  static constexpr int NTB = TileCfg<T>::NT;   // threads per CTA of this kernel
+  static constexpr int NT = NTB;
   using V = cx<T>;
   using Args = PassBArgs<T>;
   static constexpr int K = K2C;
@@ -444,6 +450,8 @@ template <typename T> struct PassAArgs {
 };
 
 template <typename T, int K1, int MODE, int SIGN> struct PassABody {
+  static constexpr int NTB = TileCfg<T>::NT;   // threads per CTA of this kernel
+  static constexpr int NT = NTB;
   using V = cx<T>;
   using Args = PassAArgs<T>;
   using LY = Lay<T, K1>;
@@ -629,6 +637,8 @@ template <typename T> struct RowsStorer {
   }
 };
 template <typename T, int K, int SIGN> struct RowsBody {
+  static constexpr int NTB = TileCfg<T>::NT;   // threads per CTA of this kernel
+  static constexpr int NT = NTB;
   using V = cx<T>;
   using Args = RowsArgs<T>;
   using LY = Lay<T, K>;
