@@ -1231,38 +1231,45 @@ int cwtb_get_signal_fft(cwtb_ctx *c, void *out) {
 int cwtb_fft_c2c(cwtb_ctx *c, const void *in, void *out, int64_t n, int batch, int sign, int precision) {
   if (!c || !in || !out || n < 2 || (n & (n - 1)) || batch < 1 || (sign != 1 && sign != -1))
     return fail(c, CWTB_ERR_ARG, "fft_c2c: bad argument");
+  if (precision != CWTB_F64 && precision != CWTB_F32) return fail(c, CWTB_ERR_ARG, "bad precision");
   if (n > (1ll << 26)) return fail(c, CWTB_ERR_UNSUPPORTED, "fft_c2c: n > 2^26");
+#ifndef CWTB_HOST_EMU
+  RT(cudaSetDevice(c->device));
+#endif
   const size_t cnt = (size_t)n * batch;
-  void *din = nullptr, *dout = nullptr;
   const size_t esz = precision == CWTB_F64 ? sizeof(double2) : sizeof(float2);
-  RT(rt_malloc(&din, cnt * esz));
-  RT(rt_malloc(&dout, cnt * esz));
-  int e = 0;
+  int e;
+  // context-owned staging buffers (released with the context, also on error paths)
+  if ((e = ensure(c, c->C, cnt * esz))) return e;
+  if ((e = ensure(c, c->A12, cnt * esz))) return e;
+  void *din = c->C.p, *dout = c->A12.p;
   if (precision == CWTB_F64) {
-    rt_h2d(din, in, cnt * esz, c->stream);
+    RT(rt_h2d(din, in, cnt * esz, c->stream));
     e = sign < 0 ? fft_rows<double, -1>(c, din, 0, n, n, (double2 *)dout, n, (unsigned)n, batch)
                  : fft_rows<double, +1>(c, din, 0, n, n, (double2 *)dout, n, (unsigned)n, batch);
-    if (!e) { rt_d2h(out, dout, cnt * esz, c->stream); e = rt_sync(c->stream) ? CWTB_ERR_CUDA : 0; }
-  } else {
-    std::vector<float> tmp(cnt * 2);
-    const double *src = (const double *)in;
-    for (size_t i = 0; i < cnt * 2; ++i) tmp[i] = (float)src[i];
-    rt_h2d(din, tmp.data(), cnt * esz, c->stream);
-    rt_sync(c->stream);
-    e = sign < 0 ? fft_rows<float, -1>(c, din, 0, n, n, (float2 *)dout, n, (unsigned)n, batch)
-                 : fft_rows<float, +1>(c, din, 0, n, n, (float2 *)dout, n, (unsigned)n, batch);
-    if (!e) {
-      rt_d2h(tmp.data(), dout, cnt * esz, c->stream);
-      e = rt_sync(c->stream) ? CWTB_ERR_CUDA : 0;
-      double *o = (double *)out;
-      for (size_t i = 0; i < cnt * 2; ++i) o[i] = (double)tmp[i];
-    }
+    if (e) return e;
+    RT(rt_d2h(out, dout, cnt * esz, c->stream));
+    RT(rt_sync(c->stream));
+    return 0;
   }
-  rt_sync(c->stream);
-  rt_free(din);
-  rt_free(dout);
-  return e;
+  std::vector<float> tmp(cnt * 2);
+  const double *src = (const double *)in;
+  for (size_t i = 0; i < cnt * 2; ++i) tmp[i] = (float)src[i];
+  RT(rt_h2d(din, tmp.data(), cnt * esz, c->stream));
+  RT(rt_sync(c->stream));
+  e = sign < 0 ? fft_rows<float, -1>(c, din, 0, n, n, (float2 *)dout, n, (unsigned)n, batch)
+               : fft_rows<float, +1>(c, din, 0, n, n, (float2 *)dout, n, (unsigned)n, batch);
+  if (e) return e;
+  RT(rt_d2h(tmp.data(), dout, cnt * esz, c->stream));
+  RT(rt_sync(c->stream));
+  double *o = (double *)out;
+  for (size_t i = 0; i < cnt * 2; ++i) o[i] = (double)tmp[i];
+  return 0;
 }
+
+}  // extern "C"
+
+extern "C" {
 
 // ---- helpers for the post-processing entry points ---------------------------------------
 static int upload_doubles(cwtb_ctx *c, Buf &b, const std::vector<double> &v) {
