@@ -123,6 +123,9 @@ struct NTabDev {
 struct cwtb_ctx {
   int device = 0;
   rt_stream stream{};
+  rt_stream aux_stream{};        // single-kernel classes run here, concurrently with the two-kernel chains
+  rt_stream cur{};               // stream the launcher uses right now
+  int two_streams = 1;           // CWTB_STREAMS=1 disables the overlap
   rt_stream copy_streams[4]{};   // large D2H copies are split over several streams / copy engines
   int d2h_split = 1;             // CWTB_D2H_SPLIT
   std::string err;
@@ -135,6 +138,7 @@ struct cwtb_ctx {
   int ring = 3;      // Z ring slots of the fused kernel
   int num_sms = 148;
   int pf_dist = 148;   // PassB: L2 prefetch distance in tiles (CWTB_PF_DIST)
+  int gauss_rec = 1;   // dense Morlet scales: Gaussian by recurrence (CWTB_GAUSS_REC=0: exp per bin)
   int pf_dist_a = 148;  // PassA (band): L2 prefetch distance in tiles (CWTB_PF_DIST_A)
   size_t batch_bytes = (size_t)4 << 30;   // coefficients per chunk of cwtb_cwt_batch  // K' <= 2^13 handled by one kernel (K' > 1024: DirectBody)
   double2 *tw64 = nullptr;
@@ -156,6 +160,7 @@ struct cwtb_ctx {
   std::set<void *> pinned, devallocs;
 #ifndef CWTB_HOST_EMU
   cudaEvent_t e0{}, e1{};
+  cudaEvent_t ev_fork{}, ev_join{};
 #endif
 };
 
@@ -256,11 +261,11 @@ static int launch(cwtb_ctx *c, unsigned gx, unsigned gy, const typename Body::Ar
       c->prof_events.push_back(e);
     }
     c->prof.push_back({body_name(__PRETTY_FUNCTION__), gx, gy, ev});
-    RT(cudaEventRecord(c->prof_events[ev], c->stream));
+    RT(cudaEventRecord(c->prof_events[ev], c->cur));
   }
-  k_run<Body><<<dim3(gx, gy), BodyNT<Body>::value, Body::SMEM, c->stream>>>(a);
+  k_run<Body><<<dim3(gx, gy), BodyNT<Body>::value, Body::SMEM, c->cur>>>(a);
   RT(cudaGetLastError());
-  if (ev >= 0) RT(cudaEventRecord(c->prof_events[ev + 1], c->stream));
+  if (ev >= 0) RT(cudaEventRecord(c->prof_events[ev + 1], c->cur));
   c->launches++;
   return 0;
 #endif
@@ -829,9 +834,24 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
         return e;
     }
   }
+  // The single-kernel classes (independent of the two-kernel chains: different W rows, read-only
+  // band products) run on a second stream so that their CTAs fill the tails of the chains.
+  const bool split = c->two_streams != 0;
+#ifndef CWTB_HOST_EMU
+  if (split) {
+    RT(cudaEventRecord(c->ev_fork, c->stream));
+    RT(cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
+  }
+#endif
+  for (int pass = 0; pass < 2; ++pass)
   for (const ClassRun &cl : job.classes) {
     const unsigned K = 1u << cl.log2K;
-    if (cl.log2K <= 10 || (cl.log2K <= c->direct_max_log2 && cl.log2K < job.log2N)) {
+    const bool single = cl.log2K <= 10 || (cl.log2K <= c->direct_max_log2 && cl.log2K < job.log2N);
+    if (single != (pass == 0)) continue;   // pass 0: single-kernel classes, pass 1: two-kernel chains
+    if (single) {
+#ifndef CWTB_HOST_EMU
+      if (split) c->cur = c->aux_stream;
+#endif
       // ---- single kernel: pruned K'-point transforms from the band products ----
       SingleArgs<T> sa{ddesc, Bbuf, W, Tw<T>::get(c), nt, job.n0, N, cl.first, epi};
       switch (cl.log2K) {
@@ -846,6 +866,7 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
         case 13: e = launch<DirectBody<T, 8>>(c, (N / K2C + Lay<T, K2C>::P - 1) / Lay<T, K2C>::P, cl.count, sa); break;
         default: e = fail(c, CWTB_ERR_STATE, "bad single-kernel class");
       }
+      c->cur = c->stream;
       if (e) return e;
       continue;
     }
@@ -863,7 +884,7 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
         PassAArgs<T> a{};
         a.descs = ddesc; a.spec = spec; a.Bbuf = Bbuf; a.Z = (V *)c->Y.p; a.tw = Tw<T>::get(c);
         a.fam = fam; a.nt = nt; a.N = N; a.first = cl.first + g0; a.row0 = 0; a.zmod = 1 << 30;
-        a.pf_dist = 0; a.K2 = Nsub;
+        a.pf_dist = 0; a.K2 = Nsub; a.gauss_rec = c->gauss_rec;
         if ((e = dispatch_passA<T, +1, MODE_DENSE>(c, l0, a, ng))) return e;
         if ((e = two_kernel_rows<T, +1>(c, c->Y.p, 0, Nsub, Nsub, W, job.n0, Nsub, ng << l0, job.n0, nullptr, 1.0,
                                          1 << l0, ddesc, cl.first + g0, 0, epi)))
@@ -878,7 +899,7 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
       PassAArgs<T> a{};
       a.descs = ddesc; a.spec = spec; a.Bbuf = Bbuf; a.Z = (V *)c->Z.p; a.tw = Tw<T>::get(c);
       a.fam = fam; a.nt = nt; a.N = N; a.first = cl.first + g0; a.row0 = 0; a.zmod = 1 << 30;
-      a.pf_dist = c->pf_dist_a; a.K2 = K2C;
+      a.pf_dist = c->pf_dist_a; a.K2 = K2C; a.gauss_rec = c->gauss_rec;
       PassBArgs<T> b{};
       b.Z = (const V *)c->Z.p; b.out = W; b.tw = Tw<T>::get(c); b.descs = ddesc;
       b.pitch = job.n0; b.nout = job.n0; b.N = N; b.first = cl.first + g0; b.row0 = 0;
@@ -901,6 +922,12 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
       if ((e = launch<PassBBody<T, +1>>(c, (N / K2C + Lay<T, K2C>::P - 1) / Lay<T, K2C>::P, ng, b))) return e;
     }
   }
+#ifndef CWTB_HOST_EMU
+  if (split) {   // join: later work on the main stream sees every row of W
+    RT(cudaEventRecord(c->ev_join, c->aux_stream));
+    RT(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+  }
+#endif
   return 0;
 }
 
@@ -992,8 +1019,13 @@ int cwtb_create(int device, cwtb_ctx **out) {
   cudaEventCreate(&c->e0);
   cudaEventCreate(&c->e1);
   for (auto &st : c->copy_streams) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
+  if (const char *g = getenv("CWTB_STREAMS")) c->two_streams = atoi(g) >= 2;
   if (const char *g = getenv("CWTB_D2H_SPLIT")) c->d2h_split = std::min(4, std::max(1, atoi(g)));
 #endif
+  c->cur = c->stream;
   if (const char *g = getenv("CWTB_GROUP")) c->group = std::max(0, atoi(g));
   if (const char *g = getenv("CWTB_GROUP_MB")) c->group_bytes = (size_t)std::max(1, atoi(g)) << 20;
   if (const char *g = getenv("CWTB_BAND_EPS")) c->band_eps = atof(g);
@@ -1001,6 +1033,7 @@ int cwtb_create(int device, cwtb_ctx **out) {
   if (const char *g = getenv("CWTB_FUSED")) c->fused = atoi(g);
   if (const char *g = getenv("CWTB_PF_DIST")) c->pf_dist = std::max(0, atoi(g));
   if (const char *g = getenv("CWTB_PF_DIST_A")) c->pf_dist_a = std::max(0, atoi(g));
+  if (const char *g = getenv("CWTB_GAUSS_REC")) c->gauss_rec = atoi(g);
   if (const char *g = getenv("CWTB_BATCH_MB")) c->batch_bytes = (size_t)std::max(1, atoi(g)) << 20;
   if (const char *g = getenv("CWTB_RING")) c->ring = std::max(1, atoi(g));
 #ifndef CWTB_HOST_EMU
@@ -1033,6 +1066,9 @@ void cwtb_destroy(cwtb_ctx *c) {
   cudaEventDestroy(c->e1);
   cudaStreamDestroy(c->stream);
   for (auto &st : c->copy_streams) cudaStreamDestroy(st);
+  cudaStreamDestroy(c->aux_stream);
+  cudaEventDestroy(c->ev_fork);
+  cudaEventDestroy(c->ev_join);
 #endif
   delete c;
 }

@@ -445,6 +445,7 @@ template <typename T> struct PassAArgs {
   int first, row0;
   int zmod;            // Z slot of row `by` is by % zmod (ring of Z buffers in the fused kernel)
   int pf_dist;         // L2 prefetch distance in tiles for the band-product rows (0 = off)
+  int gauss_rec;       // dense Morlet: evaluate the Gaussian by recurrence along each thread's bins
   unsigned K2;         // row length of Z: 1024 (second kernel = PassB) or 2^20 (pre-pass of the
                        // three-level path for Np > 2^20, where the rows are transformed again)
 };
@@ -531,6 +532,45 @@ template <typename T, int K1, int MODE, int SIGN> struct PassABody {
             TileBarrier::prefetch_l2(base + (size_t)pos * a.K2, (unsigned)(T2 * sizeof(V)));
         }
       }
+      if (MODE == MODE_DENSE && a.fam.family == 0 && a.gauss_rec && T2 <= NT) {
+        // Morlet, dense scale: a thread's bins are k0, k0 + D, k0 + 2D, ... (D = (NT/T2)*K2), so
+        //   g(k + D) = g(k) * rho(k),  rho(k + D) = rho(k) * exp(-a^2),  a = s * w_D,
+        // replaces the exp per bin by two multiplies.  Re-seeded with exact exp() when the
+        // band is entered, at the signed-bin wrap and every 16 steps (error <= ~1e-14 relative).
+        constexpr int DPOS = NT / T2;
+        const ScaleDesc &d = src.d;
+        const int b = tid % T2;
+        const long long D = (long long)DPOS * a.K2;
+        const double wd = 6.283185307179586 * ((double)D * a.fam.dw);
+        const double aa = d.s * wd;
+        const double q = exp(-aa * aa);
+        double g = 0, rho = 0;
+        long long kprev = 0;
+        int since = 1 << 30;
+        for (int pos = tid / T2; pos < K1; pos += DPOS) {
+          const unsigned r = (unsigned)pos * a.K2 + (unsigned)(r20 + b);
+          const int k = (int)r - (r >= a.N / 2 ? (int)a.N : 0);
+          V v = mk<T>(0, 0);
+          if (k >= d.k_lo && k <= d.k_hi) {
+            if (since >= 16 || (long long)k != kprev + D) {
+              const double f = d.s * (6.283185307179586 * ((double)k * a.fam.dw));
+              const double dd = f - a.fam.f0;
+              g = exp(-0.5 * dd * dd);
+              rho = exp(-aa * dd - 0.5 * aa * aa);
+              since = 0;
+            } else {
+              g *= rho;
+              rho *= q;
+              ++since;
+            }
+            kprev = k;
+            v = cscale(ldg(&a.spec[(size_t)d.chan * a.N + r]), (T)(g * d.amp));
+          } else {
+            since = 1 << 30;
+          }
+          sm[LY::phys(b, pos)] = v;
+        }
+      } else
       for (int idx = tid; idx < K1 * T2; idx += NT) {
         const int b = idx % T2, pos = idx / T2;
         sm[LY::phys(b, pos)] = src.get(pos, r20 + b);
