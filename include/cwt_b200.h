@@ -190,7 +190,8 @@ int cwtb_last_plan(cwtb_ctx *ctx, int *out, int n);
  * mean device time per iteration in ms (events on the launching stream). */
 int cwtb_bench_last(cwtb_ctx *ctx, int iters, double *ms_out);
 /* One pass of the last cwtb_cwt_dev transform with a CUDA event pair around every kernel
- * launch; writes "name|launches|total_ms|rows" lines (rows = scale rows processed) to out. */
+ * launch, on a single stream (the normal run overlaps independent kernel chains on three
+ * streams); writes "name|launches|total_ms|rows" lines (rows = scale rows processed) to out. */
 int cwtb_profile_last(cwtb_ctx *ctx, char *out, size_t cap);
 /* Device memory helpers for benchmarks (inputs resident in HBM). */
 int cwtb_dev_alloc(cwtb_ctx *ctx, size_t bytes, void **out);

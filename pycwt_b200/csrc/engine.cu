@@ -124,8 +124,10 @@ struct cwtb_ctx {
   int device = 0;
   rt_stream stream{};
   rt_stream aux_stream{};        // single-kernel classes run here, concurrently with the two-kernel chains
+  rt_stream chain2_stream{};     // every second two-kernel class runs here (own Z and band chunk)
   rt_stream cur{};               // stream the launcher uses right now
   int two_streams = 1;           // CWTB_STREAMS=1 disables the overlap
+  int three_streams = 1;         // CWTB_STREAMS=2: single-kernel classes only
   rt_stream copy_streams[4]{};   // large D2H copies are split over several streams / copy engines
   int d2h_split = 1;             // CWTB_D2H_SPLIT
   std::string err;
@@ -144,7 +146,7 @@ struct cwtb_ctx {
   double2 *tw64 = nullptr;
   float2 *tw32 = nullptr;
   std::map<unsigned, NTabDev> ntabs;
-  Buf ctr, sig, sig2, spec, Z, Y, B, W, W2, descs, table, scratch, C, A12, F, aux, rowd, win, mask, hist, noise;
+  Buf ctr, sig, sig2, spec, Z, Z2, Y, B, W, W2, descs, table, scratch, C, A12, F, aux, rowd, win, mask, hist, noise;
   Job job;
   const void *job_dsig = nullptr;  // device signal of the last cwt_dev call (not owned)
   double last_ms = 0;
@@ -160,7 +162,7 @@ struct cwtb_ctx {
   std::set<void *> pinned, devallocs;
 #ifndef CWTB_HOST_EMU
   cudaEvent_t e0{}, e1{};
-  cudaEvent_t ev_fork{}, ev_join{};
+  cudaEvent_t ev_fork{}, ev_join{}, ev_join2{};
 #endif
 };
 
@@ -780,6 +782,27 @@ static int chunk_rows(const cwtb_ctx *c, unsigned N, size_t elem_bytes) {
   return (int)std::max<size_t>(1, std::min<size_t>(g, 32768));
 }
 
+// Which of the two band-chunk regions / Z buffers a two-kernel class uses: the parity of its
+// position among the two-kernel classes (dense classes included, they only use Z).
+static int job_chain_region(const cwtb_ctx *c, const Job &job, const ClassRun &cl) {
+  int idx = 0;
+  for (const ClassRun &o : job.classes) {
+    if (&o == &cl) break;
+    const bool single = o.log2K <= 10 || (o.log2K <= c->direct_max_log2 && o.log2K < job.log2N);
+    if (!single) ++idx;
+  }
+  return idx & 1;
+}
+
+// elements of one band-chunk region: the largest chunk of band products of any two-kernel class
+static size_t band_chunk_elems(const cwtb_ctx *c, const Job &job, int G) {
+  size_t bchunk = 0;
+  for (const ClassRun &cl : job.classes)
+    if (cl.log2K > c->direct_max_log2 && cl.log2K < job.log2N)
+      bchunk = std::max(bchunk, (size_t)(c->fused ? cl.count : std::min(G, cl.count)) << cl.log2K);
+  return bchunk;
+}
+
 // all kernels of one transform: forward FFT of the (device, type T) signal, then every scale
 template <typename T>
 static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nullptr, int epi = EPI_STORE) {
@@ -811,11 +834,8 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
   NTab nt;
   if ((e = get_ntab(c, N, job.log2N, &nt))) return e;
   const int G = chunk_rows(c, N, sizeof(V));
-  size_t bchunk = 0;   // band products of one chunk of two-kernel scales
-  for (const ClassRun &cl : job.classes)
-    if (cl.log2K > c->direct_max_log2 && cl.log2K < job.log2N)
-      bchunk = std::max(bchunk, (size_t)(c->fused ? cl.count : std::min(G, cl.count)) << cl.log2K);
-  if ((e = ensure(c, c->B, (job.b_single + bchunk) * sizeof(V)))) return e;
+  const size_t bchunk = band_chunk_elems(c, job, G);   // two regions: one per chain stream
+  if ((e = ensure(c, c->B, (job.b_single + 2 * bchunk) * sizeof(V)))) return e;
   V *Bbuf = (V *)c->B.p;
 
   // band products of every single-kernel scale in one launch (their descriptors are the tail
@@ -838,11 +858,16 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
   // band products) run on a second stream so that their CTAs fill the tails of the chains.
   const bool split = c->two_streams != 0;
 #ifndef CWTB_HOST_EMU
+  const bool split2 = split && c->three_streams && !c->fused;
   if (split) {
     RT(cudaEventRecord(c->ev_fork, c->stream));
     RT(cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
+    if (split2) RT(cudaStreamWaitEvent(c->chain2_stream, c->ev_fork, 0));
   }
+#else
+  const bool split2 = false;
 #endif
+  int chain_no = 0;
   for (int pass = 0; pass < 2; ++pass)
   for (const ClassRun &cl : job.classes) {
     const unsigned K = 1u << cl.log2K;
@@ -893,15 +918,23 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
       continue;
     }
     const int chunk = c->fused ? cl.count : G;   // fused: the whole class in one persistent launch
-    if ((e = ensure(c, c->Z, (size_t)(c->fused ? c->ring : G) * N * sizeof(V)))) return e;
+    // successive two-kernel classes alternate between two streams, each with its own Z buffer
+    // and band-chunk region (descriptor offsets already point into the right region)
+    const bool on2 = split2 && (job_chain_region(c, job, cl) == 1);
+    Buf &Zb = on2 ? c->Z2 : c->Z;
+    if ((e = ensure(c, Zb, (size_t)(c->fused ? c->ring : G) * N * sizeof(V)))) return e;
+#ifndef CWTB_HOST_EMU
+    c->cur = on2 ? c->chain2_stream : c->stream;
+#endif
+    ++chain_no;
     for (int g0 = 0; g0 < cl.count; g0 += chunk) {
       const int ng = std::min(chunk, cl.count - g0);
       PassAArgs<T> a{};
-      a.descs = ddesc; a.spec = spec; a.Bbuf = Bbuf; a.Z = (V *)c->Z.p; a.tw = Tw<T>::get(c);
+      a.descs = ddesc; a.spec = spec; a.Bbuf = Bbuf; a.Z = (V *)Zb.p; a.tw = Tw<T>::get(c);
       a.fam = fam; a.nt = nt; a.N = N; a.first = cl.first + g0; a.row0 = 0; a.zmod = 1 << 30;
       a.pf_dist = c->pf_dist_a; a.K2 = K2C; a.gauss_rec = c->gauss_rec;
       PassBArgs<T> b{};
-      b.Z = (const V *)c->Z.p; b.out = W; b.tw = Tw<T>::get(c); b.descs = ddesc;
+      b.Z = (const V *)Zb.p; b.out = W; b.tw = Tw<T>::get(c); b.descs = ddesc;
       b.pitch = job.n0; b.nout = job.n0; b.N = N; b.first = cl.first + g0; b.row0 = 0;
       b.epi = epi; b.grow = nullptr; b.post = 1.0; b.zmod = 1 << 30;
       b.pf_dist = c->pf_dist; b.ny = ng;
@@ -921,11 +954,17 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
       if (e) return e;
       if ((e = launch<PassBBody<T, +1>>(c, (N / K2C + Lay<T, K2C>::P - 1) / Lay<T, K2C>::P, ng, b))) return e;
     }
+    c->cur = c->stream;
   }
+  (void)chain_no;
 #ifndef CWTB_HOST_EMU
   if (split) {   // join: later work on the main stream sees every row of W
     RT(cudaEventRecord(c->ev_join, c->aux_stream));
     RT(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    if (split2) {
+      RT(cudaEventRecord(c->ev_join2, c->chain2_stream));
+      RT(cudaStreamWaitEvent(c->stream, c->ev_join2, 0));
+    }
   }
 #endif
   return 0;
@@ -934,11 +973,13 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
 // band-buffer offsets of the two-kernel scales depend on the chunk position; set them here
 static void assign_chunk_offsets(cwtb_ctx *c, Job &job) {
   const int G = chunk_rows(c, job.N, job.precision == CWTB_F64 ? sizeof(double2) : sizeof(float2));
+  const size_t bchunk = band_chunk_elems(c, job, G);
   for (const ClassRun &cl : job.classes) {
     if (cl.log2K <= c->direct_max_log2 || cl.log2K == job.log2N) continue;
+    const size_t region = (size_t)job_chain_region(c, job, cl) * bchunk;
     for (int i = 0; i < cl.count; ++i)
       job.descs[cl.first + i].boff =
-          (long long)(job.b_single + (size_t)(c->fused ? i : i % G) * ((size_t)1 << cl.log2K));
+          (long long)(job.b_single + region + (size_t)(c->fused ? i : i % G) * ((size_t)1 << cl.log2K));
   }
 }
 
@@ -1020,9 +1061,11 @@ int cwtb_create(int device, cwtb_ctx **out) {
   cudaEventCreate(&c->e1);
   for (auto &st : c->copy_streams) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&c->chain2_stream, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&c->ev_join2, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
-  if (const char *g = getenv("CWTB_STREAMS")) c->two_streams = atoi(g) >= 2;
+  if (const char *g = getenv("CWTB_STREAMS")) { c->two_streams = atoi(g) >= 2; c->three_streams = atoi(g) >= 3; }
   if (const char *g = getenv("CWTB_D2H_SPLIT")) c->d2h_split = std::min(4, std::max(1, atoi(g)));
 #endif
   c->cur = c->stream;
@@ -1053,7 +1096,7 @@ void cwtb_destroy(cwtb_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
 #endif
-  for (Buf *b : {&c->ctr, &c->sig, &c->sig2, &c->spec, &c->Z, &c->Y, &c->B, &c->W, &c->W2, &c->descs, &c->table, &c->scratch,
+  for (Buf *b : {&c->ctr, &c->sig, &c->sig2, &c->spec, &c->Z, &c->Z2, &c->Y, &c->B, &c->W, &c->W2, &c->descs, &c->table, &c->scratch,
                  &c->C, &c->A12, &c->F, &c->aux, &c->rowd, &c->win, &c->mask, &c->hist, &c->noise})
     if (b->p) rt_free(b->p);
   for (auto &kv : c->ntabs) { rt_free(kv.second.hi); rt_free(kv.second.lo); }
@@ -1067,6 +1110,8 @@ void cwtb_destroy(cwtb_ctx *c) {
   cudaStreamDestroy(c->stream);
   for (auto &st : c->copy_streams) cudaStreamDestroy(st);
   cudaStreamDestroy(c->aux_stream);
+  cudaStreamDestroy(c->chain2_stream);
+  cudaEventDestroy(c->ev_join2);
   cudaEventDestroy(c->ev_fork);
   cudaEventDestroy(c->ev_join);
 #endif
@@ -1597,7 +1642,10 @@ int cwtb_profile_last(cwtb_ctx *c, char *out, size_t cap) {
 #else
   c->prof.clear();
   c->profiling = true;
+  const int ts = c->two_streams;
+  c->two_streams = 0;   // kernels one after the other: per-kernel times are not blurred by overlap
   int e = timed_run(c, c->job_dsig, 1, nullptr);
+  c->two_streams = ts;
   c->profiling = false;
   if (e) return e;
   RT(rt_sync(c->stream));
