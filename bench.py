@@ -33,7 +33,10 @@ F0 = 6.0
 # r1: PassBBody<double,1>, 16-row launch: 268.5 MB read + 215.5 MB written = 30.25 MB per row
 # (algorithmic 16.78 MB per row: the Z intermediate of the two-kernel scales is read back from
 # DRAM); scaled to the 32-row launches of the bench step.
-TRAFFIC = {"PassBBody": 32 * 30.21e6, "SingleBody": 16 * 13.44e6, "DirectBody": 16 * 13.68e6}
+# DRAM bytes (read + write) per scale ROW of the W-writing kernels, from the `ncu --set full`
+# captures summarised in profiles/r1/ncu_r1_*.txt (16-row launches): PassB 483.55 MB,
+# Single<1024> 216.15 MB, Direct<8> 216.66 MB per launch.
+TRAFFIC_PER_ROW = {"PassBBody": 483.55e6 / 16, "SingleBody": 216.15e6 / 16, "DirectBody": 216.66e6 / 16}
 METRIC = "cwt_scale_points_per_sec"
 UNIT = "scale-points/s"
 
@@ -266,6 +269,9 @@ def run_ours(args):
                   "ms_per_step": domw["ms"], "share_of_step": domw["ms"] / kern_ms,
                   "rows": domw["rows"], "algorithmic_bytes": dom_bytes,
                   "achieved": dom_bytes / (domw["ms"] * 1e-3) / 1e9}
+        # traffic and algorithmic bytes are both per (average) launch of the dominant kernel
+        tpr = TRAFFIC_PER_ROW.get(domw["name"].split("<")[0])
+        dom_traffic = None if tpr is None else tpr * domw["rows"] / domw["launches"]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max,
@@ -276,11 +282,12 @@ def run_ours(args):
                     "steps": e2e_steps},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "achieved": dom_rf["achieved"], "peak": peak, "unit": "GB/s",
-                         "frac": dom_rf["achieved"] / peak, "traffic": TRAFFIC.get(domw["name"].split("<")[0]),
+                         "frac": dom_rf["achieved"] / peak, "traffic": dom_traffic,
                          "peak_source": peak_src, "kernel": dom_rf["kernel"],
                          "launches_per_step": dom_rf["launches_per_step"],
                          "ms_per_step": dom_rf["ms_per_step"], "share_of_step": dom_rf["share_of_step"],
                          "algorithmic_bytes_per_step": dom_bytes,
+                         "algorithmic_bytes_per_launch": dom_bytes / domw["launches"],
                          "largest_kernel_any": dom["name"],
                          "step": {"achieved": achieved, "frac": achieved / peak,
                                   "algorithmic_bytes": alg_bytes,

@@ -13,4 +13,4 @@ cap single1024 -k 'regex:SingleBody.*int.1024' -s 1 -c 1
 cap direct8 -k 'regex:DirectBody.*int.8' -s 1 -c 1
 cp /tmp/prof/passB.ncu-rep gpurun_out/prof_r1_passB.ncu-rep
 # other configs, for the record (not bench lines)
-timeout 600 python profiles/other_configs.py 2>&1 | grep -v Warning | tail -12 | tee gpurun_out/other_configs_r1.txt
+timeout 600 python profiles/other_configs.py 2>&1 | grep -v Warning | tail -40 | tee gpurun_out/other_configs_r1.txt
