@@ -101,6 +101,9 @@ int cwtb_get_w(cwtb_ctx *ctx, void *out, int out_f64, int row0, int nrows);
  * sqrt(Np): the `fft` return value of wavelet.py:123.  Np/2-1 complex128. */
 int cwtb_get_signal_fft(cwtb_ctx *ctx, void *out);
 int64_t cwtb_padded_length(cwtb_ctx *ctx);
+/* Number of transforms this context has started: a handle to a device-resident result stays
+ * valid while this value is unchanged. */
+int64_t cwtb_job_serial(cwtb_ctx *ctx);
 /* Raw device pointer of the resident W (engine precision), for zero-copy
  * consumers (DLPack / __cuda_array_interface__ wrappers). */
 void *cwtb_w_device_ptr(cwtb_ctx *ctx);
@@ -125,8 +128,21 @@ int cwtb_icwt_sum_host(cwtb_ctx *ctx, const void *W, const double *scales,
 /* ---- derived products of the resident W ---------------- */
 /* power[j,n] = |W[j,n]|^2 (doubles, n_scales x n0). */
 int cwtb_get_power(cwtb_ctx *ctx, double *out);
-/* global wavelet spectrum: mean_n |W[j,n]|^2, n_scales doubles. */
+/* global wavelet spectrum: mean_n |W[j,n]|^2, n_scales doubles
+ * (`power.mean(axis=1)`, pycwt/sample/simple_sample.py:79). */
 int cwtb_global_power(cwtb_ctx *ctx, double *out);
+/* power[j,n] = row_scale[j] * |W[j,n]|^2; row_scale (one factor per row, NULL = 1) carries the
+ * rectification 1/s_j of Liu et al. 2007 (`power /= scales[:, None]`, docs/tutorial/cwt.md:49-53)
+ * and/or a variance normalisation. */
+int cwtb_get_power_scaled(cwtb_ctx *ctx, const double *row_scale, double *out);
+/* mean of |W[j,n]|^2 over the columns lo[j] <= n < hi[j] of every row (NaN for an empty range):
+ * the global spectrum restricted to the inside of the cone of influence, whose columns form one
+ * centred range per scale. */
+int cwtb_global_power_ranges(cwtb_ctx *ctx, const int64_t *lo, const int64_t *hi, double *out);
+/* scale-averaged power out[n] = sum_j weights[j] * |W[j,n]|^2, n0 doubles (Torrence & Compo 1998
+ * eq. 24; `scale_avg`, pycwt/sample/simple_sample.py:88-91: weights[j] = dj*dt/Cdelta/s_j inside
+ * the period band, 0 outside).  Rows with weight 0 are not read. */
+int cwtb_scale_avg_power(cwtb_ctx *ctx, const double *weights, double *out);
 
 /* ---- xwt / wct: pycwt/wavelet.py:394-399, 498-514; mothers.py:61-104 ------ */
 /* Two signals of equal length -> W12 = W1*conj(W2) (n_scales x n0 complex128). */

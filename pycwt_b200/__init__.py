@@ -9,6 +9,7 @@ runs in hand-written sm_100a CUDA kernels behind a C-ABI shared library
 from . import helpers, mothers, wavelet  # noqa: F401  (reachable as attributes, like pycwt's)
 from .wavelet import *  # noqa: F401,F403
 from ._engine import Engine, EngineError, default_engine, device_count  # noqa: F401
+from .resident import cwt_resident, ResidentTransform  # noqa: F401  (B200 extension)
 
 __all__ = ['cwt', 'icwt', 'significance', 'xwt', 'wct', 'wct_significance',
            'mothers', 'Morlet', 'Paul', 'DOG', 'MexicanHat']

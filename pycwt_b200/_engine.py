@@ -37,6 +37,7 @@ _SIGNATURES = {
     "cwtb_get_w": (_I, [_P, _P, _I, _I, _I]),
     "cwtb_get_signal_fft": (_I, [_P, _P]),
     "cwtb_padded_length": (_I64, [_P]),
+    "cwtb_job_serial": (_I64, [_P]),
     "cwtb_w_device_ptr": (_P, [_P]),
     "cwtb_last_kernel_ms": (_D, [_P]),
     "cwtb_last_launch_count": (_I, [_P]),
@@ -54,6 +55,9 @@ _SIGNATURES = {
     "cwtb_icwt_sum_host": (_I, [_P, _P, _P, _I, _I64, _P]),
     "cwtb_get_power": (_I, [_P, _P]),
     "cwtb_global_power": (_I, [_P, _P]),
+    "cwtb_get_power_scaled": (_I, [_P, _P, _P]),
+    "cwtb_global_power_ranges": (_I, [_P, _P, _P, _P]),
+    "cwtb_scale_avg_power": (_I, [_P, _P, _P]),
     "cwtb_xwt": (_I, [_P, _P, _P, _I64, _D, _P, _I, _I, _D, _P]),
     "cwtb_wct": (_I, [_P, _P, _P, _I64, _D, _D, _P, _I, _I, _D, _I, _P, _P]),
     "cwtb_smooth": (_I, [_P, _P, _I, _I, _I64, _D, _P, _I, _P]),
@@ -208,6 +212,9 @@ class Engine(object):
             self._check(self.lib.cwtb_get_signal_fft(self.h, _ptr(out)))
         return out
 
+    def job_serial(self):
+        return int(self.lib.cwtb_job_serial(self.h))
+
     def padded_length(self):
         return int(self.lib.cwtb_padded_length(self.h))
 
@@ -253,9 +260,34 @@ class Engine(object):
         self._check(self.lib.cwtb_global_power(self.h, _ptr(out)))
         return out
 
-    def power(self, nrows, n0):
-        out = np.empty((nrows, n0), dtype=np.float64)
-        self._check(self.lib.cwtb_get_power(self.h, _ptr(out)))
+    def global_power_ranges(self, lo, hi):
+        """Row means of |W|^2 over the column ranges [lo[j], hi[j]) (NaN where empty)."""
+        lo = np.ascontiguousarray(lo, dtype=np.int64)
+        hi = np.ascontiguousarray(hi, dtype=np.int64)
+        out = np.empty(lo.size, dtype=np.float64)
+        with self.lock:
+            self._check(self.lib.cwtb_global_power_ranges(self.h, _ptr(lo), _ptr(hi), _ptr(out)))
+        return out
+
+    def power(self, nrows, n0, row_scale=None):
+        """|W|^2 of the resident transform, optionally times one factor per row."""
+        out = self.result_array((nrows, n0), np.float64)
+        with self.lock:
+            if row_scale is None:
+                self._check(self.lib.cwtb_get_power(self.h, _ptr(out)))
+            else:
+                rs = np.ascontiguousarray(row_scale, dtype=np.float64)
+                if rs.size != nrows:
+                    raise ValueError("power: one factor per row expected")
+                self._check(self.lib.cwtb_get_power_scaled(self.h, _ptr(rs), _ptr(out)))
+        return out
+
+    def scale_avg_power(self, weights):
+        """sum_j weights[j] |W[j, :]|^2 of the resident transform (TC98 eq. 24)."""
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        out = np.empty(self._resident_n0, dtype=np.float64)
+        with self.lock:
+            self._check(self.lib.cwtb_scale_avg_power(self.h, _ptr(w), _ptr(out)))
         return out
 
     # ---- cross wavelet / coherence ------------------------------------------------------

@@ -126,6 +126,7 @@ struct cwtb_ctx {
   rt_stream aux_stream{};        // single-kernel classes run here, concurrently with the two-kernel chains
   rt_stream chain2_stream{};     // every second two-kernel class runs here (own Z and band chunk)
   rt_stream cur{};               // stream the launcher uses right now
+  long long serial = 0;          // counts transforms: identifies what is resident (cwtb_job_serial)
   int two_streams = 1;           // CWTB_STREAMS=1 disables the overlap
   int three_streams = 1;         // CWTB_STREAMS=2: single-kernel classes only
   rt_stream copy_streams[4]{};   // large D2H copies are split over several streams / copy engines
@@ -142,11 +143,12 @@ struct cwtb_ctx {
   int pf_dist = 148;   // PassB: L2 prefetch distance in tiles (CWTB_PF_DIST)
   int gauss_rec = 1;   // dense Morlet scales: Gaussian by recurrence (CWTB_GAUSS_REC=0: exp per bin)
   int pf_dist_a = 148;  // PassA (band): L2 prefetch distance in tiles (CWTB_PF_DIST_A)
+  int k2_band_log2 = 9; // second-pass length of the pruned two-kernel scales: 2^9 or 2^10 (CWTB_K2_BAND)
   size_t batch_bytes = (size_t)4 << 30;   // coefficients per chunk of cwtb_cwt_batch  // K' <= 2^13 handled by one kernel (K' > 1024: DirectBody)
   double2 *tw64 = nullptr;
   float2 *tw32 = nullptr;
   std::map<unsigned, NTabDev> ntabs;
-  Buf ctr, sig, sig2, spec, Z, Z2, Y, B, W, W2, descs, table, scratch, C, A12, F, aux, rowd, win, mask, hist, noise;
+  Buf ctr, sig, sig2, spec, Z, Z2, Y, B, W, W2, descs, table, scratch, C, A12, F, aux, rowd, win, mask, hist, noise, wide;
   Job job;
   const void *job_dsig = nullptr;  // device signal of the last cwt_dev call (not owned)
   double last_ms = 0;
@@ -932,7 +934,10 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
       PassAArgs<T> a{};
       a.descs = ddesc; a.spec = spec; a.Bbuf = Bbuf; a.Z = (V *)Zb.p; a.tw = Tw<T>::get(c);
       a.fam = fam; a.nt = nt; a.N = N; a.first = cl.first + g0; a.row0 = 0; a.zmod = 1 << 30;
-      a.pf_dist = c->pf_dist_a; a.K2 = K2C; a.gauss_rec = c->gauss_rec;
+      // band scales: second pass of 512 points (full 128-byte output runs, conflict-free tile);
+      // dense scales keep 1024 so that K1 = N/K2 <= 1024
+      const int l2k = (dense || c->fused || cl.log2K > 19) ? 10 : c->k2_band_log2;
+      a.pf_dist = c->pf_dist_a; a.K2 = 1u << l2k; a.gauss_rec = c->gauss_rec;
       PassBArgs<T> b{};
       b.Z = (const V *)Zb.p; b.out = W; b.tw = Tw<T>::get(c); b.descs = ddesc;
       b.pitch = job.n0; b.nout = job.n0; b.N = N; b.first = cl.first + g0; b.row0 = 0;
@@ -949,10 +954,14 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
         if (e) return e;
         continue;
       }
-      e = dense ? dispatch_passA<T, +1, MODE_DENSE>(c, cl.log2K - 10, a, ng)
-                : dispatch_passA<T, +1, MODE_BAND>(c, cl.log2K - 10, a, ng);
+      e = dense ? dispatch_passA<T, +1, MODE_DENSE>(c, cl.log2K - l2k, a, ng)
+                : dispatch_passA<T, +1, MODE_BAND>(c, cl.log2K - l2k, a, ng);
       if (e) return e;
-      if ((e = launch<PassBBody<T, +1>>(c, (N / K2C + Lay<T, K2C>::P - 1) / Lay<T, K2C>::P, ng, b))) return e;
+      if (l2k == 9)
+        e = launch<PassBBody<T, +1, 512>>(c, (N / 512 + Lay<T, 512>::P - 1) / Lay<T, 512>::P, ng, b);
+      else
+        e = launch<PassBBody<T, +1>>(c, (N / K2C + Lay<T, K2C>::P - 1) / Lay<T, K2C>::P, ng, b);
+      if (e) return e;
     }
     c->cur = c->stream;
   }
@@ -1076,6 +1085,7 @@ int cwtb_create(int device, cwtb_ctx **out) {
   if (const char *g = getenv("CWTB_FUSED")) c->fused = atoi(g);
   if (const char *g = getenv("CWTB_PF_DIST")) c->pf_dist = std::max(0, atoi(g));
   if (const char *g = getenv("CWTB_PF_DIST_A")) c->pf_dist_a = std::max(0, atoi(g));
+  if (const char *g = getenv("CWTB_K2_BAND")) c->k2_band_log2 = atoi(g) == 10 ? 10 : 9;
   if (const char *g = getenv("CWTB_GAUSS_REC")) c->gauss_rec = atoi(g);
   if (const char *g = getenv("CWTB_BATCH_MB")) c->batch_bytes = (size_t)std::max(1, atoi(g)) << 20;
   if (const char *g = getenv("CWTB_RING")) c->ring = std::max(1, atoi(g));
@@ -1097,7 +1107,7 @@ void cwtb_destroy(cwtb_ctx *c) {
   cudaStreamSynchronize(c->stream);
 #endif
   for (Buf *b : {&c->ctr, &c->sig, &c->sig2, &c->spec, &c->Z, &c->Z2, &c->Y, &c->B, &c->W, &c->W2, &c->descs, &c->table, &c->scratch,
-                 &c->C, &c->A12, &c->F, &c->aux, &c->rowd, &c->win, &c->mask, &c->hist, &c->noise})
+                 &c->C, &c->A12, &c->F, &c->aux, &c->rowd, &c->win, &c->mask, &c->hist, &c->noise, &c->wide})
     if (b->p) rt_free(b->p);
   for (auto &kv : c->ntabs) { rt_free(kv.second.hi); rt_free(kv.second.lo); }
   if (c->tw64) rt_free(c->tw64);
@@ -1174,6 +1184,7 @@ static int prepare(cwtb_ctx *c, long long n0, double dt, const double *scales, i
   RT(cudaSetDevice(c->device));
 #endif
   if (nbatch < 1 || (long long)nbatch * S > 60000) return fail(c, CWTB_ERR_ARG, "batch too large for one launch");
+  ++c->serial;   // whatever was resident is about to be replaced
   int e = build_job(c, c->job, n0, dt, scales, S, family, param, precision, table != nullptr, nbatch);
   if (e) return e;
   if (family == CWTB_TABLE) {
@@ -1243,6 +1254,7 @@ int cwtb_bench_last(cwtb_ctx *c, int iters, double *ms_out) {
 double cwtb_last_kernel_ms(cwtb_ctx *c) { return c ? c->last_ms : -1; }
 int cwtb_last_launch_count(cwtb_ctx *c) { return c ? c->launches : -1; }
 int64_t cwtb_padded_length(cwtb_ctx *c) { return (c && c->job.valid) ? (int64_t)c->job.N : -1; }
+int64_t cwtb_job_serial(cwtb_ctx *c) { return c ? c->serial : -1; }
 void *cwtb_w_device_ptr(cwtb_ctx *c) { return (c && c->job.valid) ? c->W.p : nullptr; }
 
 int cwtb_last_plan(cwtb_ctx *c, int *out, int n) {
@@ -1280,11 +1292,27 @@ int cwtb_get_w(cwtb_ctx *c, void *out, int out_f64, int row0, int nrows) {
     RT(rt_d2h(out, (const float2 *)c->W.p + (size_t)row0 * job.n0, cnt * sizeof(float2), c->stream));
     RT(rt_sync(c->stream));
   } else {
-    std::vector<float> tmp(cnt * 2);
-    RT(rt_d2h(tmp.data(), (const float2 *)c->W.p + (size_t)row0 * job.n0, cnt * sizeof(float2), c->stream));
-    RT(rt_sync(c->stream));
-    double *o = (double *)out;
-    for (size_t i = 0; i < cnt * 2; ++i) o[i] = (double)tmp[i];
+    // complex64 on the device, complex128 for the caller: widen on the device in chunks and
+    // copy each chunk out while the next one is converted (two staging halves, two streams).
+    // 16 B per element over PCIe beats an 8 B copy plus a host-side conversion pass.
+    const float2 *src = (const float2 *)c->W.p + (size_t)row0 * job.n0;
+    const size_t chunk = std::min<size_t>(cnt, (size_t)8 << 20);   // elements per staging half
+    int e;
+    if ((e = ensure(c, c->wide, 2 * chunk * sizeof(double2)))) return e;
+    RT(rt_sync(c->stream));   // kernels done
+    int half = 0;
+    for (size_t off = 0; off < cnt; off += chunk, half ^= 1) {
+      const size_t m = std::min(chunk, cnt - off);
+      double2 *stage = (double2 *)c->wide.p + (size_t)half * chunk;
+      WidenArgs wa{src + off, stage, (long long)m};
+      c->cur = c->copy_streams[half];
+      e = launch<WidenBody>(c, (unsigned)((m + 4 * NT - 1) / (4 * NT)), 1, wa);
+      c->cur = c->stream;
+      if (e) return e;
+      RT(rt_d2h((double2 *)out + off, stage, m * sizeof(double2), c->copy_streams[half]));
+    }
+    RT(rt_sync(c->copy_streams[0]));
+    RT(rt_sync(c->copy_streams[1]));
   }
   return 0;
 }
@@ -1483,33 +1511,84 @@ int cwtb_icwt_sum_host(cwtb_ctx *c, const void *W, const double *scales, int n_s
   return 0;
 }
 
-static int power_common(cwtb_ctx *c, double *power_out, double *mean_out) {
+static int power_common(cwtb_ctx *c, double *power_out, double *mean_out, const double *row_scale,
+                        const int64_t *lo, const int64_t *hi) {
   if (!c || !c->job.valid) return fail(c, CWTB_ERR_STATE, "no transform resident");
   const Job &job = c->job;
   const int R = job.S * job.nbatch;
   const size_t cnt = (size_t)R * job.n0;
-  int e = ensure(c, c->aux, (power_out ? cnt : 0) * sizeof(double) + (size_t)R * sizeof(double));
+  // aux: [row sums R][row factors R][lo R][hi R][power cnt]
+  int e = ensure(c, c->aux, (power_out ? cnt : 0) * sizeof(double) + (size_t)4 * R * sizeof(double));
   if (e) return e;
   double *dsum = (double *)c->aux.p;
-  double *dpow = power_out ? dsum + R : nullptr;
+  double *dmul = dsum + R;
+  long long *dlo = (long long *)(dmul + R), *dhi = dlo + R;
+  double *dpow = power_out ? (double *)(dhi + R) : nullptr;
   RT(rt_memset(dsum, 0, (size_t)R * sizeof(double), c->stream));
+  if (row_scale) RT(rt_h2d(dmul, row_scale, (size_t)R * sizeof(double), c->stream));
+  std::vector<long long> rng;
+  if (lo && hi) {
+    rng.resize(2 * (size_t)R);
+    for (int j = 0; j < R; ++j) {
+      rng[j] = std::max<long long>(0, lo[j]);
+      rng[R + j] = std::min<long long>(job.n0, hi[j]);
+    }
+    RT(rt_h2d(dlo, rng.data(), rng.size() * sizeof(long long), c->stream));
+  }
   const unsigned gx = (unsigned)((job.n0 + 8 * NT - 1) / (8 * NT));
   if (job.precision == CWTB_F64) {
-    PowerArgs<double> a{(const double2 *)c->W.p, dpow, dsum, job.n0};
+    PowerArgs<double> a{(const double2 *)c->W.p, dpow, dsum, job.n0, row_scale ? dmul : nullptr,
+                        rng.empty() ? nullptr : dlo, rng.empty() ? nullptr : dhi};
     e = launch<PowerBody<double>>(c, gx, R, a);
   } else {
-    PowerArgs<float> a{(const float2 *)c->W.p, dpow, dsum, job.n0};
+    PowerArgs<float> a{(const float2 *)c->W.p, dpow, dsum, job.n0, row_scale ? dmul : nullptr,
+                       rng.empty() ? nullptr : dlo, rng.empty() ? nullptr : dhi};
     e = launch<PowerBody<float>>(c, gx, R, a);
   }
   if (e) return e;
   if (power_out) RT(rt_d2h(power_out, dpow, cnt * sizeof(double), c->stream));
   if (mean_out) RT(rt_d2h(mean_out, dsum, (size_t)R * sizeof(double), c->stream));
-  RT(rt_sync(c->stream));
-  if (mean_out) for (int j = 0; j < R; ++j) mean_out[j] /= (double)job.n0;
+  RT(rt_sync(c->stream));   // also covers the pageable host sources above
+  if (mean_out)
+    for (int j = 0; j < R; ++j) {
+      const long long cntj = rng.empty() ? (long long)job.n0 : rng[R + j] - rng[j];
+      mean_out[j] = cntj > 0 ? mean_out[j] / (double)cntj : std::nan("");
+    }
   return 0;
 }
-int cwtb_get_power(cwtb_ctx *c, double *out) { return power_common(c, out, nullptr); }
-int cwtb_global_power(cwtb_ctx *c, double *out) { return power_common(c, nullptr, out); }
+int cwtb_get_power(cwtb_ctx *c, double *out) { return power_common(c, out, nullptr, nullptr, nullptr, nullptr); }
+int cwtb_global_power(cwtb_ctx *c, double *out) { return power_common(c, nullptr, out, nullptr, nullptr, nullptr); }
+int cwtb_get_power_scaled(cwtb_ctx *c, const double *row_scale, double *out) {
+  if (!out) return fail(c, CWTB_ERR_ARG, "null argument");
+  return power_common(c, out, nullptr, row_scale, nullptr, nullptr);
+}
+int cwtb_global_power_ranges(cwtb_ctx *c, const int64_t *lo, const int64_t *hi, double *out) {
+  if (!lo || !hi || !out) return fail(c, CWTB_ERR_ARG, "null argument");
+  return power_common(c, nullptr, out, nullptr, lo, hi);
+}
+
+int cwtb_scale_avg_power(cwtb_ctx *c, const double *weights, double *out) {
+  if (!c || !c->job.valid) return fail(c, CWTB_ERR_STATE, "no transform resident");
+  if (!weights || !out) return fail(c, CWTB_ERR_ARG, "null argument");
+  const Job &job = c->job;
+  if (job.nbatch != 1) return fail(c, CWTB_ERR_UNSUPPORTED, "scale average of a batched transform: fetch rows per channel");
+  std::vector<double> w(weights, weights + job.S);
+  int e = upload_doubles(c, c->rowd, w);
+  if (e) return e;
+  if ((e = ensure(c, c->aux, (size_t)job.n0 * sizeof(double)))) return e;
+  const unsigned gx = (unsigned)((job.n0 + NT - 1) / NT);
+  if (job.precision == CWTB_F64) {
+    ScaleAvgArgs<double> a{(const double2 *)c->W.p, (const double *)c->rowd.p, (double *)c->aux.p, job.n0, job.S};
+    e = launch<ScaleAvgBody<double>>(c, gx, 1, a);
+  } else {
+    ScaleAvgArgs<float> a{(const float2 *)c->W.p, (const double *)c->rowd.p, (double *)c->aux.p, job.n0, job.S};
+    e = launch<ScaleAvgBody<float>>(c, gx, 1, a);
+  }
+  if (e) return e;
+  RT(rt_d2h(out, c->aux.p, (size_t)job.n0 * sizeof(double), c->stream));
+  RT(rt_sync(c->stream));
+  return 0;
+}
 
 int cwtb_xwt(cwtb_ctx *c, const double *y1, const double *y2, int64_t n0, double dt, const double *scales,
              int n_scales, int family, double param, void *W12_out) {

@@ -109,14 +109,17 @@ template <typename T, int K, bool ROWS = false> struct Lay {
   static constexpr int TILE = TileCfg<T>::TILE;
   static constexpr int P = TILE / K;
   static constexpr int Q = TileCfg<T>::Q;
-  // ROWS = true: every row is one contiguous run (a bulk-async copy fills it).  Pitch K+1 makes
-  // the b-lanes of the last pass hit distinct banks when P >= Q; for P = Q/2 the pitch K+2
-  // spreads the b-lanes over every second bank group and the two positions sharing a
-  // quarter-warp collide 2-way on the last pass's reads.
-  // ROWS = false (default): for P < Q one pad element is inserted after every 16 positions
-  // (pos + pos/16), which shifts the second position of a quarter-warp onto the free bank
-  // groups -> conflict-free in every pass.
-  static constexpr bool SKEW = (P < Q) && !ROWS;
+  // For P < Q one pad element is inserted after every 16 positions (pos + pos/16), which shifts
+  // the second position of a quarter-warp onto the free bank groups -> conflict-free in every
+  // pass.  ROWS = true marks tiles whose rows are filled by bulk-async (TMA) copies: with the
+  // skew a row arrives as K/16 copies of 16 elements (CHUNKED); that needs 16-byte aligned
+  // chunk starts, i.e. 16-byte elements (fp64) -- fp32 row tiles stay unskewed (one contiguous
+  // copy per row, 2-way conflict on the last pass's reads when P = Q/2).
+#ifndef CWTB_ROWS_SKEW
+#define CWTB_ROWS_SKEW 0
+#endif
+  static constexpr bool SKEW = (P < Q) && (!ROWS || (CWTB_ROWS_SKEW && sizeof(T) == 8));
+  static constexpr bool CHUNKED = ROWS && SKEW;
   static constexpr int KS = SKEW ? K + K / 16 : K;
   static constexpr int PITCH = (P < Q) ? (KS - (KS % Q) + 2 + ((KS % Q) > 2 ? Q : 0)) : K + 1;
   static constexpr int ELEMS = P * PITCH;
@@ -128,6 +131,12 @@ template <typename T, int K, bool ROWS = false> struct Lay {
 // ---- bulk asynchronous copy (TMA, cp.async.bulk) global -> shared with an mbarrier --------
 // One thread arms the barrier with the expected byte count and issues the copies; every
 // thread then waits on the barrier's phase.  Host emulation: plain memcpy, wait is a no-op.
+HD void warp_sync() {
+#if defined(__CUDA_ARCH__) && !defined(CWTB_HOST_EMU)
+  __syncwarp();
+#endif
+}
+
 struct TileBarrier {
   unsigned long long *bar;  // 8-byte slot in shared memory
   HD void init_and_expect(unsigned bytes) const {

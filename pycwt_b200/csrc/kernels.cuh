@@ -338,7 +338,7 @@ template <typename T, int K1> struct DirectBody {
   }
 };
 
-// ---- Body: second kernel of the two-kernel path: K2 = 1024 over r2, rows of Z -------
+// ---- Body: second kernel of the two-kernel path: K2 = 1024 or 512 over r2, rows of Z -------
 template <typename T> struct PassBArgs {
   const cx<T> *Z;          // [ny][U][K2]
   cx<T> *out;              // [rows][pitch]
@@ -358,12 +358,15 @@ template <typename T> struct PassBArgs {
                            // (final index n*ileave + by % ileave): three-level path, Np > 2^20
 };
 
-template <typename T, int SIGN> struct PassBBody {
+// K2 = 1024 leaves P = TILE/K2 = Q/2 transforms per tile (64-byte output runs, 2-way bank
+// conflict on the last pass of the unskewed row layout); K2 = 512 has P = Q: 128-byte output
+// runs, conflict-free.  The pruned (band) scales use 512, the dense ones need 1024 (K1 <= 1024).
+template <typename T, int SIGN, int K2 = K2C> struct PassBBody {
   static constexpr int NTB = TileCfg<T>::NT;   // threads per CTA of this kernel
   static constexpr int NT = NTB;
   using V = cx<T>;
   using Args = PassBArgs<T>;
-  static constexpr int K = K2C;
+  static constexpr int K = K2;
   using LY = Lay<T, K, true>;   // rows are filled by bulk-async copies: no skew
   static constexpr int NP = Plan<K>::NP;
   // phase 0: one thread issues the bulk-async (TMA) copies of the tile's rows -- the rows
@@ -378,14 +381,24 @@ template <typename T, int SIGN> struct PassBBody {
     tb.bar = (unsigned long long *)((char *)smraw + LY::TILE_BYTES);
     if constexpr (PH == 0) {
       const int nvalid = (U - u0) < LY::P ? (U - u0) : LY::P;
-      if (tid == 0) {
-        tb.init_and_expect((unsigned)(nvalid * K * sizeof(V)));
+      if (tid < 32) {   // warp 0 issues the copies
+        if (tid == 0) tb.init_and_expect((unsigned)(nvalid * K * sizeof(V)));
+        warp_sync();    // barrier initialised before any lane's copy refers to it
         const V *src = a.Z + (size_t)(by % a.zmod) * a.N + (size_t)u0 * K;
-        for (int b = 0; b < nvalid; ++b)
-          tb.copy(sm + LY::phys(b, 0), src + (size_t)b * K, (unsigned)(K * sizeof(V)));
+        if constexpr (LY::CHUNKED) {
+          // skewed rows: 16-element pieces, spread over the lanes
+          constexpr int NCH = K / 16;
+          for (int i = tid; i < nvalid * NCH; i += 32) {
+            const int b = i / NCH, ch = i % NCH;
+            tb.copy(sm + LY::phys(b, 16 * ch), src + (size_t)b * K + 16 * ch, (unsigned)(16 * sizeof(V)));
+          }
+        } else if (tid == 0) {
+          for (int b = 0; b < nvalid; ++b)
+            tb.copy(sm + LY::phys(b, 0), src + (size_t)b * K, (unsigned)(K * sizeof(V)));
+        }
         // warm L2 with the tile a CTA `pf_dist` blocks ahead will load (same row of the grid,
         // or the next row when this one is exhausted): its TMA copies then hit L2
-        if (a.pf_dist > 0) {
+        if (tid == 0 && a.pf_dist > 0) {
           long long t = (long long)bx + a.pf_dist;
           int py = by;
           const int tiles = (U + LY::P - 1) / LY::P;
@@ -894,6 +907,8 @@ template <typename T> struct PowerArgs {
   double *power;     // [rows][n] or null
   double *rowsum;    // [rows] accumulated with atomics, or null
   long long n;
+  const double *rowmul;        // per-row factor of the stored power (rectification 1/s_j), or null
+  const long long *lo, *hi;    // per-row column range [lo, hi) of the row sum, or null (all)
 };
 template <typename T> struct PowerBody {
   using Args = PowerArgs<T>;
@@ -902,13 +917,15 @@ template <typename T> struct PowerBody {
   template <int PH> HD static void phase(const Args &a, int bx, int by, int tid, void *) {
     // each thread covers 8 columns; one atomic per thread for the row sum
     double acc = 0;
+    const double mul = a.rowmul ? a.rowmul[by] : 1.0;
+    const long long lo = a.lo ? a.lo[by] : 0, hi = a.hi ? a.hi[by] : a.n;
     for (int i = 0; i < 8; ++i) {
       const long long n = ((long long)bx * 8 + i) * NT + tid;
       if (n >= a.n) break;
       const cx<T> w = a.W[(size_t)by * a.n + n];
-      const double p = (double)w.x * w.x + (double)w.y * w.y;
+      const double p = ((double)w.x * w.x + (double)w.y * w.y) * mul;
       if (a.power) a.power[(size_t)by * a.n + n] = p;
-      acc += p;
+      if (n >= lo && n < hi) acc += p;
     }
     if (a.rowsum) {
 #if defined(__CUDA_ARCH__) && !defined(CWTB_HOST_EMU)
@@ -917,6 +934,33 @@ template <typename T> struct PowerBody {
       a.rowsum[by] += acc;
 #endif
     }
+  }
+};
+
+// ---- Body: scale-averaged power  out[n] = sum_j w_j |W[j,n]|^2  (TC98 eq. 24; the sample
+// scripts' `scale_avg`, simple_sample.py:88-91).  Rows with w_j = 0 are not read. ------------
+template <typename T> struct ScaleAvgArgs {
+  const cx<T> *W;
+  const double *w;   // per row
+  double *out;
+  long long n;
+  int rows;
+};
+template <typename T> struct ScaleAvgBody {
+  using Args = ScaleAvgArgs<T>;
+  static constexpr int NPHASE = 1;
+  static constexpr size_t SMEM = 0;
+  template <int PH> HD static void phase(const Args &a, int bx, int, int tid, void *) {
+    const long long n = (long long)bx * NT + tid;
+    if (n >= a.n) return;
+    double acc = 0.0;
+    for (int j = 0; j < a.rows; ++j) {
+      const double wj = a.w[j];
+      if (wj == 0.0) continue;
+      const cx<T> v = a.W[(size_t)j * a.n + n];
+      acc += wj * ((double)v.x * v.x + (double)v.y * v.y);
+    }
+    a.out[n] = acc;
   }
 };
 
@@ -929,6 +973,24 @@ struct R2CBody {
   template <int PH> HD static void phase(const Args &a, int bx, int, int tid, void *) {
     const long long i = (long long)bx * NT + tid;
     if (i < a.count) a.out[i] = make_double2(a.in[i], 0.0);
+  }
+};
+
+// ---- Body: complex64 -> complex128 (fp32 transforms returned through the reference API) ----
+struct WidenArgs { const float2 *in; double2 *out; long long count; };
+struct WidenBody {
+  using Args = WidenArgs;
+  static constexpr int NPHASE = 1;
+  static constexpr size_t SMEM = 0;
+  template <int PH> HD static void phase(const Args &a, int bx, int, int tid, void *) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long i = ((long long)bx * 4 + u) * NT + tid;
+      if (i < a.count) {
+        const float2 v = a.in[i];
+        a.out[i] = make_double2((double)v.x, (double)v.y);
+      }
+    }
   }
 };
 

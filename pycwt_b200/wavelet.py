@@ -11,6 +11,7 @@ Division of labour:
 There is no CPU fallback: without the CUDA library or a device, calls raise EngineError.
 """
 import os
+import threading as _threading
 
 import numpy as np
 from scipy.stats import chi2
@@ -91,18 +92,37 @@ def cwt(signal, dt, dj=1/12, s0=-1, J=-1, wavelet='morlet', freqs=None):
 
     bad = _nan_rows(wavelet, np.asarray(sj, dtype=float), npad, dt)
     keep = ~bad
-    if keep.any():
-        W, eng = _transform(signal, dt, np.asarray(sj)[keep], wavelet)
-        sj, freqs = sj[keep], freqs[keep]
-    else:
-        # every row NaN: the reference keeps them all (np.any(sel) is False)
-        _, eng = _transform(signal, dt, np.asarray(sj)[:1], wavelet)
-        W = np.full((len(sj), n0), np.nan + 1j * np.nan)
 
-    coi = (n0 / 2 - np.abs(np.arange(0, n0) - (n0 - 1) / 2))
-    coi = wavelet.flambda() * wavelet.coi() * dt * coi
-    ftfreqs = 2 * np.pi * fft.fftfreq(npad, dt)
-    return (W, sj, freqs, coi, eng.signal_fft(), ftfreqs[1:npad // 2] / (2 * np.pi))
+    # O(n0) host-side outputs (cone of influence, Fourier frequencies): for long signals they
+    # are computed on a helper thread while the engine call (which releases the GIL) copies W
+    # back from the device.
+    side = {}
+
+    def host_side():
+        coi = (n0 / 2 - np.abs(np.arange(0, n0) - (n0 - 1) / 2))
+        side['coi'] = wavelet.flambda() * wavelet.coi() * dt * coi
+        ftfreqs = 2 * np.pi * fft.fftfreq(npad, dt)
+        side['fftfreqs'] = ftfreqs[1:npad // 2] / (2 * np.pi)
+
+    helper = None
+    if n0 >= (1 << 16):
+        helper = _threading.Thread(target=host_side)
+        helper.start()
+    try:
+        if keep.any():
+            W, eng = _transform(signal, dt, np.asarray(sj)[keep], wavelet)
+            sj, freqs = sj[keep], freqs[keep]
+        else:
+            # every row NaN: the reference keeps them all (np.any(sel) is False)
+            _, eng = _transform(signal, dt, np.asarray(sj)[:1], wavelet)
+            W = np.full((len(sj), n0), np.nan + 1j * np.nan)
+        spectrum = eng.signal_fft()
+    finally:
+        if helper is not None:
+            helper.join()
+    if helper is None:
+        host_side()
+    return (W, sj, freqs, side['coi'], spectrum, side['fftfreqs'])
 
 
 def icwt(W, sj, dt, dj=1/12, wavelet='morlet'):

@@ -128,3 +128,48 @@ def test_three_level_path_beyond_2_20(emu):
     m = orc.Morlet(6)
     Wr = orc.cwt(x, 1.0, wavelet=m, freqs=1 / (m.flambda() * sj))[0]
     assert relerr(W, Wr) < 1e-10
+
+
+def _sample_products(x, dt, dj, s0, J, mother_o):
+    """The derived products of pycwt/sample/simple_sample.py:64-91 in NumPy on the oracle's W."""
+    W, sj, freqs, coi, _, _ = orc.cwt(x, dt, dj, s0, J, mother_o)
+    power = np.abs(W) ** 2
+    period = 1 / freqs
+    out = {"W": W, "sj": sj, "power": power, "rect": power / sj[:, None],
+           "glbl": power.mean(axis=1), "coi": coi, "period": period}
+    sel = (period >= 2) & (period < 8)
+    out["scale_avg"] = 1.7 * dj * dt / mother_o.cdelta * (power / sj[:, None])[sel].sum(axis=0)
+    inside = period[:, None] <= coi[None, :]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        out["glbl_coi"] = np.where(inside.any(axis=1), (power * inside).sum(axis=1) / inside.sum(axis=1), np.nan)
+    out["iW"] = orc.icwt(W, sj, dt, dj, mother_o)
+    return out
+
+
+def check_resident_products(eng, precision_tol=1e-12):
+    import pycwt_b200 as pycwt
+    g = load_golden("nino3_morlet_tutorial")
+    x, dt = g["x"], float(g["dt"])
+    ref = _sample_products(x, dt, 0.25, 0.5, 28, orc.Morlet(6))
+    r = pycwt.cwt_resident(x, dt, 0.25, 0.5, 28, pycwt.Morlet(6), engine=eng)
+    assert r.shape == ref["W"].shape
+    assert np.array_equal(r.scales, ref["sj"]) and np.array_equal(r.coi, ref["coi"])
+    assert relerr(r.power(), ref["power"]) < precision_tol
+    assert relerr(r.power(rectify=True), ref["rect"]) < precision_tol
+    assert relerr(r.power(variance=2.5), ref["power"] / 2.5) < precision_tol
+    assert relerr(r.global_power(), ref["glbl"]) < precision_tol
+    got = r.global_power(inside_coi=True)
+    assert np.array_equal(np.isnan(got), np.isnan(ref["glbl_coi"])) and np.isnan(got).any()
+    ok = ~np.isnan(got)
+    assert relerr(got[ok], ref["glbl_coi"][ok]) < precision_tol
+    assert relerr(r.scale_avg_power(2, 8, variance=1.7), ref["scale_avg"]) < precision_tol
+    assert relerr(r.icwt(), ref["iW"]) < precision_tol
+    assert relerr(r.wave(), ref["W"]) < precision_tol
+    # the handle dies with the next transform on the same engine
+    eng.cwt(x, dt, ref["sj"][:3], 0, 6.0, fetch=False)
+    with pytest.raises(pycwt.EngineError):
+        r.global_power()
+
+
+def test_resident_transform_products(emu):
+    check_resident_products(emu)

@@ -220,3 +220,59 @@ def test_engine_c2c_hook(pycwt):
         assert relerr(eng.fft_c2c(x, -1), np.fft.fft(x, axis=1)) < 1e-13
         assert relerr(eng.fft_c2c(x, +1), np.fft.ifft(x, axis=1) * n) < 1e-13
         assert relerr(eng.fft_c2c(x, -1, precision=1), np.fft.fft(x, axis=1)) < 5e-6
+
+
+def test_resident_transform_products(pycwt):
+    """power, rectified power, global spectrum (also inside the COI),
+    scale-averaged power and icwt evaluated on the device-resident transform equal the NumPy
+    arithmetic of pycwt/sample/simple_sample.py:64-91 on the oracle's W."""
+    from test_emu_kernels import check_resident_products
+    check_resident_products(pycwt.default_engine(), TOL64)
+
+
+def test_resident_products_full_size(pycwt):
+    """North-star size: the reductions agree with NumPy on rows fetched from the device,
+    and the fp32 transform comes back as complex128 through the widening fetch."""
+    n = 2 ** 20
+    x = chirp(n)
+    r = pycwt.cwt_resident(x, 1.0, 1 / 16, 2.0, 255, pycwt.Morlet(6))
+    glbl = r.global_power()
+    savg = r.scale_avg_power(16.0, 64.0, variance=1.0)
+    inside = r.global_power(inside_coi=True)
+    eng = r.engine
+    rows = [0, 100, 255]
+    per = r.period
+    lo, hi = r.coi_ranges()
+    for j in rows:
+        Wj = np.empty((1, n), dtype=np.complex128)
+        eng._check(eng.lib.cwtb_get_w(eng.h, Wj.ctypes.data, 1, j, 1))
+        p = np.abs(Wj[0]) ** 2
+        assert abs(glbl[j] / p.mean() - 1) < 1e-12
+        assert np.array_equal(np.nonzero(per[j] <= r.coi)[0][[0, -1]], [lo[j], hi[j] - 1])
+        assert abs(inside[j] / p[lo[j]:hi[j]].mean() - 1) < 1e-12
+    sel = np.nonzero((per >= 16.0) & (per < 64.0))[0]
+    acc = np.zeros(n)
+    for j in sel:
+        Wj = np.empty((1, n), dtype=np.complex128)
+        eng._check(eng.lib.cwtb_get_w(eng.h, Wj.ctypes.data, 1, int(j), 1))
+        acc += np.abs(Wj[0]) ** 2 / r.scales[j]
+    acc *= r.dj * r.dt / r.wavelet.cdelta
+    assert relerr(savg, acc) < 1e-12
+
+
+def test_fp32_fetch_widening_large(pycwt, monkeypatch):
+    """fp32 engine, complex128 result larger than one staging chunk (two-stream widening)."""
+    monkeypatch.setenv("CWTB_PRECISION", "fp32")
+    x = chirp(2 ** 18).astype(np.float32)
+    kw = dict(s0=0.5033, dj=1 / 8, J=127)
+    W, sj, *_ = pycwt.cwt(x, 1.0, wavelet=pycwt.DOG(2), **kw)
+    assert W.dtype == np.complex128 and W.shape == (128, 2 ** 18)
+    eng = pycwt.default_engine()
+    W32 = eng.get_w(128, 2 ** 18, precision=1, out_f64=False)
+    assert W32.dtype == np.complex64
+    assert np.array_equal(W, W32.astype(np.complex128))
+    rows = [0, 64, 127]
+    om = 2 * np.pi * np.fft.fftfreq(2 ** 18, 1.0)
+    xh = np.fft.fft(x.astype(np.float64))
+    filt = np.sqrt(sj[rows, None] * om[1] * 2 ** 18) * np.conj(orc.DOG(2).psi_ft(sj[rows, None] * om))
+    assert relerr(W[rows], np.fft.ifft(xh * filt, axis=1)) < TOL32
