@@ -56,3 +56,48 @@ def cwt_batch_sharded(X, dt, scales, family, param, precision, engine, dist=None
     lo, hi = shard_range(X.shape[0], rank, world)
     power, _ = engine.cwt_batch(X[lo:hi], dt, scales, family, param, precision, want_power=True)
     return gather_rows(power, X.shape[0], dist, device)
+
+
+def sum_over_ranks(array, dist=None, device=None):
+    """Element-wise sum of an integer/float array over all ranks (every rank gets the total)."""
+    array = np.ascontiguousarray(array)
+    if dist is None or dist.get_world_size() == 1:
+        return array
+    import torch
+    t = torch.from_numpy(array.copy())
+    if device is not None:
+        t = t.to(device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.cpu().numpy()
+
+
+def surrogate_pair(seed, index, N, al1, al2):
+    """Surrogate pair number `index` of a sharded Monte-Carlo run: white noise like the
+    reference's `rednoise` output (helpers.py:146-173 filters a length-1 axis, SURVEY 8a row
+    10), from an RNG stream keyed by (seed, index) so that the pair does not depend on which
+    rank draws it."""
+    rs = np.random.RandomState([int(seed) & 0x7fffffff, int(index)])
+
+    def white(al):
+        tau = 0 if al == 0 else int(np.ceil(-2 / np.log(np.abs(al))))
+        return rs.randn(N + tau)[tau:]
+    return white(al1), white(al2)
+
+
+def wct_significance_sharded(al1, al2, dt, dj, s0, J, significance_level=0.95, wavelet='morlet',
+                             mc_count=300, seed=0, engine=None, dist=None, device=None):
+    """Monte-Carlo coherence significance (reference wavelet.py:531-647) with the surrogate
+    pairs block-partitioned over the ranks: every rank accumulates the [S, 1000]
+    int64 histograms of its pairs on its GPU, ONE all-reduce (sum, ~1 MB) combines them and
+    every rank evaluates the percentiles.  The result is independent of the world size."""
+    from . import wavelet as wv
+    mother = wv._check_parameter_wavelet(wavelet)
+    rank = 0 if dist is None else dist.get_rank()
+    world = 1 if dist is None else dist.get_world_size()
+    prob = wv._mc_problem(dt, dj, s0, J, mother)
+    lo, hi = shard_range(mc_count, rank, world)
+    hist = wv._mc_histogram(prob, dt, dj, mother,
+                            lambda i: surrogate_pair(seed, i, prob['N'], al1, al2),
+                            range(lo, hi), progress=False, engine=engine)
+    hist = sum_over_ranks(hist, dist, device)
+    return wv._mc_levels(prob, hist, significance_level)

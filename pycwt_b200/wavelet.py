@@ -299,6 +299,59 @@ def wct(y1, y2, dt, dj=1/12, s0=-1, J=-1, sig=True,
     return WCT, aWCT, coi, freq, sig
 
 
+def _mc_problem(dt, dj, s0, J, wavelet):
+    """Geometry of the Monte-Carlo coherence problem (reference wavelet.py:588-607): surrogate
+    length, scales, cone-of-influence mask, last valid scale and the sig95 template."""
+    ms = s0 * (2 ** (J * dj)) / dt
+    N = int(np.ceil(ms * 6))
+    sj = s0 * 2 ** (np.arange(0, J + 1) * dj)
+    freq = 1 / (wavelet.flambda() * sj)
+    coi = (N / 2 - np.abs(np.arange(0, N) - (N - 1) / 2))
+    coi = wavelet.flambda() * wavelet.coi() * dt * coi
+    period = np.ones([1, N]) / freq[:, None]
+    outsidecoi = (period <= (np.ones([J + 1, 1]) * coi[None, :]))
+    sig95 = np.zeros(J + 1)
+    maxscale = find(outsidecoi.any(axis=1))[-1]
+    sig95[outsidecoi.any(axis=1)] = np.nan
+    return dict(N=N, sj=sj, nbins=1000, maxscale=int(maxscale), sig95=sig95,
+                mask=np.ascontiguousarray(outsidecoi, dtype=np.uint8))
+
+
+def _mc_histogram(prob, dt, dj, wavelet, draw, indices, progress=False, engine=None):
+    """1000-bin histograms of the coherence of the surrogate pairs draw(i), i in `indices`
+    (reference wavelet.py:609-630), accumulated on the GPU: int64 [S, nbins]."""
+    N, sj, nbins = prob['N'], prob['sj'], prob['nbins']
+    hist = np.zeros((sj.size, nbins), dtype=np.int64)
+    eng = engine or _pair_engine(wavelet)
+    fam = _family_of(wavelet)
+    indices = list(indices)
+    batch = max(1, min(len(indices), int((256 << 20) // (16 * N)) or 1))
+    bar = tqdm(total=len(indices), disable=not progress)
+    for b0 in range(0, len(indices), batch):
+        idx = indices[b0:b0 + batch]
+        noise = np.empty((len(idx), 2, N))
+        for k, i in enumerate(idx):
+            noise[k, 0], noise[k, 1] = draw(i)
+        eng.wct_mc(noise, dt, dj, sj, fam[0], fam[1], _boxcar_len(wavelet, dj), prob['mask'],
+                   prob['maxscale'], nbins, hist)
+        bar.update(len(idx))
+    bar.close()
+    return hist
+
+
+def _mc_levels(prob, hist, significance_level):
+    """Percentile of every scale's histogram (reference wavelet.py:632-640)."""
+    nbins = prob['nbins']
+    sig95 = prob['sig95'].copy()
+    R2y = (np.arange(nbins) + 0.5) / nbins
+    for s in range(prob['maxscale']):
+        sel = hist[s] != 0
+        P = hist[s, sel].astype(float).cumsum()
+        P = (P - 0.5) / P[-1]
+        sig95[s] = np.interp(significance_level, P, R2y[sel])
+    return sig95
+
+
 def wct_significance(al1, al2, dt, dj, s0, J, significance_level=0.95,
                      wavelet='morlet', mc_count=300, progress=True,
                      cache=True):
@@ -325,46 +378,15 @@ def wct_significance(al1, al2, dt, dj, s0, J, significance_level=0.95,
             pass
     print('Calculating wavelet coherence significance')
 
-    ms = s0 * (2 ** (J * dj)) / dt
-    N = int(np.ceil(ms * 6))
+    prob = _mc_problem(dt, dj, s0, J, wavelet)
+    N = prob['N']
     rednoise(N, al1, 1)  # the reference's set-up draw (its transform only yields sj/freq/coi)
-    sj = s0 * 2 ** (np.arange(0, J + 1) * dj)
-    freq = 1 / (wavelet.flambda() * sj)
-    coi = (N / 2 - np.abs(np.arange(0, N) - (N - 1) / 2))
-    coi = wavelet.flambda() * wavelet.coi() * dt * coi
 
-    period = np.ones([1, N]) / freq[:, None]
-    outsidecoi = (period <= (np.ones([J + 1, 1]) * coi[None, :]))
-    sig95 = np.zeros(J + 1)
-    maxscale = find(outsidecoi.any(axis=1))[-1]
-    sig95[outsidecoi.any(axis=1)] = np.nan
+    def draw(i):
+        return rednoise(N, al1, 1), rednoise(N, al2, 1)
 
-    nbins = 1000
-    hist = np.zeros((J + 1, nbins), dtype=np.int64)
-    eng = _pair_engine(wavelet)
-    fam = _family_of(wavelet)
-    mask = np.ascontiguousarray(outsidecoi, dtype=np.uint8)
-    batch = max(1, min(mc_count, int((256 << 20) // (16 * N)) or 1))
-    done = 0
-    bar = tqdm(total=mc_count, disable=not progress)
-    while done < mc_count:
-        nb = min(batch, mc_count - done)
-        noise = np.empty((nb, 2, N))
-        for i in range(nb):
-            noise[i, 0] = rednoise(N, al1, 1)
-            noise[i, 1] = rednoise(N, al2, 1)
-        eng.wct_mc(noise, dt, dj, sj, fam[0], fam[1], _boxcar_len(wavelet, dj), mask,
-                   int(maxscale), nbins, hist)
-        done += nb
-        bar.update(nb)
-    bar.close()
-
-    R2y = (np.arange(nbins) + 0.5) / nbins
-    for s in range(maxscale):
-        sel = hist[s] != 0
-        P = hist[s, sel].astype(float).cumsum()
-        P = (P - 0.5) / P[-1]
-        sig95[s] = np.interp(significance_level, P, R2y[sel])
+    hist = _mc_histogram(prob, dt, dj, wavelet, draw, range(mc_count), progress)
+    sig95 = _mc_levels(prob, hist, significance_level)
 
     if cache:
         np.savetxt('{}/{}.gz'.format(cache_dir, cache_file), sig95)

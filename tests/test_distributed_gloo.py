@@ -67,3 +67,53 @@ def test_two_rank_gather_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res == [(0, True, 2.0), (1, True, 2.0)]
+
+
+def _mc_worker(rank, world, port, q):
+    """Each rank accumulates coherence histograms of its surrogate pairs with the host-emulation
+    build of the kernels (test infrastructure, no GPU here); one gloo all-reduce sums them."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from pycwt_b200 import distributed as D, _engine
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        eng = _engine.Engine(0, lib_path=os.path.join(ROOT, "tests", "_emu", "libcwtb200_emu.so"))
+        sig = D.wct_significance_sharded(0.2, 0.1, 1.0, 0.5, 2.0, 8, 0.95, 'morlet', mc_count=5,
+                                         seed=42, engine=eng, dist=dist)
+        q.put((rank, sig.tolist()))
+        eng.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_wct_significance_gloo():
+    """World size 2 gives bit-identical significance levels to one process running every pair."""
+    pytest.importorskip("torch")
+    import torch.multiprocessing as mp
+    from pycwt_b200 import build as _build, _engine, distributed as D
+    lib = _build.build_emulation(os.path.join(ROOT, "tests", "_emu"))
+    eng = _engine.Engine(0, lib_path=lib)
+    single = D.wct_significance_sharded(0.2, 0.1, 1.0, 0.5, 2.0, 8, 0.95, 'morlet', mc_count=5,
+                                        seed=42, engine=eng)
+    eng.close()
+    assert np.isnan(single).any() and np.isfinite(single).any()
+    fin = single[np.isfinite(single)]
+    assert ((fin > 0) & (fin < 1)).all()
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_mc_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in (0, 1):
+        assert np.array_equal(np.array(res[r]), single, equal_nan=True)

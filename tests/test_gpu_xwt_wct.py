@@ -200,3 +200,31 @@ def test_cwt_batch_fp64_two_kernel_sizes_and_device_variant(pycwt):
     assert relerr(p2, power) < 1e-13
     W2 = eng.get_w(nch * len(sj), n0).reshape(nch, len(sj), n0)
     assert np.array_equal(W2, W)
+
+
+def test_sharded_wct_significance_matches_oracle(pycwt):
+    """The sharded Monte-Carlo driver (here with one rank) fed to the oracle draw for
+    draw: identical significance levels, and identical to the sum of two disjoint shards."""
+    from pycwt_b200 import distributed as D
+    args = (0.2, 0.1, 1.0, 0.5, 2.0, 10)
+    sig = D.wct_significance_sharded(*args, significance_level=0.95, wavelet='morlet', mc_count=6, seed=5)
+
+    class Replay(object):
+        """rng stand-in: hands the oracle the same white-noise columns, in its call order"""
+        def __init__(self, N):
+            tau = lambda al: int(np.ceil(-2 / np.log(abs(al))))
+            self.q = [np.zeros(N + tau(0.2))]          # the reference's discarded set-up draw
+            for i in range(6):
+                rs = np.random.RandomState([5, i])
+                self.q += [rs.randn(N + tau(0.2)), rs.randn(N + tau(0.1))]
+
+        def randn(self, n, one):
+            a = self.q.pop(0)
+            assert a.size == n and one == 1
+            return a.reshape(n, 1)
+
+    N = int(np.ceil(2.0 * 2 ** (10 * 0.5) / 1.0 * 6))
+    ref = orc.wct_significance(*args, significance_level=0.95, wavelet="morlet", mc_count=6, rng=Replay(N))
+    assert np.array_equal(np.isnan(sig), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    assert np.abs(sig[ok] - ref[ok]).max() < 1e-12
