@@ -28,6 +28,24 @@ for name, fam, par, s0, dj in (("paul4", 1, 4.0, 1.4324, 1 / 18), ("dog2", 2, 2.
     ms = kernel_time(x32, sj, fam, par, 1, 1)
     print("config3 %s fp32 N=2^18 S=128: %.3f ms kernels -> %.3e scale-points/s, %.0f GB/s algorithmic"
           % (name, ms, 128 * n / ms * 1e3, 128 * n * 8 / ms / 1e6))
+# config 3 end to end through the reference API (float32 host input, complex128 host result)
+os.environ["CWTB_PRECISION"] = "fp32"
+for name, mother, kw in (("paul4", pycwt.Paul(4), dict(s0=1.4324, dj=1 / 18, J=127)),
+                         ("dog2", pycwt.DOG(2), dict(s0=0.5033, dj=1 / 8, J=127))):
+    for _ in range(3):
+        t0 = time.perf_counter(); W = pycwt.cwt(x32, 1.0, wavelet=mother, **kw)[0]; t_e = time.perf_counter() - t0
+    print("config3 %s e2e pycwt.cwt (fp32 engine, complex128 out, %d MB D2H): %.1f ms -> %.3e scale-points/s"
+          % (name, W.nbytes >> 20, 1e3 * t_e, W.size / t_e))
+del os.environ["CWTB_PRECISION"]
+# device-resident products of config 2: nothing of size S x N crosses PCIe
+N2 = 2 ** 20
+x2 = chirp(N2)
+for _ in range(3):
+    t0 = time.perf_counter()
+    r = pycwt.cwt_resident(x2, 1.0, 1 / 16, 2.0, 255, pycwt.Morlet(6))
+    g = r.global_power(); sa = r.scale_avg_power(16.0, 64.0); iw = r.icwt()
+    t_r = time.perf_counter() - t0
+print("config2 resident: cwt + global power + scale-averaged power + icwt, host in / O(S+N) out: %.1f ms" % (1e3 * t_r))
 # config 4: xwt + wct of two N=2^18 series, 145 scales, fp64 (deterministic part) + MC rate
 rs = np.random.RandomState(0)
 y1 = chirp(n) + 0.5 * rs.randn(n)

@@ -243,10 +243,16 @@ template <class Body>
 static int launch(cwtb_ctx *c, unsigned gx, unsigned gy, const typename Body::Args &a) {
   if (gx == 0 || gy == 0) return 0;
 #ifdef CWTB_HOST_EMU
-  std::vector<unsigned char> sm(Body::SMEM + 64);
+  std::vector<unsigned char> smv(Body::SMEM + 64);
+  unsigned char *sm = smv.data();
+  sm += (16 - ((unsigned long long)sm & 15)) & 15;   // 16-byte aligned base, like the device's
   for (unsigned by = 0; by < gy; ++by)
-    for (unsigned bx = 0; bx < gx; ++bx) emu_phases<Body, 0>(a, (int)bx, (int)by, sm.data());
+    for (unsigned bx = 0; bx < gx; ++bx) emu_phases<Body, 0>(a, (int)bx, (int)by, sm);
   c->launches++;
+  if (emu_bulk_copy_faults() != 0) {
+    emu_bulk_copy_faults() = 0;
+    return fail(c, CWTB_ERR_CUDA, "emulation: bulk-async copy with a misaligned address or size");
+  }
   return 0;
 #else
   const void *fn = (const void *)k_run<Body>;
@@ -936,7 +942,9 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
       a.fam = fam; a.nt = nt; a.N = N; a.first = cl.first + g0; a.row0 = 0; a.zmod = 1 << 30;
       // band scales: second pass of 512 points (full 128-byte output runs, conflict-free tile);
       // dense scales keep 1024 so that K1 = N/K2 <= 1024
-      const int l2k = (dense || c->fused || cl.log2K > 19) ? 10 : c->k2_band_log2;
+      // (fp32: the 512-point tile has an odd row pitch, its rows would not be 16-byte aligned)
+      constexpr bool k512_ok = (Lay<T, 512, true>::PITCH * sizeof(V)) % 16 == 0;
+      const int l2k = (dense || c->fused || cl.log2K > 19 || !k512_ok) ? 10 : c->k2_band_log2;
       a.pf_dist = c->pf_dist_a; a.K2 = 1u << l2k; a.gauss_rec = c->gauss_rec;
       PassBArgs<T> b{};
       b.Z = (const V *)Zb.p; b.out = W; b.tw = Tw<T>::get(c); b.descs = ddesc;
@@ -957,9 +965,11 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
       e = dense ? dispatch_passA<T, +1, MODE_DENSE>(c, cl.log2K - l2k, a, ng)
                 : dispatch_passA<T, +1, MODE_BAND>(c, cl.log2K - l2k, a, ng);
       if (e) return e;
-      if (l2k == 9)
-        e = launch<PassBBody<T, +1, 512>>(c, (N / 512 + Lay<T, 512>::P - 1) / Lay<T, 512>::P, ng, b);
-      else
+      if constexpr (k512_ok) {
+        if (l2k == 9)
+          e = launch<PassBBody<T, +1, 512>>(c, (N / 512 + Lay<T, 512>::P - 1) / Lay<T, 512>::P, ng, b);
+      }
+      if (l2k != 9)
         e = launch<PassBBody<T, +1>>(c, (N / K2C + Lay<T, K2C>::P - 1) / Lay<T, K2C>::P, ng, b);
       if (e) return e;
     }

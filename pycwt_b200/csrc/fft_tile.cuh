@@ -137,6 +137,13 @@ HD void warp_sync() {
 #endif
 }
 
+#ifdef CWTB_HOST_EMU
+inline long long &emu_bulk_copy_faults() {   // misaligned bulk copies seen by the emulation
+  static long long n = 0;
+  return n;
+}
+#endif
+
 struct TileBarrier {
   unsigned long long *bar;  // 8-byte slot in shared memory
   HD void init_and_expect(unsigned bytes) const {
@@ -157,6 +164,11 @@ struct TileBarrier {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(d), "l"(src), "r"(bytes), "r"(a) : "memory");
 #else
+    // the hardware requirement, checked where no GPU is present: the emulation's shared
+    // memory base is 16-byte aligned, so offsets are what is being tested
+#ifdef CWTB_HOST_EMU
+    if ((((unsigned long long)dst | (unsigned long long)src | bytes) & 15ull) != 0) ++emu_bulk_copy_faults();
+#endif
     const char *s_ = (const char *)src;
     char *d_ = (char *)dst;
     for (unsigned i = 0; i < bytes; ++i) d_[i] = s_[i];

@@ -373,7 +373,10 @@ template <typename T, int SIGN, int K2 = K2C> struct PassBBody {
   // Z[u0 .. u0+P) are contiguous in global memory -- then the FFT passes run from shared memory
   static constexpr int NPHASE = NP + 1;
   static constexpr size_t SMEM = LY::TILE_BYTES + 16;
+  // bulk-async copies need 16-byte aligned shared-memory destinations: every row start
+  static constexpr bool ROWS_ALIGNED = (LY::PITCH * sizeof(V)) % 16 == 0;
   template <int PH> HD static void phase(const Args &a, int bx, int by, int tid, void *smraw) {
+    static_assert(ROWS_ALIGNED, "PassB: tile rows must start on 16-byte boundaries");
     V *sm = (V *)smraw;
     const int U = (int)(a.N / K);
     const int u0 = bx * LY::P;
