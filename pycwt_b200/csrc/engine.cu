@@ -143,6 +143,8 @@ struct cwtb_ctx {
   int pf_dist = 148;   // PassB: L2 prefetch distance in tiles (CWTB_PF_DIST)
   int gauss_rec = 1;   // dense Morlet scales: Gaussian by recurrence (CWTB_GAUSS_REC=0: exp per bin)
   int pf_dist_a = 148;  // PassA (band): L2 prefetch distance in tiles (CWTB_PF_DIST_A)
+  int k2_512_max_log2 = 16;  // largest K' that uses the 512-point second pass (CWTB_K2_512_MAX)
+  int passb_rev = 1;    // second kernel walks the rows of a launch last-to-first (CWTB_PASSB_REV)
   int k2_band_log2 = 9; // second-pass length of the pruned two-kernel scales: 2^9 or 2^10 (CWTB_K2_BAND)
   size_t batch_bytes = (size_t)4 << 30;   // coefficients per chunk of cwtb_cwt_batch  // K' <= 2^13 handled by one kernel (K' > 1024: DirectBody)
   double2 *tw64 = nullptr;
@@ -562,7 +564,7 @@ static int two_kernel_rows(cwtb_ctx *c, const void *in, int real_in, long long i
     b.Z = (const cx<T> *)c->Z.p; b.out = out; b.tw = Tw<T>::get(c); b.descs = descs;
     b.pitch = out_pitch; b.nout = nout; b.N = n; b.first = first;
     b.epi = grow ? EPI_GAUSS : epi; b.grow = grow; b.post = post; b.zmod = 1 << 30;
-    b.pf_dist = 0; b.ny = nr; b.ileave = ileave;
+    b.pf_dist = 0; b.ny = nr; b.ileave = ileave; b.rev = c->passb_rev;
     if (ileave > 1) { b.row0 = out_row0; b.by0 = r0; } else { b.row0 = out_row0 + r0; b.by0 = 0; }
     e = launch<PassBBody<T, SIGN>>(c, (n / K2C + Lay<T, K2C>::P - 1) / Lay<T, K2C>::P, nr, b);
     if (e) return e;
@@ -944,13 +946,14 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
       // dense scales keep 1024 so that K1 = N/K2 <= 1024
       // (fp32: the 512-point tile has an odd row pitch, its rows would not be 16-byte aligned)
       constexpr bool k512_ok = (Lay<T, 512, true>::PITCH * sizeof(V)) % 16 == 0;
-      const int l2k = (dense || c->fused || cl.log2K > 19 || !k512_ok) ? 10 : c->k2_band_log2;
+      // 512 pays up to K' = 2^16 (measured per class: first kernel + second kernel per row)
+      const int l2k = (dense || c->fused || cl.log2K > c->k2_512_max_log2 || !k512_ok) ? 10 : c->k2_band_log2;
       a.pf_dist = c->pf_dist_a; a.K2 = 1u << l2k; a.gauss_rec = c->gauss_rec;
       PassBArgs<T> b{};
       b.Z = (const V *)Zb.p; b.out = W; b.tw = Tw<T>::get(c); b.descs = ddesc;
       b.pitch = job.n0; b.nout = job.n0; b.N = N; b.first = cl.first + g0; b.row0 = 0;
       b.epi = epi; b.grow = nullptr; b.post = 1.0; b.zmod = 1 << 30;
-      b.pf_dist = c->pf_dist; b.ny = ng;
+      b.pf_dist = c->pf_dist; b.ny = ng; b.rev = c->passb_rev;
       if (!dense) {
         BandArgs<T> ba{ddesc, spec, Bbuf, fam, N, cl.first + g0};
         if ((e = launch<BandBody<T>>(c, (K + NT * BandBody<T>::PER - 1) / (NT * BandBody<T>::PER), ng, ba)))
@@ -1096,6 +1099,8 @@ int cwtb_create(int device, cwtb_ctx **out) {
   if (const char *g = getenv("CWTB_PF_DIST")) c->pf_dist = std::max(0, atoi(g));
   if (const char *g = getenv("CWTB_PF_DIST_A")) c->pf_dist_a = std::max(0, atoi(g));
   if (const char *g = getenv("CWTB_K2_BAND")) c->k2_band_log2 = atoi(g) == 10 ? 10 : 9;
+  if (const char *g = getenv("CWTB_K2_512_MAX")) c->k2_512_max_log2 = std::min(19, atoi(g));
+  if (const char *g = getenv("CWTB_PASSB_REV")) c->passb_rev = atoi(g) != 0;
   if (const char *g = getenv("CWTB_GAUSS_REC")) c->gauss_rec = atoi(g);
   if (const char *g = getenv("CWTB_BATCH_MB")) c->batch_bytes = (size_t)std::max(1, atoi(g)) << 20;
   if (const char *g = getenv("CWTB_RING")) c->ring = std::max(1, atoi(g));

@@ -356,6 +356,8 @@ template <typename T> struct PassBArgs {
   int by0;                 // global index of this launch's first Z row (interleave bookkeeping)
   int ileave;              // > 1: Z row `by` is sub-transform by % ileave of output row by / ileave
                            // (final index n*ileave + by % ileave): three-level path, Np > 2^20
+  int rev;                 // rows are processed last-to-first: the first kernel wrote the last rows
+                           // of Z most recently, they are the ones still resident in L2
 };
 
 // K2 = 1024 leaves P = TILE/K2 = Q/2 transforms per tile (64-byte output runs, 2-way bank
@@ -377,6 +379,8 @@ template <typename T, int SIGN, int K2 = K2C> struct PassBBody {
   static constexpr bool ROWS_ALIGNED = (LY::PITCH * sizeof(V)) % 16 == 0;
   template <int PH> HD static void phase(const Args &a, int bx, int by, int tid, void *smraw) {
     static_assert(ROWS_ALIGNED, "PassB: tile rows must start on 16-byte boundaries");
+    const int ey = by;                   // position in execution order
+    if (a.rev) by = a.ny - 1 - ey;
     V *sm = (V *)smraw;
     const int U = (int)(a.N / K);
     const int u0 = bx * LY::P;
@@ -403,9 +407,10 @@ template <typename T, int SIGN, int K2 = K2C> struct PassBBody {
         // or the next row when this one is exhausted): its TMA copies then hit L2
         if (tid == 0 && a.pf_dist > 0) {
           long long t = (long long)bx + a.pf_dist;
-          int py = by;
+          int pe = ey;
           const int tiles = (U + LY::P - 1) / LY::P;
-          while (t >= tiles && py + 1 < a.ny) { t -= tiles; ++py; }
+          while (t >= tiles && pe + 1 < a.ny) { t -= tiles; ++pe; }
+          const int py = a.rev ? a.ny - 1 - pe : pe;
           if (t < tiles && t * LY::P + LY::P <= U)
             TileBarrier::prefetch_l2(a.Z + (size_t)(py % a.zmod) * a.N + (size_t)t * LY::P * K,
                                      (unsigned)(LY::P * K * sizeof(V)));
@@ -932,7 +937,10 @@ template <typename T> struct PowerBody {
     }
     if (a.rowsum) {
 #if defined(__CUDA_ARCH__) && !defined(CWTB_HOST_EMU)
-      atomicAdd(&a.rowsum[by], acc);
+      // one atomic per warp (every lane reaches this point: no early return above)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+      if ((tid & 31) == 0) atomicAdd(&a.rowsum[by], acc);
 #else
       a.rowsum[by] += acc;
 #endif

@@ -36,11 +36,25 @@ class ResidentTransform(object):
         self.freqs = freqs
         self.precision = precision
         self._serial = serial
-        npad = fft_kwargs(np.empty(self.n0))['n']
-        self.npad = npad
-        coi = (n0 / 2 - np.abs(np.arange(0, n0) - (n0 - 1) / 2))
-        self.coi = wavelet.flambda() * wavelet.coi() * dt * coi      # wavelet.py:118-120
-        self.fftfreqs = (2 * np.pi * fft.fftfreq(npad, dt))[1:npad // 2] / (2 * np.pi)
+        self.npad = int(2 ** np.ceil(np.log2(self.n0)))   # padding policy of helpers.py:27-30
+        self._coi = None
+        self._fftfreqs = None
+
+    # O(n0) host arrays of the `cwt` return tuple, built on first use
+    @property
+    def coi(self):
+        if self._coi is None:
+            n0 = self.n0
+            coi = (n0 / 2 - np.abs(np.arange(0, n0) - (n0 - 1) / 2))
+            self._coi = self.wavelet.flambda() * self.wavelet.coi() * self.dt * coi   # wavelet.py:118-120
+        return self._coi
+
+    @property
+    def fftfreqs(self):
+        if self._fftfreqs is None:
+            npad = self.npad
+            self._fftfreqs = (2 * np.pi * fft.fftfreq(npad, self.dt))[1:npad // 2] / (2 * np.pi)
+        return self._fftfreqs
 
     # -- bookkeeping ---------------------------------------------------------------------
     def _check_live(self):

@@ -50,7 +50,11 @@ def _nan_rows(wavelet, sj, npad, dt):
     """Rows the reference would find all-NaN (wavelet.py:111): psi_ft evaluates to NaN at
     some bin (Paul: inf*0 once s*pi/dt > 709.78).  Evaluated at the two extreme bins, where
     overflow happens first; O(S) host work."""
-    edge = 2 * np.pi * fft.fftfreq(npad, dt)[[npad // 2, max(npad // 2 - 1, 0)]]
+    # the two entries of fft.fftfreq(npad, dt) at those bins (k / (npad*dt) with the signed bin
+    # number k, computed like numpy does: k * (1.0 / (npad * dt))) without building the array
+    idx = np.array([npad // 2, max(npad // 2 - 1, 0)])
+    k = np.where(idx < (npad + 1) // 2, idx, idx - npad)
+    edge = 2 * np.pi * (k * (1.0 / (npad * dt)))
     with np.errstate(all='ignore'):
         resp = wavelet.psi_ft(sj[:, None] * edge[None, :])
     return np.isnan(resp).any(axis=1)
