@@ -62,6 +62,12 @@ const char *cwtb_version(void);
  * rounding of the transform itself).  eps = 0 keeps every bin whose response
  * is representable (the reference's own underflow-to-zero set). */
 int cwtb_set_band_eps(cwtb_ctx *ctx, double eps);
+/* Transform-length policy of pycwt/helpers.py:7-30.  pad_to_pow2 != 0 (default): the signal is
+ * zero-padded to the next power of two (the reference's scipy branch, :27-30).  0: transforms
+ * run at the signal's own length (what the reference does when pyfftw is installed, :15-19) --
+ * Bluestein's algorithm on the power-of-two kernels, fp64 only, cwt / icwt / xwt only, n0 <= 2^24;
+ * power-of-two lengths are unaffected. */
+int cwtb_set_padding(cwtb_ctx *ctx, int pad_to_pow2);
 
 /* Pinned host memory (so D2H of multi-GiB results runs at PCIe speed and can
  * overlap with compute).  numpy wraps the returned pointer. */
@@ -216,8 +222,9 @@ int cwtb_memcpy_h2d(cwtb_ctx *ctx, void *dst, const void *src, size_t bytes);
 int cwtb_memcpy_d2h(cwtb_ctx *ctx, void *dst, const void *src, size_t bytes);
 int cwtb_sync(cwtb_ctx *ctx);
 
-/* Test hook: plain batched complex FFT of `batch` rows of length n (power of two)
- * through the engine's own kernels; sign = -1 forward, +1 inverse (unnormalised).
+/* Test hook: plain batched complex DFT of `batch` rows of length n through the engine's own
+ * kernels (any n >= 2; lengths other than 2^k go through Bluestein's algorithm, fp64 only);
+ * sign = -1 forward, +1 inverse (unnormalised).
  * in/out: host complex128 (precision selects the arithmetic). */
 int cwtb_fft_c2c(cwtb_ctx *ctx, const void *in, void *out, int64_t n, int batch,
                  int sign, int precision);

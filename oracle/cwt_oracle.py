@@ -39,6 +39,16 @@ def next_pow2(n):
     return int(2 ** np.ceil(np.log2(n)))
 
 
+# Transform-length policy, pycwt/helpers.py:7-30.  True: the scipy branch (zero-pad to the next
+# power of two, :27-30) -- the behaviour of the reference in this image.  False: the policy of
+# the pyfftw branch (:15-19, `kwargs['n'] = len(signal)  # do not pad`).
+PAD_NEXT_POW2 = True
+
+
+def transform_length(n):
+    return next_pow2(n) if PAD_NEXT_POW2 else int(n)
+
+
 # --------------------------------------------------------------------------
 # Mother wavelets (pycwt/mothers.py)
 # --------------------------------------------------------------------------
@@ -163,7 +173,7 @@ def cwt(signal, dt, dj=1 / 12, s0=-1, J=-1, wavelet="morlet", freqs=None,
     else:  # wavelet.py:86-88
         sj = 1 / (lam * freqs)
 
-    npad = next_pow2(n0)  # helpers.py:27-30
+    npad = transform_length(n0)  # helpers.py:15-19 / 27-30
     spec = _sfft.fft(np.asarray(signal), n=npad)  # wavelet.py:91
     omega = 2 * np.pi * _sfft.fftfreq(npad, dt)  # wavelet.py:94
     col = sj[:, None]
@@ -258,7 +268,7 @@ def rect(k, normalize=False):
 # --------------------------------------------------------------------------
 def smooth(W, dt, dj, scales, deltaj0=0.60):
     m, n = W.shape
-    npad = next_pow2(n)
+    npad = transform_length(n)
     k2 = (2 * np.pi * _sfft.fftfreq(npad)) ** 2  # mothers.py:83-84
     snorm = scales / dt
     F = np.exp(-0.5 * (snorm[:, None] ** 2) * k2)  # mothers.py:89

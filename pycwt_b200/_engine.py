@@ -30,6 +30,7 @@ _SIGNATURES = {
     "cwtb_last_error": (ctypes.c_char_p, [_P]),
     "cwtb_version": (ctypes.c_char_p, []),
     "cwtb_set_band_eps": (_I, [_P, _D]),
+    "cwtb_set_padding": (_I, [_P, _I]),
     "cwtb_host_alloc": (_I, [_P, ctypes.c_size_t, ctypes.POINTER(_P)]),
     "cwtb_host_free": (_I, [_P, _P]),
     "cwtb_cwt": (_I, [_P, _P, _I, _I64, _D, _P, _I, _I, _D, _I, _P]),
@@ -124,6 +125,12 @@ class Engine(object):
 
     def set_band_eps(self, eps):
         self._check(self.lib.cwtb_set_band_eps(self.h, float(eps)))
+
+    def set_padding(self, pad_to_pow2):
+        """True (default): pad to the next power of two like the reference's scipy branch;
+        False: transform at the signal's own length (the reference's pyfftw policy)."""
+        self._check(self.lib.cwtb_set_padding(self.h, 1 if pad_to_pow2 else 0))
+        self._pad_pow2 = bool(pad_to_pow2)
 
     # ---- pinned host arrays -------------------------------------------------------
     def pinned_empty(self, shape, dtype):

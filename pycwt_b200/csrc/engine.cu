@@ -113,6 +113,13 @@ struct Job {
   std::vector<double> scales;     // per input scale (= output row)
   size_t b_single = 0;            // elements of the band buffer used by single-kernel scales
   int sig_is_f32 = 0;
+  bool exact = false;             // un-padded mode: N = n0 (not a power of two), Bluestein transforms
+};
+
+struct BluePlan {   // chirp tables of one transform length (device memory, owned by the context)
+  unsigned n = 0, L = 0;
+  double2 *wm = nullptr;                 // e^{-i pi k^2 / n}, k < n
+  double2 *bf[2] = {nullptr, nullptr};   // FFT_L of the chirp filter for sign -1 / +1
 };
 
 struct NTabDev {
@@ -126,6 +133,10 @@ struct cwtb_ctx {
   rt_stream aux_stream{};        // single-kernel classes run here, concurrently with the two-kernel chains
   rt_stream chain2_stream{};     // every second two-kernel class runs here (own Z and band chunk)
   rt_stream cur{};               // stream the launcher uses right now
+  int pad_pow2 = 1;              // 1: transform length = next power of two (reference default,
+                                 // helpers.py:27-30); 0: the signal's own length (pyfftw policy,
+                                 // helpers.py:15-19) -- cwtb_set_padding
+  std::map<unsigned, BluePlan> blue;
   long long serial = 0;          // counts transforms: identifies what is resident (cwtb_job_serial)
   int two_streams = 1;           // CWTB_STREAMS=1 disables the overlap
   int three_streams = 1;         // CWTB_STREAMS=2: single-kernel classes only
@@ -150,7 +161,7 @@ struct cwtb_ctx {
   double2 *tw64 = nullptr;
   float2 *tw32 = nullptr;
   std::map<unsigned, NTabDev> ntabs;
-  Buf ctr, sig, sig2, spec, Z, Z2, Y, B, W, W2, descs, table, scratch, C, A12, F, aux, rowd, win, mask, hist, noise, wide;
+  Buf ctr, sig, sig2, spec, Z, Z2, Y, B, W, W2, descs, table, scratch, C, A12, F, aux, rowd, win, mask, hist, noise, wide, blueA, blueX, blueY;
   Job job;
   const void *job_dsig = nullptr;  // device signal of the last cwt_dev call (not owned)
   double last_ms = 0;
@@ -380,6 +391,15 @@ static int build_job(cwtb_ctx *c, Job &job, long long n0, double dt, const doubl
   job.n0 = n0;
   job.log2N = ilog2((unsigned long long)n0);   // pycwt/helpers.py:27-30
   job.N = 1u << job.log2N;
+  if (!c->pad_pow2 && (n0 & (n0 - 1)) != 0) {
+    // un-padded mode (helpers.py:15-19): transform length = n0; a power-of-two n0 is the
+    // padded case anyway
+    if (precision != CWTB_F64) return fail(c, CWTB_ERR_UNSUPPORTED, "un-padded transforms run in fp64");
+    if (nbatch != 1) return fail(c, CWTB_ERR_UNSUPPORTED, "batched transforms need the padded mode");
+    if (n0 > (1ll << 24)) return fail(c, CWTB_ERR_UNSUPPORTED, "un-padded transform longer than 2^24");
+    job.exact = true;
+    job.N = (unsigned)n0;
+  }
   job.S = S;
   job.nbatch = nbatch;
   job.dt = dt;
@@ -428,7 +448,7 @@ static int build_job(cwtb_ctx *c, Job &job, long long n0, double dt, const doubl
     d.boff = 0;
     const double norm = std::sqrt(s * w1 * (double)N);  // wavelet.py:103
     d.amp = (family == CWTB_TABLE ? 1.0 : norm * fconst) / (double)N;
-    long long klo = -half, khi = half - 1;
+    long long klo = -half, khi = ((long long)N - 1) / 2;   // numpy fftfreq's signed bins, any N
     if (family != CWTB_TABLE && s > 0 && std::isfinite(s)) {
       const double cc = (double)N * dt / (6.283185307179586 * s);
       double a = std::ceil(flo * cc) - 1, b = std::floor(fhi * cc) + 1;
@@ -457,7 +477,7 @@ static int build_job(cwtb_ctx *c, Job &job, long long n0, double dt, const doubl
       d.rsplit = (int)((1ll << lk) + lo);  // lo <= 0
     }
     d.log2K = lk;
-    job.plan_log2K[j] = (N < 32) ? 0 : lk;
+    job.plan_log2K[j] = job.exact ? -1 : ((N < 32) ? 0 : lk);
   }
   // one descriptor per (channel, scale) row; rows of channel ch are ch*S .. ch*S+S-1
   if (nbatch > 1) {
@@ -621,6 +641,115 @@ static int fft_rows(cwtb_ctx *c, const void *in, int real_in, long long in_pitch
     if ((e = two_kernel_rows<T, SIGN>(c, c->Y.p, 0, Nsub, Nsub, out, out_pitch, Nsub, nr * (int)K0, nout, grow, post,
                                       (int)K0, nullptr, 0, r0, EPI_STORE)))
       return e;
+  }
+  return 0;
+}
+
+
+// ======================================================================================
+// un-padded mode (pycwt/helpers.py:15-19, the reference's pyfftw branch): transforms at the
+// signal's own length n through Bluestein's chirp-z algorithm on the power-of-two kernels.
+// A compatibility path: ~2 transforms of length >= 2n per scale and no band pruning.
+// ======================================================================================
+static int get_blue(cwtb_ctx *c, unsigned n, const BluePlan **out) {
+  auto it = c->blue.find(n);
+  if (it == c->blue.end()) {
+    // keep at most a few lengths resident
+    if (c->blue.size() >= 4) {
+      for (auto &kv : c->blue) { rt_free(kv.second.wm); rt_free(kv.second.bf[0]); rt_free(kv.second.bf[1]); }
+      c->blue.clear();
+    }
+    BluePlan pl;
+    pl.n = n;
+    pl.L = 1u << ilog2(2ull * n - 1);
+    RT(rt_malloc((void **)&pl.wm, sizeof(double2) * n));
+    BlueChirpArgs ca{pl.wm, n};
+    int e = launch<BlueChirpBody>(c, (n + NT - 1) / NT, 1, ca);
+    if (e) return e;
+    if ((e = ensure(c, c->blueX, (size_t)pl.L * sizeof(double2)))) return e;
+    for (int si = 0; si < 2; ++si) {
+      RT(rt_malloc((void **)&pl.bf[si], sizeof(double2) * pl.L));
+      BlueFilterArgs fa{pl.wm, (double2 *)c->blueX.p, n, pl.L, si ? +1 : -1};
+      if ((e = launch<BlueFilterBody>(c, (pl.L + NT - 1) / NT, 1, fa))) return e;
+      if ((e = fft_rows<double, -1>(c, c->blueX.p, 0, pl.L, pl.L, pl.bf[si], pl.L, pl.L, 1, -1, nullptr, 1.0))) return e;
+    }
+    it = c->blue.emplace(n, pl).first;
+  }
+  *out = &it->second;
+  return 0;
+}
+
+// rows of the convolution buffers a chunk may use (two buffers of L complex per row)
+static int blue_chunk_rows(unsigned L, int nrows) {
+  const size_t per_row = (size_t)L * sizeof(double2);
+  return (int)std::max<size_t>(1, std::min<size_t>((size_t)nrows, ((size_t)1 << 30) / per_row));
+}
+
+// convolution core: blueA rows (pitch n) already hold a = x * w_s; result rows y in blueY
+static int blue_convolve(cwtb_ctx *c, const BluePlan &pl, int nr, int sign) {
+  int e;
+  if ((e = fft_rows<double, -1>(c, c->blueA.p, 0, pl.n, pl.n, (double2 *)c->blueX.p, pl.L, pl.L, nr, -1, nullptr, 1.0)))
+    return e;
+  BlueMulArgs ma{(double2 *)c->blueX.p, pl.bf[sign > 0 ? 1 : 0], pl.L};
+  if ((e = launch<BlueMulBody>(c, (pl.L + NT - 1) / NT, nr, ma))) return e;
+  return fft_rows<double, +1>(c, c->blueX.p, 0, pl.L, pl.L, (double2 *)c->blueY.p, pl.L, pl.L, nr, -1, nullptr, 1.0);
+}
+
+// out[r][k] = scale * sum_j in[r][j] e^{sign 2 pi i jk/n}, k < nout, for rows of any length n >= 2
+static int blue_rows(cwtb_ctx *c, const void *in, int real_in, long long in_pitch, double2 *out,
+                     long long out_pitch, unsigned n, int nrows, int sign, double scale, long long nout) {
+  const BluePlan *pl;
+  int e = get_blue(c, n, &pl);
+  if (e) return e;
+  const int chunk = blue_chunk_rows(pl->L, nrows);
+  if ((e = ensure(c, c->blueA, (size_t)chunk * n * sizeof(double2)))) return e;
+  if ((e = ensure(c, c->blueX, (size_t)chunk * pl->L * sizeof(double2)))) return e;
+  if ((e = ensure(c, c->blueY, (size_t)chunk * pl->L * sizeof(double2)))) return e;
+  const size_t isz = real_in ? sizeof(double) : sizeof(double2);
+  for (int r0 = 0; r0 < nrows; r0 += chunk) {
+    const int nr = std::min(chunk, nrows - r0);
+    BluePreArgs pa{(const char *)in + (size_t)r0 * in_pitch * isz, (double2 *)c->blueA.p, pl->wm,
+                   in_pitch, (long long)n, n, real_in, sign};
+    if ((e = launch<BluePreBody>(c, (n + NT - 1) / NT, nr, pa))) return e;
+    if ((e = blue_convolve(c, *pl, nr, sign))) return e;
+    BluePostArgs po{(const double2 *)c->blueY.p, out, pl->wm, nullptr, out_pitch, nout,
+                    scale / (double)pl->L, pl->L, 0, r0, sign, EPI_STORE};
+    if ((e = launch<BluePostBody>(c, (unsigned)((nout + NT - 1) / NT), nr, po))) return e;
+  }
+  return 0;
+}
+
+// every kernel of one un-padded transform (fp64): spectrum at length n0, then for chunks of scales
+// product + inverse transform at length n0
+static int run_job_exact(cwtb_ctx *c, const Job &job, const double *dsig, double2 *Wout, int epi) {
+  const unsigned n = job.N;
+  const int S = job.S;
+  int e;
+  if (job.nbatch != 1) return fail(c, CWTB_ERR_UNSUPPORTED, "batched transforms need the padded mode");
+  if ((e = ensure(c, c->spec, (size_t)n * sizeof(double2)))) return e;
+  if (!Wout) {
+    if ((e = ensure(c, c->W, (size_t)S * job.n0 * sizeof(double2)))) return e;
+    Wout = (double2 *)c->W.p;
+  }
+  if ((e = blue_rows(c, dsig, 1, n, (double2 *)c->spec.p, n, n, 1, -1, 1.0, n))) return e;
+  const BluePlan *pl;
+  if ((e = get_blue(c, n, &pl))) return e;
+  Fam fam = job.fam;
+  if (fam.family == CWTB_TABLE) fam.table = (const double2 *)c->table.p;
+  const int chunk = blue_chunk_rows(pl->L, S);
+  if ((e = ensure(c, c->blueA, (size_t)chunk * n * sizeof(double2)))) return e;
+  if ((e = ensure(c, c->blueX, (size_t)chunk * pl->L * sizeof(double2)))) return e;
+  if ((e = ensure(c, c->blueY, (size_t)chunk * pl->L * sizeof(double2)))) return e;
+  const ScaleDesc *ddesc = (const ScaleDesc *)c->descs.p;
+  for (int r0 = 0; r0 < S; r0 += chunk) {
+    const int nr = std::min(chunk, S - r0);
+    BlueProdArgs pa{ddesc, (const double2 *)c->spec.p, (double2 *)c->blueA.p, pl->wm, fam, (long long)n, n, r0};
+    if ((e = launch<BlueProdBody>(c, (n + NT - 1) / NT, nr, pa))) return e;
+    if ((e = blue_convolve(c, *pl, nr, +1))) return e;
+    // descriptor amplitudes already carry the 1/n of the inverse transform
+    BluePostArgs po{(const double2 *)c->blueY.p, Wout, pl->wm, ddesc, job.n0, job.n0,
+                    1.0 / (double)pl->L, pl->L, r0, 0, +1, epi};
+    if ((e = launch<BluePostBody>(c, (unsigned)((job.n0 + NT - 1) / NT), nr, po))) return e;
   }
   return 0;
 }
@@ -817,6 +946,10 @@ static size_t band_chunk_elems(const cwtb_ctx *c, const Job &job, int G) {
 template <typename T>
 static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nullptr, int epi = EPI_STORE) {
   using V = cx<T>;
+  if (job.exact) {
+    if constexpr (std::is_same<T, double>::value) return run_job_exact(c, job, dsig, Wout, epi);
+    else return fail(c, CWTB_ERR_UNSUPPORTED, "un-padded transforms run in fp64");
+  }
   const unsigned N = job.N;
   const int S = job.S * job.nbatch;   // rows: one per (channel, scale)
   int e;
@@ -1097,6 +1230,7 @@ int cwtb_create(int device, cwtb_ctx **out) {
   if (const char *g = getenv("CWTB_L2_PERSIST")) c->l2_persist = atoi(g);
   if (const char *g = getenv("CWTB_FUSED")) c->fused = atoi(g);
   if (const char *g = getenv("CWTB_PF_DIST")) c->pf_dist = std::max(0, atoi(g));
+  if (const char *g = getenv("CWTB_FFT_PAD")) c->pad_pow2 = atoi(g) != 0;
   if (const char *g = getenv("CWTB_PF_DIST_A")) c->pf_dist_a = std::max(0, atoi(g));
   if (const char *g = getenv("CWTB_K2_BAND")) c->k2_band_log2 = atoi(g) == 10 ? 10 : 9;
   if (const char *g = getenv("CWTB_K2_512_MAX")) c->k2_512_max_log2 = std::min(19, atoi(g));
@@ -1122,9 +1256,10 @@ void cwtb_destroy(cwtb_ctx *c) {
   cudaStreamSynchronize(c->stream);
 #endif
   for (Buf *b : {&c->ctr, &c->sig, &c->sig2, &c->spec, &c->Z, &c->Z2, &c->Y, &c->B, &c->W, &c->W2, &c->descs, &c->table, &c->scratch,
-                 &c->C, &c->A12, &c->F, &c->aux, &c->rowd, &c->win, &c->mask, &c->hist, &c->noise, &c->wide})
+                 &c->C, &c->A12, &c->F, &c->aux, &c->rowd, &c->win, &c->mask, &c->hist, &c->noise, &c->wide, &c->blueA, &c->blueX, &c->blueY})
     if (b->p) rt_free(b->p);
   for (auto &kv : c->ntabs) { rt_free(kv.second.hi); rt_free(kv.second.lo); }
+  for (auto &kv : c->blue) { rt_free(kv.second.wm); rt_free(kv.second.bf[0]); rt_free(kv.second.bf[1]); }
   if (c->tw64) rt_free(c->tw64);
   if (c->tw32) rt_free(c->tw32);
   for (void *p : c->pinned) rt_host_free(p);
@@ -1353,10 +1488,13 @@ int cwtb_get_signal_fft(cwtb_ctx *c, void *out) {
 }
 
 int cwtb_fft_c2c(cwtb_ctx *c, const void *in, void *out, int64_t n, int batch, int sign, int precision) {
-  if (!c || !in || !out || n < 2 || (n & (n - 1)) || batch < 1 || (sign != 1 && sign != -1))
+  if (!c || !in || !out || n < 2 || batch < 1 || (sign != 1 && sign != -1))
     return fail(c, CWTB_ERR_ARG, "fft_c2c: bad argument");
   if (precision != CWTB_F64 && precision != CWTB_F32) return fail(c, CWTB_ERR_ARG, "bad precision");
   if (n > (1ll << 26)) return fail(c, CWTB_ERR_UNSUPPORTED, "fft_c2c: n > 2^26");
+  const bool pow2 = (n & (n - 1)) == 0;
+  if (!pow2 && precision != CWTB_F64) return fail(c, CWTB_ERR_UNSUPPORTED, "fft_c2c: lengths other than 2^k run in fp64");
+  if (!pow2 && n > (1ll << 24)) return fail(c, CWTB_ERR_UNSUPPORTED, "fft_c2c: non power-of-two n > 2^24");
 #ifndef CWTB_HOST_EMU
   RT(cudaSetDevice(c->device));
 #endif
@@ -1367,6 +1505,13 @@ int cwtb_fft_c2c(cwtb_ctx *c, const void *in, void *out, int64_t n, int batch, i
   if ((e = ensure(c, c->C, cnt * esz))) return e;
   if ((e = ensure(c, c->A12, cnt * esz))) return e;
   void *din = c->C.p, *dout = c->A12.p;
+  if (!pow2) {   // any length: Bluestein on the power-of-two kernels
+    RT(rt_h2d(din, in, cnt * esz, c->stream));
+    if ((e = blue_rows(c, din, 0, n, (double2 *)dout, n, (unsigned)n, batch, sign, 1.0, n))) return e;
+    RT(rt_d2h(out, dout, cnt * esz, c->stream));
+    RT(rt_sync(c->stream));
+    return 0;
+  }
   if (precision == CWTB_F64) {
     RT(rt_h2d(din, in, cnt * esz, c->stream));
     e = sign < 0 ? fft_rows<double, -1>(c, din, 0, n, n, (double2 *)dout, n, (unsigned)n, batch)
@@ -1630,6 +1775,7 @@ int cwtb_wct(cwtb_ctx *c, const double *y1, const double *y2, int64_t n0, double
   if (family == CWTB_TABLE) return fail(c, CWTB_ERR_UNSUPPORTED, "wct needs an analytic wavelet family");
   int e = prepare(c, n0, dt, scales, n_scales, family, param, CWTB_F64, nullptr);
   if (e) return e;
+  if (c->job.exact) return fail(c, CWTB_ERR_UNSUPPORTED, "coherence and smoothing need the padded mode (cwtb_set_padding)");
   if ((e = upload_signal_f64(c, c->sig, y1, n0))) return e;
   if ((e = upload_signal_f64(c, c->sig2, y2, n0))) return e;
   if ((e = upload_window(c, boxcar_len))) return e;
@@ -1645,6 +1791,12 @@ int cwtb_wct(cwtb_ctx *c, const double *y1, const double *y2, int64_t n0, double
   if (WCT_out) RT(rt_d2h(WCT_out, dW, cnt * sizeof(double), c->stream));
   if (aWCT_out) RT(rt_d2h(aWCT_out, dA, cnt * sizeof(double), c->stream));
   RT(rt_sync(c->stream));
+  return 0;
+}
+
+int cwtb_set_padding(cwtb_ctx *c, int pad_to_pow2) {
+  if (!c) return CWTB_ERR_ARG;
+  c->pad_pow2 = pad_to_pow2 != 0;
   return 0;
 }
 
@@ -1699,6 +1851,7 @@ int cwtb_wct_mc(cwtb_ctx *c, const double *noise, int n_pairs, int64_t n0, doubl
   if (family == CWTB_TABLE) return fail(c, CWTB_ERR_UNSUPPORTED, "wct_mc needs an analytic wavelet family");
   int e = prepare(c, n0, dt, scales, n_scales, family, param, CWTB_F64, nullptr);
   if (e) return e;
+  if (c->job.exact) return fail(c, CWTB_ERR_UNSUPPORTED, "coherence and smoothing need the padded mode (cwtb_set_padding)");
   if ((e = upload_window(c, boxcar_len))) return e;
   if ((e = upload_row_tables(c, c->job))) return e;
   const size_t cnt = (size_t)n_scales * n0;

@@ -1005,6 +1005,125 @@ struct WidenBody {
   }
 };
 
+// ---- Bluestein (chirp-z) pieces: DFT of ARBITRARY length n through power-of-two transforms ----
+// (un-padded mode, pycwt/helpers.py:15-19: with pyfftw installed the reference transforms at the
+// signal's own length).  With w_s[k] = e^{s i pi k^2 / n}  (s = -1 forward, +1 inverse):
+//   X[k] = sum_j x[j] e^{s 2 pi i jk/n} = w_s[k] * sum_j (x[j] w_s[j]) conj(w_s[k-j]),
+// a linear convolution of length 2n-1 evaluated with transforms of length L = 2^m >= 2n-1:
+//   a = x * w_s (zero-padded to L),  b[m] = conj(w_s[|m|]) for |m| < n (wrapped mod L),
+//   X[k] = w_s[k] / L * IFFT_L( FFT_L(a) * FFT_L(b) )[k].
+// One table wm[k] = e^{-i pi k^2/n} serves both signs (w_+ = conj(wm)); k^2 is reduced mod 2n in
+// integers so the phase is exact.
+struct BlueChirpArgs { double2 *wm; unsigned n; };
+struct BlueChirpBody {
+  using Args = BlueChirpArgs;
+  static constexpr int NPHASE = 1;
+  static constexpr size_t SMEM = 0;
+  template <int PH> HD static void phase(const Args &a, int bx, int, int tid, void *) {
+    const unsigned long long k = (unsigned long long)bx * NT + tid;
+    if (k >= a.n) return;
+    const unsigned long long m = (k * k) % (2ull * a.n);
+    double sn, cs;
+    sincospi_hd((double)m / (double)a.n, &sn, &cs);
+    a.wm[k] = make_double2(cs, -sn);
+  }
+};
+
+HD double2 blue_w(const double2 *wm, unsigned k, int sign) {   // w_s[k]
+  const double2 v = wm[k];
+  return sign < 0 ? v : make_double2(v.x, -v.y);
+}
+
+struct BlueFilterArgs { const double2 *wm; double2 *b; unsigned n, L; int sign; };
+struct BlueFilterBody {
+  using Args = BlueFilterArgs;
+  static constexpr int NPHASE = 1;
+  static constexpr size_t SMEM = 0;
+  template <int PH> HD static void phase(const Args &a, int bx, int, int tid, void *) {
+    const unsigned m = (unsigned)bx * NT + tid;
+    if (m >= a.L) return;
+    double2 v = make_double2(0.0, 0.0);
+    if (m < a.n) v = blue_w(a.wm, m, -a.sign);             // conj(w_s[m])
+    else if (m > a.L - a.n) v = blue_w(a.wm, a.L - m, -a.sign);
+    a.b[m] = v;
+  }
+};
+
+// a[r][k] = in[r][k] * w_s[k]   (rows of a generic transform)
+struct BluePreArgs {
+  const void *in; double2 *out; const double2 *wm;
+  long long in_pitch, out_pitch; unsigned n; int real_in, sign;
+};
+struct BluePreBody {
+  using Args = BluePreArgs;
+  static constexpr int NPHASE = 1;
+  static constexpr size_t SMEM = 0;
+  template <int PH> HD static void phase(const Args &a, int bx, int by, int tid, void *) {
+    const unsigned k = (unsigned)bx * NT + tid;
+    if (k >= a.n) return;
+    double2 x;
+    if (a.real_in) x = make_double2(((const double *)a.in)[(size_t)by * a.in_pitch + k], 0.0);
+    else x = ((const double2 *)a.in)[(size_t)by * a.in_pitch + k];
+    a.out[(size_t)by * a.out_pitch + k] = cmul(x, blue_w(a.wm, k, a.sign));
+  }
+};
+
+// a[r][k] = x^[k] * norm_j conj(psi^(s_j w_k)) / n * w_+[k]: product of wavelet.py:102-104 and the
+// chirp pre-multiplication of the inverse transform in one pass
+struct BlueProdArgs {
+  const ScaleDesc *descs; const double2 *spec; double2 *out; const double2 *wm;
+  Fam fam; long long out_pitch; unsigned n; int first;
+};
+struct BlueProdBody {
+  using Args = BlueProdArgs;
+  static constexpr int NPHASE = 1;
+  static constexpr size_t SMEM = 0;
+  template <int PH> HD static void phase(const Args &a, int bx, int by, int tid, void *) {
+    const unsigned k = (unsigned)bx * NT + tid;
+    if (k >= a.n) return;
+    const ScaleDesc d = a.descs[a.first + by];
+    // numpy fftfreq ordering for any n: bins 0 .. (n-1)/2 are non-negative
+    const int ks = k < (a.n + 1) / 2 ? (int)k : (int)k - (int)a.n;
+    double2 v = make_double2(0.0, 0.0);
+    if (a.fam.family == 3 || (ks >= d.k_lo && ks <= d.k_hi)) v = band_value<double>(a.fam, d, a.spec, k, ks, a.n);
+    a.out[(size_t)by * a.out_pitch + k] = cmul(v, blue_w(a.wm, k, +1));
+  }
+};
+
+struct BlueMulArgs { double2 *x; const double2 *bf; unsigned L; };
+struct BlueMulBody {
+  using Args = BlueMulArgs;
+  static constexpr int NPHASE = 1;
+  static constexpr size_t SMEM = 0;
+  template <int PH> HD static void phase(const Args &a, int bx, int by, int tid, void *) {
+    const unsigned m = (unsigned)bx * NT + tid;
+    if (m >= a.L) return;
+    double2 *p = a.x + (size_t)by * a.L + m;
+    *p = cmul(*p, a.bf[m]);
+  }
+};
+
+// out[row][k] = epilogue(y[r][k] * w_s[k] * scale)
+struct BluePostArgs {
+  const double2 *y; double2 *out; const double2 *wm; const ScaleDesc *descs;   // descs may be null
+  long long out_pitch, nout; double scale; unsigned L; int first, row0, sign, epi;
+};
+struct BluePostBody {
+  using Args = BluePostArgs;
+  static constexpr int NPHASE = 1;
+  static constexpr size_t SMEM = 0;
+  template <int PH> HD static void phase(const Args &a, int bx, int by, int tid, void *) {
+    const long long k = (long long)bx * NT + tid;
+    if (k >= a.nout) return;
+    const int row = a.descs ? a.descs[a.first + by].row : a.row0 + by;
+    double2 v = cmul(a.y[(size_t)by * a.L + k], blue_w(a.wm, (unsigned)k, a.sign));
+    v.x *= a.scale; v.y *= a.scale;
+    double2 *o = a.out + (size_t)row * a.out_pitch + k;
+    if (a.epi == EPI_MULCONJ) v = cmul(*o, cconj(v));
+    *o = v;
+  }
+};
+
 // ---- Body: pass twiddle tables in [c][j] layout (see fft_tile.cuh: tw_offset) -------------
 struct PassTwArgs {
   double2 *out64;

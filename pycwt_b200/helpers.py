@@ -1,19 +1,31 @@
 """Host-side helpers with the interface of pycwt/helpers.py.  O(N) or O(S) glue that
 stays in NumPy (8f rank 1); the FFT-heavy work is in the engine."""
-from os import makedirs
+from os import environ, makedirs
 from os.path import exists, expanduser
 
 import numpy as np
 import scipy.fft as fft  # the reference exposes its FFT backend module under this name
 
-_FFT_NEXT_POW2 = True
+# True: the reference's scipy branch (helpers.py:22-30), transforms zero-padded to the next power
+# of two.  False: the policy of its pyfftw branch (helpers.py:15-19), transforms at the signal's
+# own length -- what a user with pyfftw installed gets from the stock package.  (In the
+# reference the switch is "is pyfftw importable"; here it is this flag / CWTB_FFT_PAD=0.)
+_FFT_NEXT_POW2 = environ.get('CWTB_FFT_PAD', '1') != '0'
+
+
+def set_fft_padding(pad_to_next_pow2):
+    """Choose the transform-length policy (see `_FFT_NEXT_POW2`).  Un-padded transforms run in
+    fp64 and cover cwt / icwt / xwt; coherence and smoothing need the padded mode."""
+    global _FFT_NEXT_POW2
+    _FFT_NEXT_POW2 = bool(pad_to_next_pow2)
 
 
 def fft_kwargs(signal, **kwargs):
-    """Padding policy of the reference's scipy branch (helpers.py:27-30): transform
-    length is the next power of two.  Other keyword arguments are dropped, as there."""
+    """Transform length for `signal` (helpers.py:15-19 and 27-30).  Other keyword arguments
+    are dropped, as in the reference's scipy branch."""
     if _FFT_NEXT_POW2:
         return {'n': int(2 ** np.ceil(np.log2(len(signal))))}
+    return {'n': len(signal)}
 
 
 def find(condition):

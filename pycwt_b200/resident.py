@@ -18,7 +18,8 @@ import numpy as np
 
 from . import _engine
 from .helpers import fft, fft_kwargs
-from .wavelet import (_check_parameter_wavelet, _nan_rows, _precision, _resolve_scales)
+from .wavelet import (_check_parameter_wavelet, _nan_rows, _precision, _resolve_scales,
+                      _sync_padding)
 
 __all__ = ['cwt_resident', 'ResidentTransform']
 
@@ -36,7 +37,7 @@ class ResidentTransform(object):
         self.freqs = freqs
         self.precision = precision
         self._serial = serial
-        self.npad = int(2 ** np.ceil(np.log2(self.n0)))   # padding policy of helpers.py:27-30
+        self.npad = fft_kwargs(range(self.n0))['n']       # transform length (helpers.py:15-30)
         self._coi = None
         self._fftfreqs = None
 
@@ -160,6 +161,8 @@ def cwt_resident(signal, dt, dj=1/12, s0=-1, J=-1, wavelet='morlet', freqs=None,
         sig = np.asarray(sig, dtype=np.float64)
     family, param = wavelet._engine_spec()
     precision = _precision()
+    if _sync_padding(eng, n0):
+        precision = _engine.F64
     eng.cwt(sig, dt, sj, family, param, precision, fetch=False)
     serial = eng.job_serial()
     return ResidentTransform(eng, wavelet, n0, dt, dj, sj, freqs, precision, serial)

@@ -18,6 +18,7 @@ from scipy.stats import chi2
 from tqdm import tqdm
 
 from . import _engine
+from . import helpers as _helpers
 from .helpers import (ar1, ar1_spectrum, fft, fft_kwargs, find, get_cache_dir,
                       rednoise)
 from .mothers import Morlet, Paul, DOG, MexicanHat
@@ -60,10 +61,26 @@ def _nan_rows(wavelet, sj, npad, dt):
     return np.isnan(resp).any(axis=1)
 
 
+def _sync_padding(eng, n0):
+    """Hand the transform-length policy of helpers.fft_kwargs to the engine.  True if this
+    transform runs un-padded (policy off and n0 not a power of two)."""
+    eng.set_padding(_helpers._FFT_NEXT_POW2)
+    return (not _helpers._FFT_NEXT_POW2) and (n0 & (n0 - 1)) != 0
+
+
+def _need_padded_mode(what):
+    if not _helpers._FFT_NEXT_POW2:
+        raise NotImplementedError(
+            '%s is built for the padded transforms only (helpers.set_fft_padding(True)); the '
+            'un-padded mode covers cwt, icwt and xwt' % what)
+
+
 def _transform(signal, dt, sj, wavelet, precision=None, engine=None):
     """W[S, n0] (complex128) for the given scales; rows are NOT yet NaN-filtered."""
     eng = engine or _engine.default_engine()
     precision = _precision() if precision is None else precision
+    if _sync_padding(eng, len(signal)):
+        precision = _engine.F64      # un-padded transforms run in fp64
     spec = wavelet._engine_spec() if hasattr(wavelet, '_engine_spec') else None
     sig = np.asarray(signal)
     if sig.dtype != np.float32:
@@ -235,7 +252,9 @@ def xwt(y1, y2, dt, dj=1/12, s0=-1, J=-1, significance_level=0.95,
     if not keep.any():
         keep[:] = True
     sj, freq = sj[keep], freq[keep]
-    W12 = _pair_engine(wavelet).xwt(y1n, y2n, dt, sj, *_family_of(wavelet))
+    eng = _pair_engine(wavelet)
+    _sync_padding(eng, n0)
+    W12 = eng.xwt(y1n, y2n, dt, sj, *_family_of(wavelet))
     coi = (n0 / 2 - np.abs(np.arange(0, n0) - (n0 - 1) / 2))
     coi = wavelet.flambda() * wavelet.coi() * dt * coi
 
@@ -276,6 +295,7 @@ def wct(y1, y2, dt, dj=1/12, s0=-1, J=-1, sig=True,
     products, the Gaussian time smoothing, the scale boxcar and the coherence ratio run
     on the GPU; `sig` comes from wct_significance (GPU Monte-Carlo) when sig=True."""
     wavelet = _check_parameter_wavelet(wavelet)
+    _need_padded_mode('wct')
     if not hasattr(wavelet, 'smooth'):
         # same failure mode as the reference for Paul / DOG (no smoothing operator)
         raise AttributeError("'{}' object has no attribute 'smooth'".format(
@@ -324,9 +344,11 @@ def _mc_problem(dt, dj, s0, J, wavelet):
 def _mc_histogram(prob, dt, dj, wavelet, draw, indices, progress=False, engine=None):
     """1000-bin histograms of the coherence of the surrogate pairs draw(i), i in `indices`
     (reference wavelet.py:609-630), accumulated on the GPU: int64 [S, nbins]."""
+    _need_padded_mode('wct_significance')
     N, sj, nbins = prob['N'], prob['sj'], prob['nbins']
     hist = np.zeros((sj.size, nbins), dtype=np.int64)
     eng = engine or _pair_engine(wavelet)
+    eng.set_padding(True)
     fam = _family_of(wavelet)
     indices = list(indices)
     batch = max(1, min(len(indices), int((256 << 20) // (16 * N)) or 1))
@@ -405,6 +427,7 @@ def _smooth_device(W, dt, dj, scales, deltaj0):
     if klen < 1:
         # deltaj0 = -1 (f0 != 6): the reference fails inside rect()
         raise ValueError('smoothing window undefined for this wavelet (deltaj0 = -1)')
+    _need_padded_mode('Morlet.smooth')
     eng = _engine.default_engine()
     if np.isreal(W).all():
         return eng.smooth(np.ascontiguousarray(W.real, dtype=np.float64), dt, scales, klen)

@@ -145,6 +145,29 @@ def main():
                                           cache=False)
     save("wct_sig_seed99", y1=ya, y2=yb, WCT=WCT, aWCT=aWCT, coi=coi, freq=freq, sig=sig)
 
+    # Un-padded transforms: the reference's own cwt/icwt/xwt code with the transform-length
+    # policy of its pyfftw branch (helpers.py:15-19: n = len(signal)).  pyfftw is not installed
+    # here, so the policy function is swapped in while the FFT library stays scipy's -- both are
+    # exact DFTs of the requested length.
+    import pycwt.wavelet as ref_wavelet
+    import pycwt.mothers as ref_mothers
+    padded_policy = ref_wavelet.fft_kwargs
+    unpadded = lambda signal, **kw: {"n": len(signal)}   # noqa: E731
+    ref_wavelet.fft_kwargs = unpadded
+    ref_mothers.fft_kwargs = unpadded
+    try:
+        cwt_case("nopad_nino3_morlet", nino, 0.25, "morlet", 6, dj=0.25, s0=0.5, J=28)
+        cwt_case("nopad_nino3_paul", nino, 0.25, "paul", 4, dj=0.25)
+        cwt_case("nopad_nino3_dog3", nino, 0.25, "dog", 3, dj=0.5)
+        x = chirp(4001) + 0.1 * np.random.RandomState(3).randn(4001)      # odd length
+        cwt_case("nopad_chirp4001_morlet", x, 1.0, "morlet", 6, stride=8, dj=1 / 8, s0=2.0, J=72)
+        cwt_case("nopad_chirp3000_dog", x[:3000], 1.0, "dog", 2, stride=8, dj=1 / 4, s0=0.5033, J=40)
+        W12, coi, freq, signif = pycwt.xwt(s1, s2, dt, dj=1 / 12, wavelet=pycwt.Morlet(6))
+        save("nopad_ao_baltic_xwt", y1=s1, y2=s2, dt=dt, W12=W12, coi=coi, freq=freq, signif=signif)
+    finally:
+        ref_wavelet.fft_kwargs = padded_policy
+        ref_mothers.fft_kwargs = padded_policy
+
 
 if __name__ == "__main__":
     main()

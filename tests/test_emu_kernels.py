@@ -173,3 +173,70 @@ def check_resident_products(eng, precision_tol=1e-12):
 
 def test_resident_transform_products(emu):
     check_resident_products(emu)
+
+
+def test_dft_of_any_length(emu):
+    """cwtb_fft_c2c for lengths that are not powers of two (Bluestein on the 2^k kernels)."""
+    rs = np.random.RandomState(3)
+    for n in [3, 5, 6, 7, 12, 100, 147, 504, 1000, 1023, 1025, 4001]:
+        x = rs.randn(2, n) + 1j * rs.randn(2, n)
+        assert relerr(emu.fft_c2c(x, -1), np.fft.fft(x, axis=1)) < 1e-13, n
+        assert relerr(emu.fft_c2c(x, +1), np.fft.ifft(x, axis=1) * n) < 1e-13, n
+
+
+def check_unpadded_mode(eng, tol):
+    """Un-padded transforms (the reference's pyfftw length policy) through the public API
+    against fixtures made by the reference's own code with that policy."""
+    import pycwt_b200 as pycwt
+    from pycwt_b200 import helpers
+    helpers.set_fft_padding(False)
+    try:
+        for name in ["nopad_nino3_morlet", "nopad_nino3_paul", "nopad_nino3_dog3",
+                     "nopad_chirp4001_morlet", "nopad_chirp3000_dog"]:
+            g = load_golden(name)
+            cls = {"morlet": pycwt.Morlet, "paul": pycwt.Paul, "dog": pycwt.DOG}[str(g["wavelet"])]
+            mother = cls(int(g["param"]))
+            kw = golden_cwt_kwargs(g)
+            W, sj, freqs, coi, fft, fftfreqs = pycwt.cwt(g["x"], float(g["dt"]), wavelet=mother, **kw)
+            assert tuple(W.shape) == tuple(g["shape"]), name
+            st = int(g["stride"])
+            assert relerr(W[:, ::st], g["W"]) < tol, (name, relerr(W[:, ::st], g["W"]))
+            assert np.array_equal(sj, g["sj"]) and np.array_equal(freqs, g["freqs"])
+            assert relerr(fft, g["fft"]) < tol and np.array_equal(fftfreqs, g["fftfreqs"])
+            np.testing.assert_allclose(coi, g["coi"], rtol=1e-15)
+            if "iW" in g.files:
+                iW = pycwt.icwt(W, sj, float(g["dt"]), kw.get("dj", 1 / 12), mother)
+                assert relerr(iW, g["iW"]) < tol
+        g = load_golden("nopad_ao_baltic_xwt")
+        W12, coi, freq, signif = pycwt.xwt(g["y1"], g["y2"], float(g["dt"]), dj=1 / 12,
+                                           wavelet=pycwt.Morlet(6))
+        assert relerr(W12, g["W12"]) < tol
+        np.testing.assert_allclose(signif, g["signif"], rtol=1e-12)
+        # duck-typed wavelet (host table) and the device-resident handle follow the same policy
+        class Duck(object):
+            def __init__(self):
+                self.m = pycwt.Morlet(6)
+            def __getattr__(self, k):
+                if k == '_engine_spec':
+                    raise AttributeError(k)
+                return getattr(self.m, k)
+        g = load_golden("nopad_nino3_morlet")
+        Wd = pycwt.cwt(g["x"], 0.25, 0.25, 0.5, 28, Duck())[0]
+        assert relerr(Wd, g["W"]) < tol
+        r = pycwt.cwt_resident(g["x"], 0.25, 0.25, 0.5, 28, pycwt.Morlet(6))
+        assert r.npad == 504 and relerr(r.global_power(), (np.abs(g["W"]) ** 2).mean(axis=1)) < tol
+        # coherence / smoothing are padded-mode only
+        with pytest.raises(NotImplementedError):
+            pycwt.wct(g["x"], g["x"][::-1].copy(), 0.25, sig=False)
+    finally:
+        helpers.set_fft_padding(True)
+    # back in the padded mode the same call gives the padded result again
+    g = load_golden("nino3_morlet_tutorial")
+    W = pycwt.cwt(g["x"], 0.25, 0.25, 0.5, 28, pycwt.Morlet(6))[0]
+    assert relerr(W, g["W"]) < tol
+
+
+def test_unpadded_mode_public_api(emu, monkeypatch):
+    from pycwt_b200 import _engine
+    monkeypatch.setattr(_engine, "default_engine", lambda *a, **k: emu)
+    check_unpadded_mode(emu, 1e-12)

@@ -276,3 +276,35 @@ def test_fp32_fetch_widening_large(pycwt, monkeypatch):
     xh = np.fft.fft(x.astype(np.float64))
     filt = np.sqrt(sj[rows, None] * om[1] * 2 ** 18) * np.conj(orc.DOG(2).psi_ft(sj[rows, None] * om))
     assert relerr(W[rows], np.fft.ifft(xh * filt, axis=1)) < TOL32
+
+
+def test_unpadded_mode(pycwt):
+    """transforms at the signal's own length (the reference's pyfftw policy,
+    helpers.py:15-19) against fixtures produced by the reference's own code with that policy."""
+    from test_emu_kernels import check_unpadded_mode
+    check_unpadded_mode(pycwt.default_engine(), TOL64)
+
+
+def test_unpadded_long_signal_and_any_length_dft(pycwt):
+    """Un-padded transform whose convolution length needs the two-kernel FFT (L = 2^18), rows
+    checked against direct numpy DFTs; and the DFT hook for awkward lengths."""
+    from pycwt_b200 import helpers
+    eng = pycwt.default_engine()
+    rs = np.random.RandomState(2)
+    for n in [3, 7, 1000, 4099, 65537, 100003]:
+        x = rs.randn(2, n) + 1j * rs.randn(2, n)
+        assert relerr(eng.fft_c2c(x, -1), np.fft.fft(x, axis=1)) < 1e-12, n
+    n = 100000
+    x = chirp(n) + 0.1 * rs.randn(n)
+    helpers.set_fft_padding(False)
+    try:
+        W, sj, *_ = pycwt.cwt(x, 1.0, 0.5, 2.0, 24, pycwt.Morlet(6))
+    finally:
+        helpers.set_fft_padding(True)
+    om = 2 * np.pi * np.fft.fftfreq(n, 1.0)
+    xh = np.fft.fft(x)
+    rows = [0, 11, 24]
+    filt = np.sqrt(sj[rows, None] * om[1] * n) * orc.Morlet(6).psi_ft(sj[rows, None] * om)
+    assert relerr(W[rows], np.fft.ifft(xh * filt, axis=1)) < TOL64
+    Wp = pycwt.cwt(x, 1.0, 0.5, 2.0, 24, pycwt.Morlet(6))[0]
+    assert relerr(Wp[rows], W[rows]) > 1e-6      # padded and un-padded differ at the edges

@@ -39,6 +39,43 @@ def test_cwt_matches_reference(name):
         assert relerr(iW, g["iW"]) < max(tol, 1e-12)
 
 
+NOPAD_CASES = ["nopad_nino3_morlet", "nopad_nino3_paul", "nopad_nino3_dog3",
+               "nopad_chirp4001_morlet", "nopad_chirp3000_dog"]
+
+
+@pytest.fixture
+def unpadded_oracle(monkeypatch):
+    """The oracle with the transform-length policy of the reference's pyfftw branch."""
+    monkeypatch.setattr(orc, "PAD_NEXT_POW2", False)
+
+
+@pytest.mark.parametrize("name", NOPAD_CASES)
+def test_unpadded_cwt_matches_reference(unpadded_oracle, name):
+    """Fixtures: the reference's own cwt/icwt run with `fft_kwargs -> {'n': len(signal)}`
+    (helpers.py:15-19), see make_golden.py."""
+    g = load_golden(name)
+    mother = mother_of(g)
+    kw = golden_cwt_kwargs(g)
+    W, sj, freqs, coi, fft, fftfreqs = orc.cwt(g["x"], float(g["dt"]), wavelet=mother, **kw)
+    assert tuple(W.shape) == tuple(g["shape"])
+    st = int(g["stride"])
+    assert relerr(W[:, ::st], g["W"]) < TOL
+    np.testing.assert_array_equal(sj, g["sj"])
+    assert fft.size == g["x"].size // 2 - 1 and relerr(fft, g["fft"]) < TOL
+    np.testing.assert_allclose(fftfreqs, g["fftfreqs"], rtol=1e-15)
+    if "iW" in g.files:
+        assert relerr(orc.icwt(W, sj, float(g["dt"]), kw.get("dj", 1 / 12), mother), g["iW"]) < 1e-12
+
+
+def test_unpadded_differs_from_padded_and_xwt(unpadded_oracle, monkeypatch):
+    g = load_golden("nopad_ao_baltic_xwt")
+    W12 = orc.xwt(g["y1"], g["y2"], float(g["dt"]), dj=1 / 12, wavelet=orc.Morlet(6))[0]
+    assert relerr(W12, g["W12"]) < TOL
+    monkeypatch.setattr(orc, "PAD_NEXT_POW2", True)
+    W12p = orc.xwt(g["y1"], g["y2"], float(g["dt"]), dj=1 / 12, wavelet=orc.Morlet(6))[0]
+    assert relerr(W12p, g["W12"]) > 1e-3     # the two policies really give different edges
+
+
 def test_known_anchors():
     """SURVEY 8c anchors measured on the reference."""
     g = load_golden("nino3_morlet_tutorial")
