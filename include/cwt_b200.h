@@ -65,8 +65,9 @@ int cwtb_set_band_eps(cwtb_ctx *ctx, double eps);
 /* Transform-length policy of pycwt/helpers.py:7-30.  pad_to_pow2 != 0 (default): the signal is
  * zero-padded to the next power of two (the reference's scipy branch, :27-30).  0: transforms
  * run at the signal's own length (what the reference does when pyfftw is installed, :15-19) --
- * Bluestein's algorithm on the power-of-two kernels, fp64 only, cwt / icwt / xwt only, n0 <= 2^24;
- * power-of-two lengths are unaffected. */
+ * Bluestein's algorithm on the power-of-two kernels, fp64 only, single-channel calls, n0 <= 2^24;
+ * the smoothing filter of wct / smooth / wct_mc then is circular at the rows' own length, as in
+ * the reference.  Power-of-two lengths are unaffected. */
 int cwtb_set_padding(cwtb_ctx *ctx, int pad_to_pow2);
 
 /* Pinned host memory (so D2H of multi-GiB results runs at PCIe speed and can

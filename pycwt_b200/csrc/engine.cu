@@ -1577,6 +1577,13 @@ static int smooth_time(cwtb_ctx *c, double2 *X, int S, long long n0, unsigned N,
   if (e) return e;
   double2 *F = (double2 *)c->F.p;
   if (N < 2) return 0;  // single sample: filter is exp(0) = 1
+  if ((N & (N - 1)) != 0) {
+    // un-padded mode: circular filter at the rows' own length (N == n0), Bluestein transforms
+    if ((e = blue_rows(c, X, 0, n0, F, N, N, S, -1, 1.0, N))) return e;
+    BlueGaussArgs ga{F, d_g, (long long)N, N, 1.0 / (double)N};
+    if ((e = launch<BlueGaussBody>(c, (N + NT - 1) / NT, S, ga))) return e;
+    return blue_rows(c, F, 0, N, X, n0, N, S, +1, 1.0, n0);
+  }
   if ((e = fft_rows<double, -1>(c, X, 0, n0, n0, F, N, N, S, N, d_g, 1.0 / (double)N))) return e;
   return fft_rows<double, +1>(c, F, 0, N, N, X, n0, N, S, n0);
 }
@@ -1775,7 +1782,6 @@ int cwtb_wct(cwtb_ctx *c, const double *y1, const double *y2, int64_t n0, double
   if (family == CWTB_TABLE) return fail(c, CWTB_ERR_UNSUPPORTED, "wct needs an analytic wavelet family");
   int e = prepare(c, n0, dt, scales, n_scales, family, param, CWTB_F64, nullptr);
   if (e) return e;
-  if (c->job.exact) return fail(c, CWTB_ERR_UNSUPPORTED, "coherence and smoothing need the padded mode (cwtb_set_padding)");
   if ((e = upload_signal_f64(c, c->sig, y1, n0))) return e;
   if ((e = upload_signal_f64(c, c->sig2, y2, n0))) return e;
   if ((e = upload_window(c, boxcar_len))) return e;
@@ -1810,7 +1816,8 @@ int cwtb_smooth(cwtb_ctx *c, const void *in, int is_complex, int n_scales, int64
 #endif
   const int S = n_scales;
   const size_t cnt = (size_t)S * n;
-  const unsigned N = 1u << ilog2((unsigned long long)n);
+  if (!c->pad_pow2 && n > (1ll << 24)) return fail(c, CWTB_ERR_UNSUPPORTED, "smooth: un-padded rows longer than 2^24");
+  const unsigned N = c->pad_pow2 ? 1u << ilog2((unsigned long long)n) : (unsigned)n;   // helpers.py:15-30
   int e = upload_window(c, boxcar_len);
   if (e) return e;
   std::vector<double> g(2 * (size_t)S);
@@ -1851,7 +1858,6 @@ int cwtb_wct_mc(cwtb_ctx *c, const double *noise, int n_pairs, int64_t n0, doubl
   if (family == CWTB_TABLE) return fail(c, CWTB_ERR_UNSUPPORTED, "wct_mc needs an analytic wavelet family");
   int e = prepare(c, n0, dt, scales, n_scales, family, param, CWTB_F64, nullptr);
   if (e) return e;
-  if (c->job.exact) return fail(c, CWTB_ERR_UNSUPPORTED, "coherence and smoothing need the padded mode (cwtb_set_padding)");
   if ((e = upload_window(c, boxcar_len))) return e;
   if ((e = upload_row_tables(c, c->job))) return e;
   const size_t cnt = (size_t)n_scales * n0;

@@ -1124,6 +1124,24 @@ struct BluePostBody {
   }
 };
 
+// F[r][k] *= exp(g_r * w_k^2) * post,  w_k = 2 pi fftfreq(n)[k]: the Gaussian time filter of
+// Morlet.smooth (mothers.py:83-91) for a transform length that is not a power of two
+struct BlueGaussArgs { double2 *f; const double *g; long long pitch; unsigned n; double post; };
+struct BlueGaussBody {
+  using Args = BlueGaussArgs;
+  static constexpr int NPHASE = 1;
+  static constexpr size_t SMEM = 0;
+  template <int PH> HD static void phase(const Args &a, int bx, int by, int tid, void *) {
+    const unsigned k = (unsigned)bx * NT + tid;
+    if (k >= a.n) return;
+    const long long ks = k < (a.n + 1) / 2 ? (long long)k : (long long)k - (long long)a.n;
+    const double w = 6.283185307179586 * ((double)ks * (1.0 / (double)a.n));
+    const double m = exp(a.g[by] * (w * w)) * a.post;
+    double2 *p = a.f + (size_t)by * a.pitch + k;
+    p->x *= m; p->y *= m;
+  }
+};
+
 // ---- Body: pass twiddle tables in [c][j] layout (see fft_tile.cuh: tw_offset) -------------
 struct PassTwArgs {
   double2 *out64;

@@ -15,7 +15,7 @@ _FFT_NEXT_POW2 = environ.get('CWTB_FFT_PAD', '1') != '0'
 
 def set_fft_padding(pad_to_next_pow2):
     """Choose the transform-length policy (see `_FFT_NEXT_POW2`).  Un-padded transforms run in
-    fp64 and cover cwt / icwt / xwt; coherence and smoothing need the padded mode."""
+    fp64 (Bluestein's algorithm on the engine's power-of-two kernels)."""
     global _FFT_NEXT_POW2
     _FFT_NEXT_POW2 = bool(pad_to_next_pow2)
 

@@ -68,13 +68,6 @@ def _sync_padding(eng, n0):
     return (not _helpers._FFT_NEXT_POW2) and (n0 & (n0 - 1)) != 0
 
 
-def _need_padded_mode(what):
-    if not _helpers._FFT_NEXT_POW2:
-        raise NotImplementedError(
-            '%s is built for the padded transforms only (helpers.set_fft_padding(True)); the '
-            'un-padded mode covers cwt, icwt and xwt' % what)
-
-
 def _transform(signal, dt, sj, wavelet, precision=None, engine=None):
     """W[S, n0] (complex128) for the given scales; rows are NOT yet NaN-filtered."""
     eng = engine or _engine.default_engine()
@@ -295,7 +288,6 @@ def wct(y1, y2, dt, dj=1/12, s0=-1, J=-1, sig=True,
     products, the Gaussian time smoothing, the scale boxcar and the coherence ratio run
     on the GPU; `sig` comes from wct_significance (GPU Monte-Carlo) when sig=True."""
     wavelet = _check_parameter_wavelet(wavelet)
-    _need_padded_mode('wct')
     if not hasattr(wavelet, 'smooth'):
         # same failure mode as the reference for Paul / DOG (no smoothing operator)
         raise AttributeError("'{}' object has no attribute 'smooth'".format(
@@ -308,7 +300,9 @@ def wct(y1, y2, dt, dj=1/12, s0=-1, J=-1, sig=True,
     y2, y2n, _ = _standardise(y2, normalize)
     n0 = y1n.size
     sj, freq = _resolve_scales(n0, dt, dj, s0, J, wavelet, None)
-    WCT, aWCT = _pair_engine(wavelet).wct(y1n, y2n, dt, dj, sj, *_family_of(wavelet),
+    eng = _pair_engine(wavelet)
+    _sync_padding(eng, len(y1n))
+    WCT, aWCT = eng.wct(y1n, y2n, dt, dj, sj, *_family_of(wavelet),
                                           boxcar_len=_boxcar_len(wavelet, dj))
     coi = (n0 / 2 - np.abs(np.arange(0, n0) - (n0 - 1) / 2))
     coi = wavelet.flambda() * wavelet.coi() * dt * coi
@@ -344,11 +338,10 @@ def _mc_problem(dt, dj, s0, J, wavelet):
 def _mc_histogram(prob, dt, dj, wavelet, draw, indices, progress=False, engine=None):
     """1000-bin histograms of the coherence of the surrogate pairs draw(i), i in `indices`
     (reference wavelet.py:609-630), accumulated on the GPU: int64 [S, nbins]."""
-    _need_padded_mode('wct_significance')
     N, sj, nbins = prob['N'], prob['sj'], prob['nbins']
     hist = np.zeros((sj.size, nbins), dtype=np.int64)
     eng = engine or _pair_engine(wavelet)
-    eng.set_padding(True)
+    _sync_padding(eng, N)
     fam = _family_of(wavelet)
     indices = list(indices)
     batch = max(1, min(len(indices), int((256 << 20) // (16 * N)) or 1))
@@ -427,8 +420,8 @@ def _smooth_device(W, dt, dj, scales, deltaj0):
     if klen < 1:
         # deltaj0 = -1 (f0 != 6): the reference fails inside rect()
         raise ValueError('smoothing window undefined for this wavelet (deltaj0 = -1)')
-    _need_padded_mode('Morlet.smooth')
     eng = _engine.default_engine()
+    _sync_padding(eng, W.shape[1])
     if np.isreal(W).all():
         return eng.smooth(np.ascontiguousarray(W.real, dtype=np.float64), dt, scales, klen)
     return eng.smooth(np.ascontiguousarray(W, dtype=np.complex128), dt, scales, klen)

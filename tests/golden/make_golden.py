@@ -164,6 +164,20 @@ def main():
         cwt_case("nopad_chirp3000_dog", x[:3000], 1.0, "dog", 2, stride=8, dj=1 / 4, s0=0.5033, J=40)
         W12, coi, freq, signif = pycwt.xwt(s1, s2, dt, dj=1 / 12, wavelet=pycwt.Morlet(6))
         save("nopad_ao_baltic_xwt", y1=s1, y2=s2, dt=dt, W12=W12, coi=coi, freq=freq, signif=signif)
+        # coherence and smoothing: the Gaussian time filter is circular at the rows' own length
+        WCT, aWCT, coi2, freq2, sig = pycwt.wct(s1, s2, dt, dj=1 / 12, s0=-1, J=-1, sig=False,
+                                                wavelet=pycwt.Morlet(6), normalize=True)
+        rs2 = np.random.RandomState(7)
+        sjs = 2.0 * 2 ** (np.arange(0, 25) / 4.0)
+        Wr = rs2.rand(25, 300)
+        Wc = rs2.randn(25, 301) + 1j * rs2.randn(25, 301)
+        mo = pycwt.Morlet(6)
+        np.random.seed(4321)
+        sig95 = pycwt.wct_significance(0.2, 0.1, dt=1.0, dj=0.5, s0=2.0, J=10,
+                                       significance_level=0.95, wavelet=mo,
+                                       mc_count=5, progress=False, cache=False)
+        save("nopad_wct_smooth", y1=s1, y2=s2, dt=dt, WCT=WCT, aWCT=aWCT, sj=sjs, Wr=Wr, Wc=Wc,
+             Sr=mo.smooth(Wr, 1.0, 0.25, sjs), Sc=mo.smooth(Wc, 1.0, 0.25, sjs), sig95=sig95)
     finally:
         ref_wavelet.fft_kwargs = padded_policy
         ref_mothers.fft_kwargs = padded_policy

@@ -225,9 +225,18 @@ def check_unpadded_mode(eng, tol):
         assert relerr(Wd, g["W"]) < tol
         r = pycwt.cwt_resident(g["x"], 0.25, 0.25, 0.5, 28, pycwt.Morlet(6))
         assert r.npad == 504 and relerr(r.global_power(), (np.abs(g["W"]) ** 2).mean(axis=1)) < tol
-        # coherence / smoothing are padded-mode only
-        with pytest.raises(NotImplementedError):
-            pycwt.wct(g["x"], g["x"][::-1].copy(), 0.25, sig=False)
+        # coherence, smoothing and the Monte-Carlo levels: the Gaussian filter is circular at the
+        # rows' own length in this mode
+        g = load_golden("nopad_wct_smooth")
+        m = pycwt.Morlet(6)
+        assert relerr(m.smooth(g["Wr"], 1.0, 0.25, g["sj"]), g["Sr"]) < tol
+        assert relerr(m.smooth(g["Wc"], 1.0, 0.25, g["sj"]), g["Sc"]) < tol
+        WCT, aWCT, _, _, _ = pycwt.wct(g["y1"], g["y2"], float(g["dt"]), dj=1 / 12, sig=False, wavelet=m)
+        assert relerr(WCT, g["WCT"]) < 100 * tol and relerr(aWCT, g["aWCT"]) < 100 * tol
+        np.random.seed(4321)
+        sig95 = pycwt.wct_significance(0.2, 0.1, 1.0, 0.5, 2.0, 10, 0.95, m, mc_count=5,
+                                       progress=False, cache=False)
+        np.testing.assert_allclose(sig95, g["sig95"], rtol=1e-9, equal_nan=True)
     finally:
         helpers.set_fft_padding(True)
     # back in the padded mode the same call gives the padded result again

@@ -76,6 +76,18 @@ def test_unpadded_differs_from_padded_and_xwt(unpadded_oracle, monkeypatch):
     assert relerr(W12p, g["W12"]) > 1e-3     # the two policies really give different edges
 
 
+def test_unpadded_coherence_and_smoothing(unpadded_oracle):
+    g = load_golden("nopad_wct_smooth")
+    m = orc.Morlet(6)
+    assert relerr(m.smooth(g["Wr"], 1.0, 0.25, g["sj"]), g["Sr"]) < TOL
+    assert relerr(m.smooth(g["Wc"], 1.0, 0.25, g["sj"]), g["Sc"]) < TOL
+    WCT, aWCT, _, _, _ = orc.wct(g["y1"], g["y2"], float(g["dt"]), dj=1 / 12, sig=False, wavelet=m)
+    assert relerr(WCT, g["WCT"]) < 1e-11 and relerr(aWCT, g["aWCT"]) < 1e-11
+    sig95 = orc.wct_significance(0.2, 0.1, 1.0, 0.5, 2.0, 10, 0.95, m, mc_count=5,
+                                 rng=np.random.RandomState(4321))
+    np.testing.assert_allclose(sig95, g["sig95"], rtol=1e-12, equal_nan=True)
+
+
 def test_known_anchors():
     """SURVEY 8c anchors measured on the reference."""
     g = load_golden("nino3_morlet_tutorial")
