@@ -953,6 +953,9 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
   const unsigned N = job.N;
   const int S = job.S * job.nbatch;   // rows: one per (channel, scale)
   int e;
+  // whatever path leaves this function (also an error in the middle of the fork), the launcher
+  // is back on the engine's stream afterwards
+  struct CurGuard { cwtb_ctx *c; ~CurGuard() { c->cur = c->stream; } } cur_guard{c};
   if ((e = ensure(c, c->spec, (size_t)job.nbatch * N * sizeof(V)))) return e;
   if (!Wout) {
     if ((e = ensure(c, c->W, (size_t)S * job.n0 * sizeof(V)))) return e;
