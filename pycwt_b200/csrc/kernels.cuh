@@ -388,33 +388,36 @@ template <typename T, int SIGN, int K2 = K2C> struct PassBBody {
     tb.bar = (unsigned long long *)((char *)smraw + LY::TILE_BYTES);
     if constexpr (PH == 0) {
       const int nvalid = (U - u0) < LY::P ? (U - u0) : LY::P;
-      if (tid < 32) {   // warp 0 issues the copies
-        if (tid == 0) tb.init_and_expect((unsigned)(nvalid * K * sizeof(V)));
-        warp_sync();    // barrier initialised before any lane's copy refers to it
-        const V *src = a.Z + (size_t)(by % a.zmod) * a.N + (size_t)u0 * K;
-        if constexpr (LY::CHUNKED) {
-          // skewed rows: 16-element pieces, spread over the lanes
+      const V *src = a.Z + (size_t)(by % a.zmod) * a.N + (size_t)u0 * K;
+      if constexpr (LY::CHUNKED) {
+        // skewed rows (compile-time option CWTB_ROWS_SKEW): 16-element pieces issued by the
+        // lanes of warp 0 after lane 0 has armed the barrier
+        if (tid < 32) {
+          if (tid == 0) tb.init_and_expect((unsigned)(nvalid * K * sizeof(V)));
+          warp_sync();
           constexpr int NCH = K / 16;
           for (int i = tid; i < nvalid * NCH; i += 32) {
             const int b = i / NCH, ch = i % NCH;
             tb.copy(sm + LY::phys(b, 16 * ch), src + (size_t)b * K + 16 * ch, (unsigned)(16 * sizeof(V)));
           }
-        } else if (tid == 0) {
-          for (int b = 0; b < nvalid; ++b)
-            tb.copy(sm + LY::phys(b, 0), src + (size_t)b * K, (unsigned)(K * sizeof(V)));
         }
-        // warm L2 with the tile a CTA `pf_dist` blocks ahead will load (same row of the grid,
-        // or the next row when this one is exhausted): its TMA copies then hit L2
-        if (tid == 0 && a.pf_dist > 0) {
-          long long t = (long long)bx + a.pf_dist;
-          int pe = ey;
-          const int tiles = (U + LY::P - 1) / LY::P;
-          while (t >= tiles && pe + 1 < a.ny) { t -= tiles; ++pe; }
-          const int py = a.rev ? a.ny - 1 - pe : pe;
-          if (t < tiles && t * LY::P + LY::P <= U)
-            TileBarrier::prefetch_l2(a.Z + (size_t)(py % a.zmod) * a.N + (size_t)t * LY::P * K,
-                                     (unsigned)(LY::P * K * sizeof(V)));
-        }
+      } else if (tid == 0) {
+        // one thread arms the barrier and issues one bulk copy per row
+        tb.init_and_expect((unsigned)(nvalid * K * sizeof(V)));
+        for (int b = 0; b < nvalid; ++b)
+          tb.copy(sm + LY::phys(b, 0), src + (size_t)b * K, (unsigned)(K * sizeof(V)));
+      }
+      // warm L2 with the tile a CTA `pf_dist` blocks ahead will load (same row of the grid,
+      // or the next row when this one is exhausted): its TMA copies then hit L2
+      if (tid == 0 && a.pf_dist > 0) {
+        long long t = (long long)bx + a.pf_dist;
+        int pe = ey;
+        const int tiles = (U + LY::P - 1) / LY::P;
+        while (t >= tiles && pe + 1 < a.ny) { t -= tiles; ++pe; }
+        const int py = a.rev ? a.ny - 1 - pe : pe;
+        if (t < tiles && t * LY::P + LY::P <= U)
+          TileBarrier::prefetch_l2(a.Z + (size_t)(py % a.zmod) * a.N + (size_t)t * LY::P * K,
+                                   (unsigned)(LY::P * K * sizeof(V)));
       }
       for (int b = nvalid; b < LY::P; ++b)
         for (int i = tid; i < K; i += NT) sm[LY::phys(b, i)] = mk<T>(0, 0);
