@@ -34,9 +34,16 @@ F0 = 6.0
 # (algorithmic 16.78 MB per row: the Z intermediate of the two-kernel scales is read back from
 # DRAM); scaled to the 32-row launches of the bench step.
 # DRAM bytes (read + write) per scale ROW of the W-writing kernels, from the `ncu --set full`
-# captures summarised in profiles/r1/ncu_r1_*.txt (16-row launches): PassB 483.55 MB,
-# Single<1024> 216.15 MB, Direct<8> 216.66 MB per launch.
-TRAFFIC_PER_ROW = {"PassBBody": 483.55e6 / 16, "SingleBody": 216.15e6 / 16, "DirectBody": 216.66e6 / 16}
+# captures summarised in profiles/r1/ncu_r1_*.txt (16-row launches): PassB<1024> 484.84 MB,
+# PassB<512> 478.56 MB, Single<1024> 214.78 MB, Direct<8> 217.69 MB per launch.
+TRAFFIC_PER_ROW = {"PassBBody<double, 1, 1024>": 484.84e6 / 16, "PassBBody<double, 1, 512>": 478.56e6 / 16,
+                   "SingleBody": 214.78e6 / 16, "DirectBody": 217.69e6 / 16}
+
+
+def traffic_per_row(kernel_name):
+    return TRAFFIC_PER_ROW.get(kernel_name, TRAFFIC_PER_ROW.get(kernel_name.split("<")[0]))
+
+
 METRIC = "cwt_scale_points_per_sec"
 UNIT = "scale-points/s"
 
@@ -270,7 +277,7 @@ def run_ours(args):
                   "rows": domw["rows"], "algorithmic_bytes": dom_bytes,
                   "achieved": dom_bytes / (domw["ms"] * 1e-3) / 1e9}
         # traffic and algorithmic bytes are both per (average) launch of the dominant kernel
-        tpr = TRAFFIC_PER_ROW.get(domw["name"].split("<")[0])
+        tpr = traffic_per_row(domw["name"])
         dom_traffic = None if tpr is None else tpr * domw["rows"] / domw["launches"]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
