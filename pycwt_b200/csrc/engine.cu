@@ -131,7 +131,9 @@ struct cwtb_ctx {
   int device = 0;
   rt_stream stream{};
   rt_stream aux_stream{};        // single-kernel classes run here, concurrently with the two-kernel chains
-  rt_stream chain2_stream{};     // every second two-kernel class runs here (own Z and band chunk)
+  rt_stream chain_streams[3]{};  // two-kernel classes rotate over the engine's stream and these (own Z
+                                 // and band-chunk region per chain)
+  int n_chains = 2;              // chains in use, 1..4 (CWTB_CHAINS)
   rt_stream cur{};               // stream the launcher uses right now
   int pad_pow2 = 1;              // 1: transform length = next power of two (reference default,
                                  // helpers.py:27-30); 0: the signal's own length (pyfftw policy,
@@ -161,7 +163,7 @@ struct cwtb_ctx {
   double2 *tw64 = nullptr;
   float2 *tw32 = nullptr;
   std::map<unsigned, NTabDev> ntabs;
-  Buf ctr, sig, sig2, spec, Z, Z2, Y, B, W, W2, descs, table, scratch, C, A12, F, aux, rowd, win, mask, hist, noise, wide, blueA, blueX, blueY;
+  Buf ctr, sig, sig2, spec, Z, Zc[3], Y, B, W, W2, descs, table, scratch, C, A12, F, aux, rowd, win, mask, hist, noise, wide, blueA, blueX, blueY;
   Job job;
   const void *job_dsig = nullptr;  // device signal of the last cwt_dev call (not owned)
   double last_ms = 0;
@@ -177,7 +179,7 @@ struct cwtb_ctx {
   std::set<void *> pinned, devallocs;
 #ifndef CWTB_HOST_EMU
   cudaEvent_t e0{}, e1{};
-  cudaEvent_t ev_fork{}, ev_join{}, ev_join2{};
+  cudaEvent_t ev_fork{}, ev_join{}, ev_joinc[3]{};
 #endif
 };
 
@@ -921,8 +923,8 @@ static int chunk_rows(const cwtb_ctx *c, unsigned N, size_t elem_bytes) {
   return (int)std::max<size_t>(1, std::min<size_t>(g, 32768));
 }
 
-// Which of the two band-chunk regions / Z buffers a two-kernel class uses: the parity of its
-// position among the two-kernel classes (dense classes included, they only use Z).
+// Which band-chunk region / Z buffer / stream a two-kernel class uses: its position among the
+// two-kernel classes modulo the number of chains (dense classes included, they only use Z).
 static int job_chain_region(const cwtb_ctx *c, const Job &job, const ClassRun &cl) {
   int idx = 0;
   for (const ClassRun &o : job.classes) {
@@ -930,7 +932,7 @@ static int job_chain_region(const cwtb_ctx *c, const Job &job, const ClassRun &c
     const bool single = o.log2K <= 10 || (o.log2K <= c->direct_max_log2 && o.log2K < job.log2N);
     if (!single) ++idx;
   }
-  return idx & 1;
+  return idx % std::max(1, c->n_chains);
 }
 
 // elements of one band-chunk region: the largest chunk of band products of any two-kernel class
@@ -981,7 +983,7 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
   if ((e = get_ntab(c, N, job.log2N, &nt))) return e;
   const int G = chunk_rows(c, N, sizeof(V));
   const size_t bchunk = band_chunk_elems(c, job, G);   // two regions: one per chain stream
-  if ((e = ensure(c, c->B, (job.b_single + 2 * bchunk) * sizeof(V)))) return e;
+  if ((e = ensure(c, c->B, (job.b_single + (size_t)std::max(1, c->n_chains) * bchunk) * sizeof(V)))) return e;
   V *Bbuf = (V *)c->B.p;
 
   // band products of every single-kernel scale in one launch (their descriptors are the tail
@@ -1008,7 +1010,8 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
   if (split) {
     RT(cudaEventRecord(c->ev_fork, c->stream));
     RT(cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
-    if (split2) RT(cudaStreamWaitEvent(c->chain2_stream, c->ev_fork, 0));
+    if (split2)
+      for (int k = 1; k < c->n_chains; ++k) RT(cudaStreamWaitEvent(c->chain_streams[k - 1], c->ev_fork, 0));
   }
 #else
   const bool split2 = false;
@@ -1064,13 +1067,13 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
       continue;
     }
     const int chunk = c->fused ? cl.count : G;   // fused: the whole class in one persistent launch
-    // successive two-kernel classes alternate between two streams, each with its own Z buffer
+    // successive two-kernel classes rotate over the chains, each with its own stream, Z buffer
     // and band-chunk region (descriptor offsets already point into the right region)
-    const bool on2 = split2 && (job_chain_region(c, job, cl) == 1);
-    Buf &Zb = on2 ? c->Z2 : c->Z;
+    const int chain = split2 ? job_chain_region(c, job, cl) : 0;
+    Buf &Zb = chain > 0 ? c->Zc[chain - 1] : c->Z;
     if ((e = ensure(c, Zb, (size_t)(c->fused ? c->ring : G) * N * sizeof(V)))) return e;
 #ifndef CWTB_HOST_EMU
-    c->cur = on2 ? c->chain2_stream : c->stream;
+    c->cur = chain > 0 ? c->chain_streams[chain - 1] : c->stream;
 #endif
     ++chain_no;
     for (int g0 = 0; g0 < cl.count; g0 += chunk) {
@@ -1119,10 +1122,11 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
   if (split) {   // join: later work on the main stream sees every row of W
     RT(cudaEventRecord(c->ev_join, c->aux_stream));
     RT(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
-    if (split2) {
-      RT(cudaEventRecord(c->ev_join2, c->chain2_stream));
-      RT(cudaStreamWaitEvent(c->stream, c->ev_join2, 0));
-    }
+    if (split2)
+      for (int k = 1; k < c->n_chains; ++k) {
+        RT(cudaEventRecord(c->ev_joinc[k - 1], c->chain_streams[k - 1]));
+        RT(cudaStreamWaitEvent(c->stream, c->ev_joinc[k - 1], 0));
+      }
   }
 #endif
   return 0;
@@ -1219,8 +1223,8 @@ int cwtb_create(int device, cwtb_ctx **out) {
   cudaEventCreate(&c->e1);
   for (auto &st : c->copy_streams) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking);
-  cudaStreamCreateWithFlags(&c->chain2_stream, cudaStreamNonBlocking);
-  cudaEventCreateWithFlags(&c->ev_join2, cudaEventDisableTiming);
+  for (auto &st : c->chain_streams) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+  for (auto &ev : c->ev_joinc) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
   if (const char *g = getenv("CWTB_STREAMS")) { c->two_streams = atoi(g) >= 2; c->three_streams = atoi(g) >= 3; }
@@ -1233,6 +1237,7 @@ int cwtb_create(int device, cwtb_ctx **out) {
   if (const char *g = getenv("CWTB_L2_PERSIST")) c->l2_persist = atoi(g);
   if (const char *g = getenv("CWTB_FUSED")) c->fused = atoi(g);
   if (const char *g = getenv("CWTB_PF_DIST")) c->pf_dist = std::max(0, atoi(g));
+  if (const char *g = getenv("CWTB_CHAINS")) c->n_chains = std::min(4, std::max(1, atoi(g)));
   if (const char *g = getenv("CWTB_FFT_PAD")) c->pad_pow2 = atoi(g) != 0;
   if (const char *g = getenv("CWTB_PF_DIST_A")) c->pf_dist_a = std::max(0, atoi(g));
   if (const char *g = getenv("CWTB_K2_BAND")) c->k2_band_log2 = atoi(g) == 10 ? 10 : 9;
@@ -1258,7 +1263,7 @@ void cwtb_destroy(cwtb_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
 #endif
-  for (Buf *b : {&c->ctr, &c->sig, &c->sig2, &c->spec, &c->Z, &c->Z2, &c->Y, &c->B, &c->W, &c->W2, &c->descs, &c->table, &c->scratch,
+  for (Buf *b : {&c->ctr, &c->sig, &c->sig2, &c->spec, &c->Z, &c->Zc[0], &c->Zc[1], &c->Zc[2], &c->Y, &c->B, &c->W, &c->W2, &c->descs, &c->table, &c->scratch,
                  &c->C, &c->A12, &c->F, &c->aux, &c->rowd, &c->win, &c->mask, &c->hist, &c->noise, &c->wide, &c->blueA, &c->blueX, &c->blueY})
     if (b->p) rt_free(b->p);
   for (auto &kv : c->ntabs) { rt_free(kv.second.hi); rt_free(kv.second.lo); }
@@ -1273,8 +1278,8 @@ void cwtb_destroy(cwtb_ctx *c) {
   cudaStreamDestroy(c->stream);
   for (auto &st : c->copy_streams) cudaStreamDestroy(st);
   cudaStreamDestroy(c->aux_stream);
-  cudaStreamDestroy(c->chain2_stream);
-  cudaEventDestroy(c->ev_join2);
+  for (auto &st : c->chain_streams) cudaStreamDestroy(st);
+  for (auto &ev : c->ev_joinc) cudaEventDestroy(ev);
   cudaEventDestroy(c->ev_fork);
   cudaEventDestroy(c->ev_join);
 #endif
