@@ -298,6 +298,9 @@ def run_ours(args):
                          "largest_kernel_any": dom["name"],
                          "step": {"achieved": achieved, "frac": achieved / peak,
                                   "algorithmic_bytes": alg_bytes,
+                                  # secondary figure of SURVEY 8d: 5 N log2 N flops per (un-pruned)
+                                  # inverse transform of the reference algorithm, per second
+                                  "nominal_fp64_tflops": S * 5.0 * N0 * np.log2(N0) / (ms_max * 1e-3) / 1e12,
                                   "note": "whole step: forward FFT + all per-scale inverse transforms"},
                          "kernels": {k["name"]: {"launches": k["launches"], "ms": round(k["ms"], 4),
                                                  "rows": k["rows"]} for k in prof}},

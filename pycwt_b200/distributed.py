@@ -101,3 +101,26 @@ def wct_significance_sharded(al1, al2, dt, dj, s0, J, significance_level=0.95, w
                             range(lo, hi), progress=False, engine=engine)
     hist = sum_over_ranks(hist, dist, device)
     return wv._mc_levels(prob, hist, significance_level)
+
+
+def cwt_scale_sharded(signal, dt, scales, family, param, precision, engine, dist=None, device=None,
+                      fetch=False):
+    """One long signal, scales block-partitioned over the ranks.  Every rank
+    holds the signal and runs its own forward transform (0.04 ms at N = 2^20 -- cheaper than
+    broadcasting the 16 MiB spectrum), then transforms only its slab of scales, which stays
+    resident in that GPU's HBM.  No collective on the data path; the per-scale global power
+    (mean_n |W|^2, [S]) is all-gathered so that every rank sees the whole spectrum.
+
+    Returns (lo, hi, global_power[S], W_slab or None): rows [lo, hi) are this rank's scales."""
+    rank = 0 if dist is None else dist.get_rank()
+    world = 1 if dist is None else dist.get_world_size()
+    scales = np.ascontiguousarray(scales, dtype=np.float64)
+    lo, hi = shard_range(scales.size, rank, world)
+    W = None
+    if hi > lo:
+        W = engine.cwt(signal, dt, scales[lo:hi], family, param, precision, fetch=fetch)
+        local = engine.global_power(hi - lo)
+    else:
+        local = np.zeros(0)
+    power = gather_rows(local.reshape(-1, 1), scales.size, dist, device).ravel()
+    return lo, hi, power, W

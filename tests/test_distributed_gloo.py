@@ -83,7 +83,11 @@ def _mc_worker(rank, world, port, q):
         eng = _engine.Engine(0, lib_path=os.path.join(ROOT, "tests", "_emu", "libcwtb200_emu.so"))
         sig = D.wct_significance_sharded(0.2, 0.1, 1.0, 0.5, 2.0, 8, 0.95, 'morlet', mc_count=5,
                                          seed=42, engine=eng, dist=dist)
-        q.put((rank, sig.tolist()))
+        # one signal, scales sharded over the ranks; the global spectrum is gathered
+        x = np.random.RandomState(5).randn(3000)
+        sj = 2.0 * 2 ** (np.arange(13) / 2.0)
+        lo, hi, power, W = D.cwt_scale_sharded(x, 1.0, sj, 0, 6.0, 0, eng, dist, fetch=True)
+        q.put((rank, sig.tolist(), (lo, hi), power.tolist(), np.abs(W).sum()))
         eng.close()
     finally:
         dist.destroy_process_group()
@@ -111,9 +115,21 @@ def test_sharded_wct_significance_gloo():
     procs = [ctx.Process(target=_mc_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = dict(q.get(timeout=300) for _ in procs)
+    got = [q.get(timeout=300) for _ in procs]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
+    res = {g[0]: g for g in got}
     for r in (0, 1):
-        assert np.array_equal(np.array(res[r]), single, equal_nan=True)
+        assert np.array_equal(np.array(res[r][1]), single, equal_nan=True)
+    # scale-sharded single signal: slabs [0,7) and [7,13), identical gathered spectrum that
+    # matches the oracle
+    from oracle import cwt_oracle as orc
+    x = np.random.RandomState(5).randn(3000)
+    sj = 2.0 * 2 ** (np.arange(13) / 2.0)
+    Wr = orc.cwt(x, 1.0, wavelet=orc.Morlet(6), freqs=1 / (orc.Morlet(6).flambda() * sj))[0]
+    ref = (np.abs(Wr) ** 2).mean(axis=1)
+    assert res[0][2] == (0, 7) and res[1][2] == (7, 13)
+    for r in (0, 1):
+        assert np.allclose(res[r][3], ref, rtol=1e-12)
+    assert abs(res[0][4] + res[1][4] - np.abs(Wr).sum()) < 1e-9 * np.abs(Wr).sum()
