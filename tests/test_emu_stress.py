@@ -54,3 +54,51 @@ def test_random_transforms(emu, seed):
         assert err < (1e-10 if prec == 0 else 3e-5), (n0, dt, fam, par, S, prec, err)
         checked += 1
     assert checked > 40
+
+
+@pytest.mark.parametrize("seed", [21, 22])
+def test_random_unpadded_transforms(emu, seed):
+    """Same sweep for the un-padded policy (helpers.py:15-19): transform length = n0, any n0
+    (odd, prime, smooth), through the Bluestein path; plus the any-length DFT hook."""
+    rs = np.random.RandomState(seed)
+    emu.set_padding(False)
+    try:
+        checked = 0
+        for _ in range(40):
+            n0 = max(3, int(2 ** rs.uniform(1.6, 13.5)))
+            dt = float(10 ** rs.uniform(-2, 2))
+            fam = rs.randint(3)
+            if fam == 0:
+                par = float(rs.choice([6, 6, 4.5, 8, 12]))
+                mo = orc.Morlet(par)
+            elif fam == 1:
+                par = int(rs.choice([4, 1, 2, 6]))
+                mo = orc.Paul(par)
+            else:
+                par = int(rs.choice([2, 1, 3, 6]))
+                mo = orc.DOG(par)
+            S = rs.randint(1, 12)
+            sj = dt * 2 ** rs.uniform(-1, np.log2(n0) + 2, size=S)
+            x = rs.randn(n0) * 10 ** rs.uniform(-3, 3)
+            om = 2 * np.pi * np.fft.fftfreq(n0, dt)
+            with np.errstate(all="ignore"):
+                filt = (sj[:, None] * om[1] * n0) ** .5 * np.conj(mo.psi_ft(sj[:, None] * om))
+                Wr = np.fft.ifft(np.fft.fft(x) * filt, axis=1)
+            ok = ~np.isnan(Wr).any(axis=1)
+            if not ok.any() or np.abs(Wr[ok]).max() < 1e-15 * np.abs(x).max():
+                continue
+            W = emu.cwt(x, dt, sj, fam, par, 0)
+            assert emu.padded_length() == (n0 if n0 & (n0 - 1) else n0)
+            err = np.abs(W[ok] - Wr[ok]).max() / np.abs(Wr[ok]).max()
+            assert err < 1e-10, (n0, dt, fam, par, S, err)
+            spec = emu.signal_fft()
+            ref = np.fft.fft(x)[1:n0 // 2] / np.sqrt(n0)
+            if ref.size:
+                assert np.abs(spec - ref).max() <= 1e-12 * max(np.abs(ref).max(), 1e-300)
+            checked += 1
+        assert checked > 25
+        for n in rs.randint(3, 3000, size=12):
+            z = rs.randn(1, int(n)) + 1j * rs.randn(1, int(n))
+            assert np.abs(emu.fft_c2c(z, -1) - np.fft.fft(z, axis=1)).max() < 1e-12 * n
+    finally:
+        emu.set_padding(True)
