@@ -198,6 +198,16 @@ class Engine(object):
             table = np.ascontiguousarray(table, dtype=np.complex128)
             tptr = _ptr(table)
         with self.lock:
+            if fetch and table is None:
+                # transform and copy back in one call: the engine starts the device->host copy
+                # of the rows that are finished first while the remaining kernels still run
+                dtype = np.complex128 if (precision == F64 or out_f64) else np.complex64
+                W = self.result_array((sj.size, sig.size), dtype)
+                self._check(self.lib.cwtb_cwt_to_host(self.h, _ptr(sig), is32, sig.size, float(dt),
+                                                      _ptr(sj), sj.size, int(family), float(param),
+                                                      int(precision), _ptr(W), 1 if out_f64 else 0))
+                self._resident_n0 = sig.size
+                return W
             self._check(self.lib.cwtb_cwt(self.h, _ptr(sig), is32, sig.size, float(dt),
                                           _ptr(sj), sj.size, int(family), float(param),
                                           int(precision), tptr))

@@ -1483,9 +1483,13 @@ int cwtb_get_signal_fft(cwtb_ctx *c, void *out) {
   const double sc = 1.0 / std::sqrt((double)job.N);
   double *o = (double *)out;
   if (job.precision == CWTB_F64) {
-    RT(rt_d2h(out, (const double2 *)c->spec.p + 1, cnt * sizeof(double2), c->stream));
+    // scaled on the device (the host loop cost as much as the 8 MB copy at N = 2^20)
+    int e = ensure(c, c->aux, cnt * sizeof(double2));
+    if (e) return e;
+    ScaleCopyArgs sa{(const double *)((const double2 *)c->spec.p + 1), (double *)c->aux.p, (long long)(2 * cnt), sc};
+    if ((e = launch<ScaleCopyBody>(c, (unsigned)((2 * cnt + NT - 1) / NT), 1, sa))) return e;
+    RT(rt_d2h(out, c->aux.p, cnt * sizeof(double2), c->stream));
     RT(rt_sync(c->stream));
-    for (size_t i = 0; i < cnt * 2; ++i) o[i] *= sc;
   } else {
     std::vector<float> tmp(cnt * 2);
     RT(rt_d2h(tmp.data(), (const float2 *)c->spec.p + 1, cnt * sizeof(float2), c->stream));
@@ -1633,9 +1637,66 @@ static int upload_row_tables(cwtb_ctx *c, const Job &job) {
   return upload_doubles(c, c->rowd, v);
 }
 
+// rows of W written by the single-kernel classes (the chain on aux_stream): true and *r0 set if
+// they are exactly the rows [r0, S) -- the case for any ascending scale array
+static bool single_kernel_rows(const cwtb_ctx *c, const Job &job, int *r0) {
+  const int S = job.S;
+  int lo = S, cnt = 0;
+  for (const ClassRun &cl : job.classes) {
+    if (!(cl.log2K <= 10 || (cl.log2K <= c->direct_max_log2 && cl.log2K < job.log2N))) continue;
+    for (int i = cl.first; i < cl.first + cl.count; ++i) {
+      lo = std::min(lo, job.descs[i].row);
+      ++cnt;
+    }
+  }
+  if (cnt == 0 || cnt == S || lo != S - cnt) return false;
+  *r0 = lo;
+  return true;
+}
+
 int cwtb_cwt_to_host(cwtb_ctx *c, const void *signal, int signal_is_f32, int64_t n0, double dt,
                      const double *scales, int n_scales, int family, double param, int precision,
                      void *out, int out_f64) {
+  if (!c || !signal || !out) return fail(c, CWTB_ERR_ARG, "null argument");
+#ifndef CWTB_HOST_EMU
+  // fp64, analytic family, forked streams: the device->host copy of the rows the single-kernel
+  // chain produced starts as soon as that chain is done, while the two-kernel chains still run
+  if (precision == CWTB_F64 && family != CWTB_TABLE && c->two_streams && !c->profiling) {
+    int e = prepare(c, n0, dt, scales, n_scales, family, param, precision, nullptr);
+    if (e) return e;
+    const Job &job = c->job;
+    int r0 = 0;
+    if (!job.exact && job.N >= 32 && job.nbatch == 1 && single_kernel_rows(c, job, &r0)) {
+      if ((e = ensure(c, c->sig, (size_t)n0 * sizeof(double)))) return e;
+      if (signal_is_f32) {
+        std::vector<double> tmp((size_t)n0);
+        for (int64_t i = 0; i < n0; ++i) tmp[i] = (double)((const float *)signal)[i];
+        RT(rt_h2d(c->sig.p, tmp.data(), (size_t)n0 * sizeof(double), c->stream));
+        RT(rt_sync(c->stream));
+      } else {
+        RT(rt_h2d(c->sig.p, signal, (size_t)n0 * sizeof(double), c->stream));
+      }
+      c->job_dsig = c->sig.p;
+      c->job.sig_is_f32 = 0;
+      c->launches = 0;
+      RT(cudaEventRecord(c->e0, c->stream));
+      if ((e = run_job<double>(c, job, (const double *)c->sig.p))) return e;
+      RT(cudaEventRecord(c->e1, c->stream));
+      const size_t rowb = (size_t)n0 * sizeof(double2);
+      const char *W = (const char *)c->W.p;
+      RT(cudaStreamWaitEvent(c->copy_streams[0], c->ev_join, 0));   // single-kernel chain done
+      RT(rt_d2h((char *)out + (size_t)r0 * rowb, W + (size_t)r0 * rowb, (size_t)(n_scales - r0) * rowb, c->copy_streams[0]));
+      RT(rt_d2h(out, W, (size_t)r0 * rowb, c->stream));               // after every chain has joined
+      RT(rt_sync(c->copy_streams[0]));
+      RT(rt_sync(c->stream));
+      float ms = 0;
+      RT(cudaEventElapsedTime(&ms, c->e0, c->e1));
+      c->last_ms = ms;
+      return 0;
+    }
+    // not eligible: fall through to the plain sequence (prepare runs again, cheap)
+  }
+#endif
   int e = cwtb_cwt(c, signal, signal_is_f32, n0, dt, scales, n_scales, family, param, precision, nullptr);
   if (e) return e;
   return cwtb_get_w(c, out, out_f64, 0, n_scales);

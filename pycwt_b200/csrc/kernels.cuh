@@ -990,6 +990,18 @@ struct R2CBody {
   }
 };
 
+// ---- Body: out[i] = in[i] * f ------------------------------------------------------------
+struct ScaleCopyArgs { const double *in; double *out; long long count; double f; };
+struct ScaleCopyBody {
+  using Args = ScaleCopyArgs;
+  static constexpr int NPHASE = 1;
+  static constexpr size_t SMEM = 0;
+  template <int PH> HD static void phase(const Args &a, int bx, int, int tid, void *) {
+    const long long i = (long long)bx * NT + tid;
+    if (i < a.count) a.out[i] = a.in[i] * a.f;
+  }
+};
+
 // ---- Body: complex64 -> complex128 (fp32 transforms returned through the reference API) ----
 struct WidenArgs { const float2 *in; double2 *out; long long count; };
 struct WidenBody {

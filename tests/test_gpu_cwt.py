@@ -308,3 +308,20 @@ def test_unpadded_long_signal_and_any_length_dft(pycwt):
     assert relerr(W[rows], np.fft.ifft(xh * filt, axis=1)) < TOL64
     Wp = pycwt.cwt(x, 1.0, 0.5, 2.0, 24, pycwt.Morlet(6))[0]
     assert relerr(Wp[rows], W[rows]) > 1e-6      # padded and un-padded differ at the edges
+
+
+def test_overlapped_fetch_equals_plain_fetch(pycwt):
+    """Engine.cwt(fetch=True) copies the rows of the single-kernel chain back while the two-kernel
+    chains still run; the result must be bit-identical to transform-then-fetch."""
+    eng = pycwt.default_engine()
+    n = 2 ** 17
+    x = chirp(n) + 0.05 * np.random.RandomState(8).randn(n)
+    sj = 2.0 * 2 ** (np.arange(0, 120) / 8.0)          # every class, ascending scales
+    W1 = eng.cwt(x, 1.0, sj, 0, 6.0)
+    eng.cwt(x, 1.0, sj, 0, 6.0, fetch=False)
+    W2 = eng.get_w(sj.size, n)
+    assert np.array_equal(W1, W2)
+    perm = np.random.RandomState(9).permutation(sj.size)  # unordered scales: plain sequence
+    W3 = eng.cwt(x, 1.0, sj[perm], 0, 6.0)
+    assert np.array_equal(W3, W1[perm])
+    assert eng.last_kernel_ms() > 0
