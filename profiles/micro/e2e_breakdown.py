@@ -10,6 +10,7 @@ x = np.sin(2 * np.pi * (50 * t + (N / 8) * t ** 2))
 sj = 2.0 * 2 ** (np.arange(256) / 16.0)
 for _ in range(3):
     W, *_ = pycwt.cwt(x, 1.0, 1 / 16, 2.0, 255, pycwt.Morlet(6))
+del W, _   # a held result keeps its 4.3 GB pinned buffer out of the pool (two circulate below)
 def tm(f, n=5):
     f(); t0 = time.perf_counter()
     for _ in range(n): r = f()
