@@ -53,3 +53,12 @@ print("peak of the global wavelet spectrum at period %.2f yr" % period[np.argmax
 print("2-8 yr scale-averaged variance: max %.3f degC^2, 95%% level %.3f" % (std ** 2 * scale_avg.max(), scale_avg_signif))
 eng = wavelet.default_engine()
 print("engine: %s, kernels of the cwt call above: %d launches" % (eng.version(), eng.last_launch_count()))
+
+# The same products without moving the coefficient array to the host (B200 extension):
+r = wavelet.cwt_resident(dat_norm, dt, dj, s0, J, mother)
+assert np.allclose(r.global_power(), glbl_power, rtol=1e-12)
+assert np.allclose(r.scale_avg_power(2, 8), scale_avg, rtol=1e-12)
+assert np.allclose(r.icwt() * std, iwave, rtol=1e-12, atol=1e-12)
+print("device-resident handle: global spectrum, 2-8 yr average and reconstruction agree with the "
+      "host arithmetic; inside-COI global spectrum peak at %.2f yr"
+      % period[np.nanargmax(r.global_power(inside_coi=True))])
