@@ -165,7 +165,9 @@ class Engine(object):
             self._pool_bytes -= nbytes
         else:
             p = _P()
-            self._check(self.lib.cwtb_host_alloc(self.h, nbytes, ctypes.byref(p)))
+            if self.lib.cwtb_host_alloc(self.h, nbytes, ctypes.byref(p)) != 0 or not p.value:
+                # page-locked memory exhausted: an ordinary array still works, the copy is slower
+                return np.empty(shape, dtype=dtype)
             addr = p.value
         buf = (ctypes.c_char * nbytes).from_address(addr)
         self._outstanding += 1
