@@ -22,7 +22,6 @@ Each function cites the reference lines it restates (paths relative to
 (scipy.fftpack -> scipy.fft / DUCC, unpinned version; scipy 1.18.1 here); any
 exact FFT agrees to ~1e-15*log2(N), we use scipy.fft.
 """
-import math
 
 import numpy as np
 import scipy.fft as _sfft

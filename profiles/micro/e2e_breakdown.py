@@ -2,7 +2,6 @@
 import os, sys, time, ctypes, numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import pycwt_b200 as pycwt
-from pycwt_b200 import _engine
 eng = pycwt.default_engine()
 N = 2 ** 20
 t = np.arange(N) / N

@@ -2,7 +2,6 @@
 import os, sys, time, numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import pycwt_b200 as pycwt
-from pycwt_b200 import helpers
 eng = pycwt.default_engine()
 for n in (100000, 1000000):
     t = np.arange(n) / n

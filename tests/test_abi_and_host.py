@@ -4,12 +4,11 @@ host-side O(S) logic (scale resolution, NaN-row prediction, significance, helper
 the reference fixtures."""
 import os
 import re
-import ctypes
 
 import numpy as np
 import pytest
 
-from conftest import ROOT, load_golden, relerr
+from conftest import ROOT, load_golden
 
 import pycwt_b200 as pycwt
 from pycwt_b200 import _engine, build as _build
