@@ -102,3 +102,76 @@ def test_random_unpadded_transforms(emu, seed):
             assert np.abs(emu.fft_c2c(z, -1) - np.fft.fft(z, axis=1)).max() < 1e-12 * n
     finally:
         emu.set_padding(True)
+
+
+@pytest.mark.parametrize("seed", [31, 32])
+def test_random_pairs_smoothing_and_batches(emu, seed):
+    """Randomised shapes through the cross-wavelet, coherence, smoothing and batched entry
+    points (both transform-length policies), against the oracle."""
+    rs = np.random.RandomState(seed)
+    m = orc.Morlet(6)
+    for it in range(14):
+        pad = bool(rs.rand() < 0.6)
+        emu.set_padding(pad)
+        orc.PAD_NEXT_POW2 = pad
+        try:
+            n = int(2 ** rs.uniform(4.5, 12.5))
+            dt = float(10 ** rs.uniform(-1, 1))
+            dj = float(rs.choice([0.5, 0.25, 1 / 6]))
+            s0 = 2 * dt
+            J = int(rs.randint(4, int(np.log2(n) / dj)))
+            sj = s0 * 2 ** (np.arange(J + 1) * dj)
+            y1 = rs.randn(n).cumsum()
+            y2 = np.roll(y1, 3) + rs.randn(n)
+            klen = int(np.round(m.deltaj0 / dj * 2))
+            # xwt: W1 conj(W2)
+            W12 = emu.xwt(y1, y2, dt, sj, 0, 6.0)
+            W1 = orc.cwt(y1, dt, wavelet=m, freqs=1 / (m.flambda() * sj))[0]
+            W2 = orc.cwt(y2, dt, wavelet=m, freqs=1 / (m.flambda() * sj))[0]
+            ref = W1 * W2.conj()
+            assert np.abs(W12 - ref).max() < 1e-10 * np.abs(ref).max(), (it, n, pad)
+            # smoothing operator on its own (complex and real input)
+            S = emu.smooth(ref, dt, sj, klen)
+            Sr = m.smooth(ref, dt, dj, sj)
+            assert np.abs(S - Sr).max() < 1e-10 * np.abs(Sr).max(), (it, n, pad)
+            P = np.abs(W1) ** 2
+            assert np.abs(emu.smooth(P, dt, sj, klen) - m.smooth(P, dt, dj, sj)).max() < 1e-10 * P.max()
+            # coherence
+            WCT, aWCT = emu.wct(y1, y2, dt, dj, sj, 0, 6.0, klen)
+            inv = 1 / sj[:, None]
+            R = np.abs(m.smooth(ref * inv, dt, dj, sj)) ** 2 / (
+                m.smooth(np.abs(W1) ** 2 * inv, dt, dj, sj) * m.smooth(np.abs(W2) ** 2 * inv, dt, dj, sj))
+            assert np.abs(WCT - R).max() < 1e-8, (it, n, pad, np.abs(WCT - R).max())
+            assert np.abs(np.exp(1j * aWCT) - np.exp(1j * np.angle(ref))).max() < 1e-8
+            # batched channels (padded policy only) equal per-channel transforms
+            if pad and n >= 32:
+                X = rs.randn(3, n)
+                power, Wb = emu.cwt_batch(X, dt, sj, 0, 6.0, 0, want_power=True, want_w=True)
+                for ch in range(3):
+                    Wc = orc.cwt(X[ch], dt, wavelet=m, freqs=1 / (m.flambda() * sj))[0]
+                    assert np.abs(Wb[ch] - Wc).max() < 1e-10 * np.abs(Wc).max()
+                    assert np.allclose(power[ch], (np.abs(Wc) ** 2).mean(axis=1), rtol=1e-10)
+        finally:
+            emu.set_padding(True)
+            orc.PAD_NEXT_POW2 = True
+
+
+def test_random_cross_wavelet_all_families(emu):
+    rs = np.random.RandomState(41)
+    for it in range(12):
+        n = int(2 ** rs.uniform(4.5, 13))
+        dt = float(10 ** rs.uniform(-1, 1))
+        fam = int(rs.randint(3))
+        par, mo = [(6.0, orc.Morlet(6)), (4, orc.Paul(4)), (2, orc.DOG(2))][fam]
+        if rs.rand() < 0.3:
+            par, mo = [(8.0, orc.Morlet(8)), (2, orc.Paul(2)), (5, orc.DOG(5))][fam]
+        sj = (2 * dt / mo.flambda()) * 2 ** (np.arange(int(rs.randint(3, 20))) * 0.5)
+        y1, y2 = rs.randn(n), rs.randn(n).cumsum()
+        W12 = emu.xwt(y1, y2, dt, sj, fam, par)
+        with np.errstate(all="ignore"):
+            W1 = orc.cwt(y1, dt, wavelet=mo, freqs=1 / (mo.flambda() * sj))
+            W2 = orc.cwt(y2, dt, wavelet=mo, freqs=1 / (mo.flambda() * sj))
+        if W1[0].shape[0] != sj.size:      # Paul rows the reference drops: not the point here
+            continue
+        ref = W1[0] * W2[0].conj()
+        assert np.abs(W12 - ref).max() < 1e-10 * np.abs(ref).max(), (it, n, fam, par)
