@@ -58,8 +58,9 @@ const char *cwtb_last_error(cwtb_ctx *ctx);
 const char *cwtb_version(void);
 
 /* Relative cut-off below which the analytic frequency response is treated as
- * zero when the per-scale band is pruned (default 1e-20, i.e. far below fp64
- * rounding of the transform itself).  eps = 0 keeps every bin whose response
+ * zero when the per-scale band is pruned (default 1e-16: at the level of the fp64
+ * rounding of the transform itself -- parity against the reference fixtures is the
+ * same 5e-16 as with 1e-20, profiles/r1/eps_parity_r1.txt).  eps = 0 keeps every bin whose response
  * is representable (the reference's own underflow-to-zero set). */
 int cwtb_set_band_eps(cwtb_ctx *ctx, double eps);
 /* Transform-length policy of pycwt/helpers.py:7-30.  pad_to_pow2 != 0 (default): the signal is

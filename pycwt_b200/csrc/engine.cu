@@ -145,7 +145,7 @@ struct cwtb_ctx {
   rt_stream copy_streams[4]{};   // large D2H copies are split over several streams / copy engines
   int d2h_split = 1;             // CWTB_D2H_SPLIT
   std::string err;
-  double band_eps = 1e-20;
+  double band_eps = 1e-16;
   int group = 0;   // rows per two-kernel chunk; 0 = as many as fit in group_bytes of Z (CWTB_GROUP)
   size_t group_bytes = (size_t)512 << 20;
   int l2_persist = 0;

@@ -154,7 +154,7 @@ def test_band_eps_exact_mode_matches(pycwt):
     try:
         W1 = eng.cwt(x, 1.0, sj, 0, 6.0)
     finally:
-        eng.set_band_eps(1e-20)
+        eng.set_band_eps(1e-16)
     assert relerr(W0, W1) < 1e-14
     Wr = orc.cwt(x, 1.0, dj=0.25, s0=2.0, J=39, wavelet=orc.Morlet(6))[0]
     assert relerr(W1, Wr) < TOL64
