@@ -1,0 +1,112 @@
+"""Public-API sweeps on the host-emulation build (CPU; see tests/test_emu_kernels.py for what
+that build is): every return value of `cwt` for tiny and awkward lengths under both
+transform-length policies, unordered custom frequencies, list / float32 input, both `icwt`
+orientations, special signals and the reference's exception types -- against the oracle."""
+import warnings
+
+import numpy as np
+import pytest
+from scipy.signal import lfilter
+
+from conftest import ROOT
+from oracle import cwt_oracle as orc
+
+
+@pytest.fixture(scope="module")
+def api():
+    import os
+    import pycwt_b200 as pycwt
+    from pycwt_b200 import build as _build, _engine
+    eng = _engine.Engine(0, lib_path=_build.build_emulation(os.path.join(ROOT, "tests", "_emu")))
+    saved = _engine.default_engine
+    _engine.default_engine = lambda *a, **k: eng
+    yield pycwt
+    _engine.default_engine = saved
+    eng.close()
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.mark.parametrize("pad", [True, False])
+def test_every_output_for_tiny_and_awkward_lengths(api, pad):
+    from pycwt_b200 import helpers
+    rs = np.random.RandomState(123)
+    helpers.set_fft_padding(pad)
+    orc.PAD_NEXT_POW2 = pad
+    try:
+        for n0 in list(range(2, 41)) + [63, 64, 65, 100, 127, 128, 129]:
+            x = rs.randn(n0)
+            for mo, mr in ((api.Morlet(6), orc.Morlet(6)), (api.Paul(4), orc.Paul(4)),
+                           (api.DOG(2), orc.DOG(2)), (api.DOG(3), orc.DOG(3))):
+                with np.errstate(all="ignore"), warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    try:
+                        r = orc.cwt(x, 0.5, dj=0.5, wavelet=mr)
+                    except Exception:
+                        with pytest.raises(Exception):
+                            api.cwt(x, 0.5, dj=0.5, wavelet=mo)
+                        continue
+                    g = api.cwt(x, 0.5, dj=0.5, wavelet=mo)
+                tag = (pad, n0, type(mo).__name__)
+                assert r[0].shape == g[0].shape, tag
+                fin = np.isfinite(r[0])
+                assert np.array_equal(fin, np.isfinite(g[0])), tag
+                if fin.any():
+                    assert rel(g[0][fin], r[0][fin]) < 1e-10, tag
+                for k in (1, 2, 3, 5):      # sj, freqs, coi, fftfreqs: bit-identical host outputs
+                    assert np.array_equal(r[k], g[k]), (tag, k)
+                if r[4].size:
+                    assert np.abs(r[4] - g[4]).max() <= 1e-12 * max(np.abs(r[4]).max(), 1e-300), tag
+    finally:
+        helpers.set_fft_padding(True)
+        orc.PAD_NEXT_POW2 = True
+
+
+def test_api_corners(api):
+    warnings.filterwarnings("ignore")
+    rs = np.random.RandomState(7)
+    for it in range(12):
+        n = int(2 ** rs.uniform(5, 13))
+        dt = float(10 ** rs.uniform(-1, 1))
+        x = rs.randn(n).cumsum()
+        fam = rs.randint(3)
+        mo, mr = [(api.Morlet(6), orc.Morlet(6)), (api.Paul(4), orc.Paul(4)), (api.DOG(2), orc.DOG(2))][fam]
+        name = ["morlet", "paul", "dog"][fam]
+        fr = rs.uniform(2 / (n * dt), 0.4 / dt, size=rs.randint(1, 30))     # unordered, non-geometric
+        g, r = api.cwt(x, dt, wavelet=mo, freqs=fr), orc.cwt(x, dt, wavelet=mr, freqs=fr)
+        assert g[0].shape == r[0].shape and rel(g[0], r[0]) < 1e-10
+        g2, r2 = api.cwt(list(x), dt, dj=0.5, wavelet=name), orc.cwt(list(x), dt, dj=0.5, wavelet=name)
+        assert rel(g2[0], r2[0]) < 1e-10
+        if mr.cdelta != -1:
+            assert rel(api.icwt(g2[0], g2[1], dt, 0.5, name), orc.icwt(r2[0], r2[1], dt, 0.5, name)) < 1e-10
+            if g2[0].shape[0] != g2[0].shape[1]:     # (N, S) input: the reference still sums axis 0
+                a = api.icwt(g2[0].T.copy(), g2[1], dt, 0.5, name)
+                b = orc.icwt(r2[0].T.copy(), r2[1], dt, 0.5, name)
+                assert a.shape == b.shape and rel(a, b) < 1e-10
+        xs = lfilter([1], [1, -0.6], rs.randn(n))
+        y2 = np.roll(xs, 5) + rs.randn(n)
+        a = api.xwt(xs, y2, dt, dj=0.5, wavelet=name, normalize=False)
+        b = orc.xwt(xs, y2, dt, dj=0.5, wavelet=name, normalize=False)
+        assert rel(a[0], b[0]) < 1e-10 and np.allclose(a[3], b[3], rtol=1e-12)
+        x32 = x.astype(np.float32)
+        assert rel(api.cwt(x32, dt, dj=0.5, wavelet=name)[0],
+                   orc.cwt(x32.astype(np.float64), dt, dj=0.5, wavelet=name)[0]) < 1e-10
+
+
+def test_special_signals_and_exception_types(api):
+    for x in (np.zeros(100), np.ones(257), np.r_[np.zeros(50), 1e300, np.zeros(50)],
+              np.r_[1.0, np.inf, np.zeros(30)], np.r_[np.nan, np.ones(20)]):
+        with np.errstate(all="ignore"):
+            g, r = api.cwt(x, 1.0, dj=0.5)[0], orc.cwt(x, 1.0, dj=0.5)[0]
+        assert np.array_equal(np.isfinite(g), np.isfinite(r))
+        f = np.isfinite(r)
+        if f.any() and np.abs(r[f]).max() > 0:
+            assert rel(g[f], r[f]) < 1e-10
+    with pytest.raises(KeyError):
+        api.cwt(np.ones(64), 1.0, wavelet="nope")
+    with pytest.raises(AttributeError):
+        api.wct(np.ones(64), np.ones(64), 1.0, wavelet="paul", sig=False)
+    with pytest.raises(Warning):
+        api.icwt(np.ones((5, 7)), np.ones(3), 1.0)
