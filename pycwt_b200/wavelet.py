@@ -51,10 +51,11 @@ def _nan_rows(wavelet, sj, npad, dt):
     """Rows the reference would find all-NaN (wavelet.py:111): psi_ft evaluates to NaN at
     some bin (Paul: inf*0 once s*pi/dt > 709.78).  Evaluated at the two extreme bins, where
     overflow happens first; O(S) host work."""
-    # the two entries of fft.fftfreq(npad, dt) at those bins (k / (npad*dt) with the signed bin
-    # number k, computed like numpy does: k * (1.0 / (npad * dt))) without building the array
-    idx = np.array([npad // 2, max(npad // 2 - 1, 0)])
-    k = np.where(idx < (npad + 1) // 2, idx, idx - npad)
+    # the entries of fft.fftfreq(npad, dt) at the most negative and the most positive bin
+    # (k / (npad*dt) with the signed bin number k, computed like numpy does:
+    # k * (1.0 / (npad * dt))) without building the array.  Any npad: for an odd length the
+    # most negative bin is -(npad-1)/2 at index (npad+1)/2.
+    k = np.array([-(npad // 2), (npad - 1) // 2])
     edge = 2 * np.pi * (k * (1.0 / (npad * dt)))
     with np.errstate(all='ignore'):
         resp = wavelet.psi_ft(sj[:, None] * edge[None, :])

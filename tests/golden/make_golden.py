@@ -159,6 +159,8 @@ def main():
         cwt_case("nopad_nino3_morlet", nino, 0.25, "morlet", 6, dj=0.25, s0=0.5, J=28)
         cwt_case("nopad_nino3_paul", nino, 0.25, "paul", 4, dj=0.25)
         cwt_case("nopad_nino3_dog3", nino, 0.25, "dog", 3, dj=0.5)
+        # odd length + Paul: the all-NaN rows come from the most negative bin, -(n-1)/2
+        cwt_case("nopad_nino501_paul", nino[:501], 0.25, "paul", 4, dj=0.25)
         x = chirp(4001) + 0.1 * np.random.RandomState(3).randn(4001)      # odd length
         cwt_case("nopad_chirp4001_morlet", x, 1.0, "morlet", 6, stride=8, dj=1 / 8, s0=2.0, J=72)
         cwt_case("nopad_chirp3000_dog", x[:3000], 1.0, "dog", 2, stride=8, dj=1 / 4, s0=0.5033, J=40)

@@ -110,3 +110,57 @@ def test_special_signals_and_exception_types(api):
         api.wct(np.ones(64), np.ones(64), 1.0, wavelet="paul", sig=False)
     with pytest.raises(Warning):
         api.icwt(np.ones((5, 7)), np.ones(3), 1.0)
+
+
+def test_resident_handle_random(api):
+    """Derived products of the device-resident handle for random lengths, families and both
+    length policies (incl. odd un-padded lengths where Paul rows are dropped) vs the oracle."""
+    from pycwt_b200 import helpers
+    warnings.filterwarnings("ignore")
+    rs = np.random.RandomState(17)
+    checked = 0
+    try:
+        for it in range(40):
+            pad = bool(rs.rand() < 0.5)
+            helpers.set_fft_padding(pad)
+            orc.PAD_NEXT_POW2 = pad
+            n = int(2 ** rs.uniform(3, 12))
+            dt = float(10 ** rs.uniform(-1, 1))
+            x = rs.randn(n)
+            fam = rs.randint(3)
+            mo, mr = [(api.Morlet(6), orc.Morlet(6)), (api.Paul(4), orc.Paul(4)), (api.DOG(2), orc.DOG(2))][fam]
+            dj = float(rs.choice([0.5, 0.25, 0.125]))
+            try:
+                with np.errstate(all="ignore"):
+                    W, sj, fr, coi, _, _ = orc.cwt(x, dt, dj=dj, wavelet=mr)
+            except Exception:
+                continue
+            if W.size == 0 or not np.isfinite(W).all():
+                continue
+            r = api.cwt_resident(x, dt, dj, wavelet=mo)
+            tag = (it, pad, n, fam, dj)
+            P = np.abs(W) ** 2
+            assert r.shape == W.shape, tag
+            assert np.array_equal(r.scales, sj) and np.array_equal(r.coi, coi), tag
+            assert rel(r.power(), P) < 1e-10 and rel(r.power(rectify=True), P / sj[:, None]) < 1e-10, tag
+            assert rel(r.global_power(), P.mean(axis=1)) < 1e-10, tag
+            per = 1 / fr
+            inside = per[:, None] <= coi[None, :]
+            g = r.global_power(inside_coi=True)
+            with np.errstate(all="ignore"):
+                ref = np.where(inside.any(axis=1), (P * inside).sum(axis=1) / inside.sum(axis=1), np.nan)
+            assert np.array_equal(np.isnan(g), np.isnan(ref)), tag
+            ok = ~np.isnan(ref)
+            if ok.any():
+                assert rel(g[ok], ref[ok]) < 1e-10, tag
+            lo, hi = np.percentile(per, [20, 70])
+            sel = (per >= lo) & (per < hi)
+            want = 2.0 * dj * dt / mr.cdelta * (P / sj[:, None])[sel].sum(axis=0)
+            assert np.abs(r.scale_avg_power(lo, hi, variance=2.0) - want).max() <= 1e-10 * max(np.abs(want).max(), 1e-300), tag
+            assert rel(r.icwt(), orc.icwt(W, sj, dt, dj, mr)) < 1e-10, tag
+            assert rel(r.wave(), W) < 1e-10, tag
+            checked += 1
+    finally:
+        helpers.set_fft_padding(True)
+        orc.PAD_NEXT_POW2 = True
+    assert checked > 25

@@ -191,7 +191,7 @@ def check_unpadded_mode(eng, tol):
     from pycwt_b200 import helpers
     helpers.set_fft_padding(False)
     try:
-        for name in ["nopad_nino3_morlet", "nopad_nino3_paul", "nopad_nino3_dog3",
+        for name in ["nopad_nino3_morlet", "nopad_nino3_paul", "nopad_nino501_paul", "nopad_nino3_dog3",
                      "nopad_chirp4001_morlet", "nopad_chirp3000_dog"]:
             g = load_golden(name)
             cls = {"morlet": pycwt.Morlet, "paul": pycwt.Paul, "dog": pycwt.DOG}[str(g["wavelet"])]

@@ -39,7 +39,7 @@ def test_cwt_matches_reference(name):
         assert relerr(iW, g["iW"]) < max(tol, 1e-12)
 
 
-NOPAD_CASES = ["nopad_nino3_morlet", "nopad_nino3_paul", "nopad_nino3_dog3",
+NOPAD_CASES = ["nopad_nino3_morlet", "nopad_nino3_paul", "nopad_nino501_paul", "nopad_nino3_dog3",
                "nopad_chirp4001_morlet", "nopad_chirp3000_dog"]
 
 
