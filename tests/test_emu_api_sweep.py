@@ -164,3 +164,88 @@ def test_resident_handle_random(api):
         helpers.set_fft_padding(True)
         orc.PAD_NEXT_POW2 = True
     assert checked > 25
+
+
+class _Duck(object):
+    """A mother wavelet the engine does not recognise: forces the host-table path."""
+    def __init__(self, m):
+        self.m = m
+
+    def __getattr__(self, k):
+        if k == '_engine_spec':
+            raise AttributeError(k)
+        return getattr(self.m, k)
+
+
+def test_table_path_and_fp32_engine_random(api, monkeypatch):
+    from pycwt_b200 import helpers
+    warnings.filterwarnings("ignore")
+    rs = np.random.RandomState(5)
+    try:
+        for it in range(40):
+            pad = bool(rs.rand() < 0.6)
+            helpers.set_fft_padding(pad)
+            orc.PAD_NEXT_POW2 = pad
+            n = int(2 ** rs.uniform(1.2, 11))
+            dt = float(10 ** rs.uniform(-1, 1))
+            x = rs.randn(n)
+            fam = rs.randint(3)
+            mo, mr = [(api.Morlet(6), orc.Morlet(6)), (api.Paul(4), orc.Paul(4)), (api.DOG(2), orc.DOG(2))][fam]
+            try:
+                with np.errstate(all="ignore"):
+                    r = orc.cwt(x, dt, dj=0.5, wavelet=mr)
+            except Exception:
+                continue
+            if r[0].size == 0:
+                continue
+            fin = np.isfinite(r[0])
+            tag = (it, pad, n, fam)
+            g = api.cwt(x, dt, dj=0.5, wavelet=_Duck(mo))
+            assert g[0].shape == r[0].shape, tag
+            if fin.any():
+                assert rel(g[0][fin], r[0][fin]) < 1e-10, tag
+            x32 = x.astype(np.float32)
+            r32 = orc.cwt(x32.astype(np.float64), dt, dj=0.5, wavelet=mr)
+            f2 = np.isfinite(r32[0])
+            monkeypatch.setenv("CWTB_PRECISION", "fp32")
+            try:
+                g32 = api.cwt(x32, dt, dj=0.5, wavelet=mo)
+                gd = api.cwt(x32, dt, dj=0.5, wavelet=_Duck(mo))
+            finally:
+                monkeypatch.delenv("CWTB_PRECISION")
+            assert g32[0].shape == r32[0].shape and g32[0].dtype == np.complex128, tag
+            if f2.any() and np.abs(r32[0][f2]).max() > 1e-30:
+                assert rel(g32[0][f2], r32[0][f2]) < 3e-5, tag
+                assert rel(gd[0][f2], r32[0][f2]) < 3e-5, tag
+    finally:
+        helpers.set_fft_padding(True)
+        orc.PAD_NEXT_POW2 = True
+
+
+def test_coherence_api_random(api):
+    from pycwt_b200 import helpers
+    warnings.filterwarnings("ignore")
+    rs = np.random.RandomState(77)
+    try:
+        for it in range(16):
+            pad = bool(rs.rand() < 0.5)
+            helpers.set_fft_padding(pad)
+            orc.PAD_NEXT_POW2 = pad
+            n = int(2 ** rs.uniform(5, 11))
+            dt = float(10 ** rs.uniform(-1, 1))
+            y1 = lfilter([1], [1, -0.5], rs.randn(n))
+            y2 = np.roll(y1, 2) + 0.7 * rs.randn(n)
+            dj = float(rs.choice([0.5, 0.25, 1 / 6, 1 / 12]))
+            kw = dict(dj=dj, sig=False, wavelet='morlet', normalize=bool(rs.rand() < 0.7))
+            if rs.rand() < 0.5:
+                kw.update(s0=2 * dt, J=int(rs.randint(3, int(np.log2(n) / dj))))
+            b = orc.wct(y1, y2, dt, **kw)
+            a = api.wct(y1, y2, dt, **kw)
+            tag = (it, pad, n, dj)
+            assert a[0].shape == b[0].shape, tag
+            assert np.abs(a[0] - b[0]).max() < 1e-8, tag
+            assert np.abs(np.exp(1j * a[1]) - np.exp(1j * b[1])).max() < 1e-7, tag
+            assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3]), tag
+    finally:
+        helpers.set_fft_padding(True)
+        orc.PAD_NEXT_POW2 = True
