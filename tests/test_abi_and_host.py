@@ -158,3 +158,34 @@ def test_cache_key_and_dir(tmp_path, monkeypatch):
     np.savetxt(os.path.join(d, key + ".gz"), np.arange(13.0))
     out = pycwt.wct_significance(0.1, 0.2, 1.0, 0.25, 2.0, 12, wavelet="morlet", progress=False)
     np.testing.assert_array_equal(out, np.arange(13.0))
+
+
+def test_header_is_plain_c_and_c_example_links(tmp_path):
+    """include/cwt_b200.h compiles as C99 and as C++; the C example links against the engine
+    library and fails loudly where no device is present."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    hdr = os.path.join(ROOT, "include", "cwt_b200.h")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr],
+                   check=True)
+    subprocess.run([shutil.which("g++"), "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", hdr],
+                   check=True)
+    from pycwt_b200 import build
+    lib = build.build()
+    exe = str(tmp_path / "c_abi_example")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "c_abi_example.c"), "-L" + os.path.dirname(lib),
+                    "-l:" + os.path.basename(lib), "-lm", "-Wl,-rpath," + os.path.dirname(lib), "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    import pycwt_b200._engine as eng
+    try:
+        have = eng.device_count() > 0
+    except Exception:
+        have = False
+    if have:
+        assert r.returncode == 0 and "kernel launches" in r.stdout
+    else:
+        assert r.returncode != 0 and "cwtb_create failed" in r.stderr
