@@ -123,6 +123,19 @@ class Engine(object):
     def version(self):
         return self.lib.cwtb_version().decode()
 
+    # (rows, n0) of the transform the device holds, when the last call left a single well-defined
+    # one there; the fetch/reduction methods check their arguments against it because the C side
+    # sizes its copies from the resident job, not from the caller's arrays
+    _resident = None
+
+    def _expect_resident(self, rows=None, n0=None):
+        if self._resident is None:
+            return
+        r, n = self._resident
+        if (rows is not None and rows != r) or (n0 is not None and n0 != n):
+            raise ValueError("the resident transform is %d x %d, the call asks for %s x %s"
+                             % (r, n, "?" if rows is None else rows, "?" if n0 is None else n0))
+
     def set_band_eps(self, eps):
         self._check(self.lib.cwtb_set_band_eps(self.h, float(eps)))
 
@@ -209,17 +222,22 @@ class Engine(object):
                                                       _ptr(sj), sj.size, int(family), float(param),
                                                       int(precision), _ptr(W), 1 if out_f64 else 0))
                 self._resident_n0 = sig.size
+                self._resident = (sj.size, sig.size)
                 return W
             self._check(self.lib.cwtb_cwt(self.h, _ptr(sig), is32, sig.size, float(dt),
                                           _ptr(sj), sj.size, int(family), float(param),
                                           int(precision), tptr))
             self._resident_n0 = sig.size
+            self._resident = (sj.size, sig.size)
             if not fetch:
                 return None
             return self.get_w(sj.size, sig.size, precision, out_f64)
 
     def get_w(self, nrows, n0, precision=F64, out_f64=True):
         dtype = np.complex128 if (precision == F64 or out_f64) else np.complex64
+        self._expect_resident(None, n0)
+        if self._resident is not None and nrows > self._resident[0]:
+            raise ValueError("get_w: %d rows requested, %d resident" % (nrows, self._resident[0]))
         W = self.result_array((nrows, n0), dtype)
         self._check(self.lib.cwtb_get_w(self.h, _ptr(W), 1 if out_f64 else 0, 0, nrows))
         return W
@@ -275,6 +293,7 @@ class Engine(object):
             return out
 
     def global_power(self, nrows):
+        self._expect_resident(nrows)
         out = np.empty(nrows, dtype=np.float64)
         self._check(self.lib.cwtb_global_power(self.h, _ptr(out)))
         return out
@@ -283,6 +302,9 @@ class Engine(object):
         """Row means of |W|^2 over the column ranges [lo[j], hi[j]) (NaN where empty)."""
         lo = np.ascontiguousarray(lo, dtype=np.int64)
         hi = np.ascontiguousarray(hi, dtype=np.int64)
+        if lo.shape != hi.shape:
+            raise ValueError("global_power_ranges: lo and hi must have one entry per row")
+        self._expect_resident(lo.size)
         out = np.empty(lo.size, dtype=np.float64)
         with self.lock:
             self._check(self.lib.cwtb_global_power_ranges(self.h, _ptr(lo), _ptr(hi), _ptr(out)))
@@ -290,6 +312,7 @@ class Engine(object):
 
     def power(self, nrows, n0, row_scale=None):
         """|W|^2 of the resident transform, optionally times one factor per row."""
+        self._expect_resident(nrows, n0)
         out = self.result_array((nrows, n0), np.float64)
         with self.lock:
             if row_scale is None:
@@ -304,6 +327,7 @@ class Engine(object):
     def scale_avg_power(self, weights):
         """sum_j weights[j] |W[j, :]|^2 of the resident transform (TC98 eq. 24)."""
         w = np.ascontiguousarray(weights, dtype=np.float64)
+        self._expect_resident(w.size)
         out = np.empty(self._resident_n0, dtype=np.float64)
         with self.lock:
             self._check(self.lib.cwtb_scale_avg_power(self.h, _ptr(w), _ptr(out)))
@@ -320,6 +344,8 @@ class Engine(object):
         with self.lock:
             self._check(self.lib.cwtb_xwt(self.h, _ptr(y1), _ptr(y2), y1.size, float(dt), _ptr(sj),
                                           sj.size, int(family), float(param), _ptr(out)))
+            self._resident_n0 = y1.size
+            self._resident = (sj.size, y1.size)     # W12 stays on the device
         return out
 
     def wct(self, y1, y2, dt, dj, scales, family, param, boxcar_len, want_angle=True):
@@ -335,6 +361,7 @@ class Engine(object):
                                           _ptr(sj), sj.size, int(family), float(param),
                                           int(boxcar_len), _ptr(WCT),
                                           _ptr(aWCT) if want_angle else None))
+            self._resident = None                   # several intermediates, no single transform
         return WCT, aWCT
 
     def smooth(self, W, dt, scales, boxcar_len):
@@ -342,6 +369,10 @@ class Engine(object):
         is_c = np.iscomplexobj(W)
         W = np.ascontiguousarray(W, dtype=np.complex128 if is_c else np.float64)
         sj = np.ascontiguousarray(scales, dtype=np.float64)
+        if W.ndim != 2 or sj.ndim != 1 or sj.size != W.shape[0]:
+            # the reference fails here too (broadcast of the [S, 1] filter against W, mothers.py:87)
+            raise ValueError("smooth: W must be [scales, time] with one scale per row "
+                             "(got W %s, %d scales)" % (W.shape, sj.size))
         out = np.empty_like(W)
         with self.lock:
             self._check(self.lib.cwtb_smooth(self.h, _ptr(W), int(is_c), W.shape[0], W.shape[1],
@@ -361,6 +392,7 @@ class Engine(object):
                                              float(dt), float(dj), _ptr(sj), sj.size, int(family),
                                              float(param), int(boxcar_len), _ptr(mask),
                                              int(maxscale), int(nbins), _ptr(hist)))
+            self._resident = None
         return hist
 
     def cwt_batch(self, X, dt, scales, family, param, precision=F64, want_power=True,
@@ -380,6 +412,7 @@ class Engine(object):
                                                 float(param), int(precision),
                                                 _ptr(power) if want_power else None,
                                                 _ptr(W) if want_w else None))
+            self._resident = None                   # the last chunk of channels only
         return power, W
 
     # ---- device-resident benchmarking helpers -------------------------------------
@@ -400,6 +433,8 @@ class Engine(object):
         self._check(self.lib.cwtb_cwt_dev(self.h, dptr, int(is_f32), int(n0), float(dt),
                                           _ptr(sj), sj.size, int(family), float(param),
                                           int(precision)))
+        self._resident_n0 = int(n0)
+        self._resident = (sj.size, int(n0))
 
     def cwt_batch_dev(self, dptr, n_chan, n0, dt, scales, family, param, precision=F64,
                       want_power=False):
@@ -408,6 +443,8 @@ class Engine(object):
         self._check(self.lib.cwtb_cwt_batch_dev(self.h, dptr, int(n_chan), int(n0), float(dt),
                                                 _ptr(sj), sj.size, int(family), float(param),
                                                 int(precision), _ptr(power) if want_power else None))
+        self._resident_n0 = int(n0)
+        self._resident = (int(n_chan) * sj.size, int(n0))
         return power
 
     def bench_last(self, iters):

@@ -249,3 +249,26 @@ def test_unpadded_mode_public_api(emu, monkeypatch):
     from pycwt_b200 import _engine
     monkeypatch.setattr(_engine, "default_engine", lambda *a, **k: emu)
     check_unpadded_mode(emu, 1e-12)
+
+
+def test_python_side_shape_guards(emu):
+    """The C side sizes its copies from the resident job; the ctypes layer refuses calls whose
+    array shapes disagree with it instead of letting them overrun."""
+    x = np.random.RandomState(0).randn(100)
+    sj = np.array([2.0, 4.0, 8.0])
+    emu.cwt(x, 1.0, sj, 0, 6.0, fetch=False)
+    with pytest.raises(ValueError):
+        emu.get_w(3, 64)                 # wrong column count
+    with pytest.raises(ValueError):
+        emu.get_w(4, 100)                # more rows than resident
+    with pytest.raises(ValueError):
+        emu.global_power(5)
+    with pytest.raises(ValueError):
+        emu.power(3, 99)
+    with pytest.raises(ValueError):
+        emu.scale_avg_power(np.ones(2))
+    with pytest.raises(ValueError):
+        emu.global_power_ranges(np.zeros(3), np.ones(4))
+    with pytest.raises(ValueError):
+        emu.smooth(np.ones((4, 100)), 1.0, sj, 5)
+    assert emu.get_w(2, 100).shape == (2, 100) and emu.global_power(3).shape == (3,)
