@@ -30,6 +30,7 @@ _SIGNATURES = {
     "cwtb_last_error": (ctypes.c_char_p, [_P]),
     "cwtb_version": (ctypes.c_char_p, []),
     "cwtb_set_band_eps": (_I, [_P, _D]),
+    "cwtb_set_expand_eps": (_I, [_P, _D, _D]),
     "cwtb_set_padding": (_I, [_P, _I]),
     "cwtb_host_alloc": (_I, [_P, ctypes.c_size_t, ctypes.POINTER(_P)]),
     "cwtb_host_free": (_I, [_P, _P]),
@@ -86,8 +87,23 @@ def _ptr(a):
     return a.ctypes.data_as(_P)
 
 
+def _locked(method):
+    """Run an Engine method under the engine's (re-entrant) lock."""
+    import functools
+
+    @functools.wraps(method)
+    def wrapper(self, *args, **kwargs):
+        with self.lock:
+            return method(self, *args, **kwargs)
+    return wrapper
+
+
 class Engine(object):
-    """One context = one device + one stream.  Calls are serialised by a lock."""
+    """One context = one device + one stream.  Every call into the C library is made under
+    `self.lock`, a re-entrant lock: compound operations of the Python surface (set the length
+    policy, transform, fetch the coefficients, fetch the spectrum) hold it across all their
+    steps, so concurrent callers of the shared default engine cannot interleave inside one
+    another's transform (the C side keeps ONE resident job per context)."""
 
     def __init__(self, device=0, lib_path=None):
         self.lib = load_library(lib_path)
@@ -99,15 +115,47 @@ class Engine(object):
             raise EngineError("cwtb_create(device=%d) failed with status %d" % (device, rc))
         self.h = h
         self.device = device
-        self.lock = threading.Lock()
-        self._pool = {}          # nbytes -> [pointers of idle pinned buffers]
+        self.lock = threading.RLock()
+        # pinned result buffers: bookkeeping has its own small lock because buffers come back
+        # from weakref finalizers on arbitrary threads (re-entrant: a finalizer may run at any
+        # allocation point of the thread that already holds it)
+        self._pool_lock = threading.RLock()
+        self._pool = []          # idle pinned buffers, least recently released first: (nbytes, addr)
         self._pool_bytes = 0
+        self._dead = []          # retired pinned buffers waiting for _reap()
         self._outstanding = 0    # result arrays still alive that alias pinned memory
 
+    def _reap(self):
+        """Free the pinned buffers the finalizers retired.  Finalizers never call into the
+        library themselves (they can fire at any allocation point of any thread, also inside
+        this class's critical sections); the frees happen here, under the engine lock."""
+        with self._pool_lock:
+            dead, self._dead = self._dead, []
+        if dead and getattr(self, "h", None):
+            with self.lock:
+                for addr in dead:
+                    self.lib.cwtb_host_free(self.h, _P(addr))
+
+    def trim(self, keep_bytes=0):
+        """Release idle pinned result buffers until at most `keep_bytes` stay pooled."""
+        with self._pool_lock:
+            while self._pool and self._pool_bytes > keep_bytes:
+                nbytes, addr = self._pool.pop(0)
+                self._pool_bytes -= nbytes
+                self._dead.append(addr)
+        self._reap()
+
     def close(self):
-        if getattr(self, "h", None) and self._outstanding == 0:
-            self.lib.cwtb_destroy(self.h)
-            self.h = None
+        """Destroy the context.  While result arrays that alias its pinned memory are alive
+        only the idle pooled buffers are released; the context goes with the last array."""
+        if not getattr(self, "h", None):
+            return
+        with self.lock:
+            self._closing = True
+            self.trim(0)
+            if self._outstanding == 0:
+                self.lib.cwtb_destroy(self.h)
+                self.h = None
 
     def __del__(self):
         try:
@@ -136,9 +184,17 @@ class Engine(object):
             raise ValueError("the resident transform is %d x %d, the call asks for %s x %s"
                              % (r, n, "?" if rows is None else rows, "?" if n0 is None else n0))
 
+    @_locked
     def set_band_eps(self, eps):
         self._check(self.lib.cwtb_set_band_eps(self.h, float(eps)))
 
+    @_locked
+    def set_expand_eps(self, eps64=5e-13, eps32=2e-7):
+        """Tolerance of the band-limited expansion path (include/cwt_b200.h); 0 switches it off
+        (every scale through the exact pruned transforms)."""
+        self._check(self.lib.cwtb_set_expand_eps(self.h, float(eps64), float(eps32)))
+
+    @_locked
     def set_padding(self, pad_to_pow2):
         """True (default): pad to the next power of two like the reference's scipy branch;
         False: transform at the signal's own length (the reference's pyfftw policy)."""
@@ -146,6 +202,7 @@ class Engine(object):
         self._pad_pow2 = bool(pad_to_pow2)
 
     # ---- pinned host arrays -------------------------------------------------------
+    @_locked
     def pinned_empty(self, shape, dtype):
         """numpy array backed by page-locked memory owned by the engine context."""
         dtype = np.dtype(dtype)
@@ -156,12 +213,17 @@ class Engine(object):
         arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
         return arr, p
 
+    @_locked
     def pinned_free(self, p):
         self.lib.cwtb_host_free(self.h, p)
 
     #: results at least this large are returned in page-locked memory (D2H at PCIe speed)
     PINNED_MIN_BYTES = 1 << 20
-    POOL_MAX_BYTES = 12 << 30
+    #: idle pinned memory kept for reuse (env CWTB_POOL_MB).  Default: room for one result of
+    #: the north-star size (4.3 GB) so that steady-state calls neither allocate nor pin; least
+    #: recently released buffers of any size are evicted first.
+    POOL_MAX_BYTES = int(os.environ.get("CWTB_POOL_MB", "4608")) << 20
+    _closing = False
 
     def result_array(self, shape, dtype):
         """Array for a transform result.  Large results alias pinned host memory taken
@@ -172,33 +234,58 @@ class Engine(object):
         nbytes = count * dtype.itemsize
         if nbytes < self.PINNED_MIN_BYTES:
             return np.empty(shape, dtype=dtype)
-        idle = self._pool.setdefault(nbytes, [])
-        if idle:
-            addr = idle.pop()
-            self._pool_bytes -= nbytes
-        else:
+        self._reap()
+        addr = None
+        with self._pool_lock:
+            for i in range(len(self._pool) - 1, -1, -1):     # most recently released first
+                if self._pool[i][0] == nbytes:
+                    addr = self._pool.pop(i)[1]
+                    self._pool_bytes -= nbytes
+                    break
+        if addr is None:
             p = _P()
-            if self.lib.cwtb_host_alloc(self.h, nbytes, ctypes.byref(p)) != 0 or not p.value:
+            with self.lock:
+                rc = self.lib.cwtb_host_alloc(self.h, nbytes, ctypes.byref(p))
+            if rc != 0 or not p.value:
+                self.trim(0)      # give pooled buffers of other sizes back and retry once
+                with self.lock:
+                    rc = self.lib.cwtb_host_alloc(self.h, nbytes, ctypes.byref(p))
+            if rc != 0 or not p.value:
                 # page-locked memory exhausted: an ordinary array still works, the copy is slower
                 return np.empty(shape, dtype=dtype)
             addr = p.value
         buf = (ctypes.c_char * nbytes).from_address(addr)
-        self._outstanding += 1
+        with self._pool_lock:
+            self._outstanding += 1
         fin = weakref.finalize(buf, self._release, nbytes, addr)
         fin.atexit = False
         return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
 
     def _release(self, nbytes, addr):
-        self._outstanding -= 1
-        if self.h is None:
-            return
-        if self._pool_bytes + nbytes <= self.POOL_MAX_BYTES and len(self._pool.get(nbytes, [])) < 2:
-            self._pool.setdefault(nbytes, []).append(addr)
-            self._pool_bytes += nbytes
-        else:
-            self.lib.cwtb_host_free(self.h, _P(addr))
+        """Finalizer of a pinned result array (any thread, any time): pool the buffer and
+        retire the least recently released ones beyond POOL_MAX_BYTES.  No library calls."""
+        with self._pool_lock:
+            self._outstanding -= 1
+            last = self._outstanding == 0
+            if self.h is None:
+                return
+            if self._closing or nbytes > self.POOL_MAX_BYTES:
+                self._dead.append(addr)
+            else:
+                self._pool.append((nbytes, addr))
+                self._pool_bytes += nbytes
+                while self._pool_bytes > self.POOL_MAX_BYTES and len(self._pool) > 1:
+                    nb, ad = self._pool.pop(0)
+                    self._pool_bytes -= nb
+                    self._dead.append(ad)
+        if self._closing and last and self.lock.acquire(blocking=False):
+            try:
+                self.close()
+            finally:
+                self.lock.release()
 
     # ---- transform ------------------------------------------------------------------
+    @_locked
     def cwt(self, signal, dt, scales, family, param, precision=F64, table=None,
             fetch=True, out_f64=True):
         sig = np.ascontiguousarray(signal)
@@ -233,6 +320,7 @@ class Engine(object):
                 return None
             return self.get_w(sj.size, sig.size, precision, out_f64)
 
+    @_locked
     def get_w(self, nrows, n0, precision=F64, out_f64=True):
         dtype = np.complex128 if (precision == F64 or out_f64) else np.complex64
         self._expect_resident(None, n0)
@@ -242,6 +330,7 @@ class Engine(object):
         self._check(self.lib.cwtb_get_w(self.h, _ptr(W), 1 if out_f64 else 0, 0, nrows))
         return W
 
+    @_locked
     def signal_fft(self):
         npad = int(self.lib.cwtb_padded_length(self.h))
         out = np.empty(max(npad // 2 - 1, 0), dtype=np.complex128)
@@ -249,23 +338,29 @@ class Engine(object):
             self._check(self.lib.cwtb_get_signal_fft(self.h, _ptr(out)))
         return out
 
+    @_locked
     def job_serial(self):
         return int(self.lib.cwtb_job_serial(self.h))
 
+    @_locked
     def padded_length(self):
         return int(self.lib.cwtb_padded_length(self.h))
 
+    @_locked
     def last_plan(self, n):
         out = (ctypes.c_int * n)()
         m = self.lib.cwtb_last_plan(self.h, out, n)
         return list(out)[:max(m, 0)]
 
+    @_locked
     def last_kernel_ms(self):
         return float(self.lib.cwtb_last_kernel_ms(self.h))
 
+    @_locked
     def last_launch_count(self):
         return int(self.lib.cwtb_last_launch_count(self.h))
 
+    @_locked
     def fft_c2c(self, x, sign, precision=F64):
         x = np.ascontiguousarray(x, dtype=np.complex128)
         if x.ndim == 1:
@@ -276,6 +371,7 @@ class Engine(object):
         return out
 
     # ---- reductions / derived products of the resident transform ------------------------
+    @_locked
     def icwt_sum(self, W=None, scales=None):
         """sum_j Re(W[j, :]) / sqrt(s_j): of the resident transform (W is None) or of a host
         array W[S, n]."""
@@ -292,12 +388,14 @@ class Engine(object):
                                                     W.shape[1], _ptr(out)))
             return out
 
+    @_locked
     def global_power(self, nrows):
         self._expect_resident(nrows)
         out = np.empty(nrows, dtype=np.float64)
         self._check(self.lib.cwtb_global_power(self.h, _ptr(out)))
         return out
 
+    @_locked
     def global_power_ranges(self, lo, hi):
         """Row means of |W|^2 over the column ranges [lo[j], hi[j]) (NaN where empty)."""
         lo = np.ascontiguousarray(lo, dtype=np.int64)
@@ -310,6 +408,7 @@ class Engine(object):
             self._check(self.lib.cwtb_global_power_ranges(self.h, _ptr(lo), _ptr(hi), _ptr(out)))
         return out
 
+    @_locked
     def power(self, nrows, n0, row_scale=None):
         """|W|^2 of the resident transform, optionally times one factor per row."""
         self._expect_resident(nrows, n0)
@@ -324,6 +423,7 @@ class Engine(object):
                 self._check(self.lib.cwtb_get_power_scaled(self.h, _ptr(rs), _ptr(out)))
         return out
 
+    @_locked
     def scale_avg_power(self, weights):
         """sum_j weights[j] |W[j, :]|^2 of the resident transform (TC98 eq. 24)."""
         w = np.ascontiguousarray(weights, dtype=np.float64)
@@ -334,6 +434,7 @@ class Engine(object):
         return out
 
     # ---- cross wavelet / coherence ------------------------------------------------------
+    @_locked
     def xwt(self, y1, y2, dt, scales, family, param):
         y1 = np.ascontiguousarray(y1, dtype=np.float64)
         y2 = np.ascontiguousarray(y2, dtype=np.float64)
@@ -348,6 +449,7 @@ class Engine(object):
             self._resident = (sj.size, y1.size)     # W12 stays on the device
         return out
 
+    @_locked
     def wct(self, y1, y2, dt, dj, scales, family, param, boxcar_len, want_angle=True):
         y1 = np.ascontiguousarray(y1, dtype=np.float64)
         y2 = np.ascontiguousarray(y2, dtype=np.float64)
@@ -364,6 +466,7 @@ class Engine(object):
             self._resident = None                   # several intermediates, no single transform
         return WCT, aWCT
 
+    @_locked
     def smooth(self, W, dt, scales, boxcar_len):
         W = np.ascontiguousarray(W)
         is_c = np.iscomplexobj(W)
@@ -379,6 +482,7 @@ class Engine(object):
                                              float(dt), _ptr(sj), int(boxcar_len), _ptr(out)))
         return out
 
+    @_locked
     def wct_mc(self, noise, dt, dj, scales, family, param, boxcar_len, mask, maxscale, nbins,
                hist):
         noise = np.ascontiguousarray(noise, dtype=np.float64)
@@ -395,6 +499,7 @@ class Engine(object):
             self._resident = None
         return hist
 
+    @_locked
     def cwt_batch(self, X, dt, scales, family, param, precision=F64, want_power=True,
                   want_w=False):
         X = np.ascontiguousarray(X)
@@ -416,18 +521,22 @@ class Engine(object):
         return power, W
 
     # ---- device-resident benchmarking helpers -------------------------------------
+    @_locked
     def dev_alloc(self, nbytes):
         p = _P()
         self._check(self.lib.cwtb_dev_alloc(self.h, nbytes, ctypes.byref(p)))
         return p
 
+    @_locked
     def dev_free(self, p):
         self.lib.cwtb_dev_free(self.h, p)
 
+    @_locked
     def h2d(self, dptr, arr):
         arr = np.ascontiguousarray(arr)
         self._check(self.lib.cwtb_memcpy_h2d(self.h, dptr, _ptr(arr), arr.nbytes))
 
+    @_locked
     def cwt_dev(self, dptr, is_f32, n0, dt, scales, family, param, precision=F64):
         sj = np.ascontiguousarray(scales, dtype=np.float64)
         self._check(self.lib.cwtb_cwt_dev(self.h, dptr, int(is_f32), int(n0), float(dt),
@@ -436,6 +545,7 @@ class Engine(object):
         self._resident_n0 = int(n0)
         self._resident = (sj.size, int(n0))
 
+    @_locked
     def cwt_batch_dev(self, dptr, n_chan, n0, dt, scales, family, param, precision=F64,
                       want_power=False):
         sj = np.ascontiguousarray(scales, dtype=np.float64)
@@ -447,11 +557,13 @@ class Engine(object):
         self._resident = (int(n_chan) * sj.size, int(n0))
         return power
 
+    @_locked
     def bench_last(self, iters):
         ms = _D()
         self._check(self.lib.cwtb_bench_last(self.h, int(iters), ctypes.byref(ms)))
         return ms.value
 
+    @_locked
     def profile_last(self):
         """Per-kernel-type device times of one pass of the last cwt_dev transform:
         list of dicts {name, launches, ms, rows}."""
@@ -465,6 +577,7 @@ class Engine(object):
             out.append({"name": name, "launches": int(nl), "ms": float(ms), "rows": int(rows)})
         return out
 
+    @_locked
     def sync(self):
         self._check(self.lib.cwtb_sync(self.h))
 

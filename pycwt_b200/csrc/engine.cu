@@ -92,9 +92,13 @@ struct Buf {
   size_t bytes = 0;
 };
 
-struct ClassRun {   // scales sharing one pruned length K'
-  int log2K;
+struct ClassRun {   // scales sharing one execution plan
+  int log2K;        // exact path: pruned length K' = 1 << log2K
   int first, count; // range in the sorted descriptor array
+  int expand = 0;   // 1: band-limited expansion path (coarse transform + interpolation)
+  int log2Nc = 0;   // expansion: coarse grid length
+  int taps = 0;     // expansion: interpolation taps
+  long long woff = 0;   // expansion: offset of the class's weight table
 };
 
 struct Job {
@@ -112,6 +116,7 @@ struct Job {
   std::vector<int> plan_log2K;    // per input scale
   std::vector<double> scales;     // per input scale (= output row)
   size_t b_single = 0;            // elements of the band buffer used by single-kernel scales
+  size_t coarse_elems = 0;        // elements of the coarse buffers used by the expansion rows
   int sig_is_f32 = 0;
   bool exact = false;             // un-padded mode: N = n0 (not a power of two), Bluestein transforms
 };
@@ -146,6 +151,11 @@ struct cwtb_ctx {
   int d2h_split = 1;             // CWTB_D2H_SPLIT
   std::string err;
   double band_eps = 1e-16;
+  double expand_eps = 5e-13;     // fp64 engine: bound on the aliasing error of the expansion path
+                                 // (0: path off, every scale through the exact pruned transforms)
+  double expand_eps32 = 2e-7;    // fp32 engine
+  int expand_min_log2R = 3;      // expansion needs Np / Nc >= 8 (CWTB_EXPAND_MIN_R: log2)
+  Buf *ztmp = nullptr;           // intermediate of two_kernel_rows (set per stream; default Z)
   int group = 0;   // rows per two-kernel chunk; 0 = as many as fit in group_bytes of Z (CWTB_GROUP)
   size_t group_bytes = (size_t)512 << 20;
   int l2_persist = 0;
@@ -163,6 +173,11 @@ struct cwtb_ctx {
   double2 *tw64 = nullptr;
   float2 *tw32 = nullptr;
   std::map<unsigned, NTabDev> ntabs;
+  Buf Zx, Cin, Cout, wtab;       // expansion path: its own transform intermediate, coarse spectra /
+                                 // samples, interpolation weight tables
+  std::map<std::array<long long, 3>, long long> wtab_index;   // (log2R, taps, round(beta*1e6)) -> offset
+  std::vector<double> wtab_host; // host mirror of wtab (tables are appended, never moved)
+  size_t wtab_uploaded = 0;      // elements already on the device
   Buf ctr, sig, sig2, spec, Z, Zc[3], Y, B, W, W2, descs, table, scratch, C, A12, F, aux, rowd, win, mask, hist, noise, wide, blueA, blueX, blueY;
   Job job;
   const void *job_dsig = nullptr;  // device signal of the last cwt_dev call (not owned)
@@ -380,6 +395,72 @@ static void family_band(int family, double param, double eps, double *flo, doubl
   }
 }
 
+// ---- band-limited expansion path: Kaiser-Bessel kernel, alias bound, weight tables ------------
+// phi(x) = I0(beta sqrt(1 - (2x/w)^2)) / I0(beta) on |x| <= w/2; its transform is
+// phi^(xi) = w / I0(beta) * sinh(z)/z, z = sqrt(beta^2 - (pi w xi)^2)  (sin(z)/z beyond the cut-off).
+static double kb_hat_shape(double xi, int w, double beta) {   // phi^(xi) * I0(beta) / w
+  const double x = M_PI * w * xi;
+  const double z2 = beta * beta - x * x;
+  const double z = std::sqrt(std::fabs(z2));
+  if (z < 1e-8) return 1.0;
+  return z2 > 0 ? std::sinh(z) / z : std::sin(z) / z;
+}
+// max over |xi| <= xi_b of sum_{l != 0} |phi^(xi + l)| / |phi^(xi)|, beta = pi w (1 - xi_b): the
+// relative aliasing error of the expansion for a band of half-width xi_b * Nc bins
+static double kb_alias_bound(double xi_b, int w) {
+  const double beta = M_PI * w * (1.0 - xi_b);
+  double worst = 0;
+  for (int i = 0; i <= 64; ++i) {
+    const double xi = xi_b * i / 64.0;
+    double num = 0;
+    for (int l = 1; l <= 4; ++l) num += std::fabs(kb_hat_shape(xi + l, w, beta)) + std::fabs(kb_hat_shape(xi - l, w, beta));
+    worst = std::max(worst, num / std::fabs(kb_hat_shape(xi, w, beta)));
+  }
+  return worst;
+}
+static const double kExpandXi[] = {1.0 / 16, 3.0 / 32, 1.0 / 8, 5.0 / 32, 3.0 / 16, 7.0 / 32, 1.0 / 4};
+static const int kExpandTaps64[] = {10, 12, 14, 16};
+static const int kExpandTaps32[] = {6, 8, 10};
+
+// smallest tap count whose alias bound at the bucket of `xi` is <= eps; 0 if none.  *xi_b: bucket.
+static int expand_taps(double xi, double eps, bool f32, double *xi_b) {
+  static std::map<std::pair<int, int>, double> cache;   // (bucket, taps) -> bound
+  int b = -1;
+  for (int i = 0; i < 7; ++i)
+    if (xi <= kExpandXi[i] * (1 + 1e-12)) { b = i; break; }
+  if (b < 0) return 0;
+  *xi_b = kExpandXi[b];
+  const int *taps = f32 ? kExpandTaps32 : kExpandTaps64;
+  const int ntaps = f32 ? 3 : 4;
+  for (int i = 0; i < ntaps; ++i) {
+    auto key = std::make_pair(b, taps[i]);
+    auto it = cache.find(key);
+    if (it == cache.end()) it = cache.emplace(key, kb_alias_bound(kExpandXi[b], taps[i])).first;
+    if (it->second <= eps) return taps[i];
+  }
+  return 0;
+}
+
+// weight table of one class: h[t][rho] = phi(rho / R - (t - (w/2 - 1))), t < w, rho < R (doubles,
+// appended to the context's host mirror; uploaded by upload_descs when it grew)
+static long long expand_weights(cwtb_ctx *c, std::vector<double> &host, int log2R, int w, double beta) {
+  const std::array<long long, 3> key{log2R, w, (long long)std::llround(beta * 1e6)};
+  auto it = c->wtab_index.find(key);
+  if (it != c->wtab_index.end()) return it->second;
+  const long long off = (long long)host.size();
+  const int R = 1 << log2R;
+  host.resize(host.size() + (size_t)w * R);
+  const double i0b = std::cyl_bessel_i(0.0, beta);
+  for (int t = 0; t < w; ++t)
+    for (int rho = 0; rho < R; ++rho) {
+      const double x = (double)rho / R - (double)(t - (w / 2 - 1));
+      const double a = 1.0 - (2.0 * x / w) * (2.0 * x / w);
+      host[off + (size_t)t * R + rho] = a >= 0 ? std::cyl_bessel_i(0.0, beta * std::sqrt(a)) / i0b : 0.0;
+    }
+  c->wtab_index.emplace(key, off);
+  return off;
+}
+
 static int build_job(cwtb_ctx *c, Job &job, long long n0, double dt, const double *scales, int S,
                      int family, double param, int precision, bool have_table, int nbatch = 1) {
   if (n0 < 1 || S < 1 || !(dt > 0)) return fail(c, CWTB_ERR_ARG, "bad n0 / n_scales / dt");
@@ -480,6 +561,34 @@ static int build_job(cwtb_ctx *c, Job &job, long long n0, double dt, const doubl
     }
     d.log2K = lk;
     job.plan_log2K[j] = job.exact ? -1 : ((N < 32) ? 0 : lk);
+    // ---- band-limited expansion instead of the pruned transforms (kernels.cuh: ExpandBody) ----
+    d.ip_log2Nc = 0; d.ip_kc = 0; d.ip_w = 0; d.ip_pad_ = 0; d.ip_coff = 0; d.ip_woff = 0;
+    d.ip_beta = 0; d.ip_dc = 0;
+    const double xeps = precision == CWTB_F64 ? c->expand_eps : c->expand_eps32;
+    if (xeps > 0 && !job.exact && family != CWTB_TABLE && khi >= klo && job.log2N >= 9 && lk < job.log2N) {
+      const long long kc = (klo + khi) / 2 - (((klo + khi) % 2 != 0 && (klo + khi) < 0) ? 1 : 0);   // floor
+      const long long hw = std::max(khi - kc, kc - klo);
+      int lmin = std::max(6, ilog2((unsigned long long)std::max<long long>(4 * hw, 1)));
+      lmin = std::max(lmin, job.log2N - 14);          // weight tables of at most 2^14 phases
+      double best = 1e300;
+      for (int l = lmin; l <= lmin + 2 && job.log2N - l >= c->expand_min_log2R; ++l) {
+        double xi_b = 0;
+        const int w = expand_taps((double)hw / (double)(1ll << l), xeps, precision != CWTB_F64, &xi_b);
+        if (!w) continue;
+        // cost model (us at Np = 2^20): fp64 work of the expansion + the coarse transform
+        const double cost = 0.06 * (2 * w + 8) + 12.0 * (double)(1ll << l) / (double)N;
+        if (cost < best) {
+          best = cost;
+          d.ip_log2Nc = l; d.ip_kc = (int)kc; d.ip_w = w;
+          d.ip_beta = M_PI * w * (1.0 - xi_b);
+          d.ip_dc = std::cyl_bessel_i(0.0, d.ip_beta) / w;
+        }
+      }
+      if (d.ip_log2Nc) {
+        d.ip_woff = expand_weights(c, c->wtab_host, job.log2N - d.ip_log2Nc, d.ip_w, d.ip_beta);
+        job.plan_log2K[j] = -d.ip_log2Nc;
+      }
+    }
   }
   // one descriptor per (channel, scale) row; rows of channel ch are ch*S .. ch*S+S-1
   if (nbatch > 1) {
@@ -496,21 +605,40 @@ static int build_job(cwtb_ctx *c, Job &job, long long n0, double dt, const doubl
   // sort by class (descending K': small scales first), stable
   std::vector<int> order(R);
   for (int j = 0; j < R; ++j) order[j] = j;
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return ds[a].log2K > ds[b].log2K; });
+  // exact classes first (two-kernel, then single-kernel: descending K'), expansion classes last
+  // (descending coarse length, then taps / weight table)
+  auto sort_key = [&](const ScaleDesc &d) -> long long {
+    if (!d.ip_log2Nc) return (1ll << 40) + d.log2K;
+    return ((long long)d.ip_log2Nc << 32) - ((long long)d.ip_w << 24) - (d.ip_woff & 0xffffff);
+  };
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return sort_key(ds[a]) > sort_key(ds[b]); });
   job.descs.resize(R);
-  size_t boff = 0;
+  size_t boff = 0, coff = 0;
   for (int i = 0; i < R; ++i) {
     job.descs[i] = ds[order[i]];
     ScaleDesc &d = job.descs[i];
-    if (job.classes.empty() || job.classes.back().log2K != d.log2K)
-      job.classes.push_back(ClassRun{d.log2K, i, 0});
+    bool same = !job.classes.empty();
+    if (same) {
+      const ClassRun &b = job.classes.back();
+      same = d.ip_log2Nc ? (b.expand && b.log2Nc == d.ip_log2Nc && b.taps == d.ip_w && b.woff == d.ip_woff)
+                         : (!b.expand && b.log2K == d.log2K);
+    }
+    if (!same) {
+      ClassRun cl{d.log2K, i, 0};
+      if (d.ip_log2Nc) { cl.expand = 1; cl.log2Nc = d.ip_log2Nc; cl.taps = d.ip_w; cl.woff = d.ip_woff; }
+      job.classes.push_back(cl);
+    }
     job.classes.back().count++;
-    if (d.log2K <= 10 || (d.log2K <= c->direct_max_log2 && d.log2K < job.log2N)) {  // single-kernel scale
+    if (d.ip_log2Nc) {
+      d.ip_coff = (long long)coff;
+      coff += (size_t)1 << d.ip_log2Nc;
+    } else if (d.log2K <= 10 || (d.log2K <= c->direct_max_log2 && d.log2K < job.log2N)) {  // single-kernel scale
       d.boff = (long long)boff;
       boff += (size_t)1 << d.log2K;
     }
   }
   job.b_single = boff;
+  job.coarse_elems = coff;
   job.valid = true;
   return 0;
 }
@@ -572,18 +700,19 @@ static int two_kernel_rows(cwtb_ctx *c, const void *in, int real_in, long long i
   int e = get_ntab(c, n, l2, &nt);
   if (e) return e;
   const int chunk = std::max(1, std::min(nrows, (int)std::max<size_t>(1, ((size_t)64 << 20) / ((size_t)n * sizeof(cx<T>)))));
-  if ((e = ensure(c, c->Z, (size_t)chunk * n * sizeof(cx<T>)))) return e;
+  Buf &Zt = c->ztmp ? *c->ztmp : c->Z;
+  if ((e = ensure(c, Zt, (size_t)chunk * n * sizeof(cx<T>)))) return e;
   for (int r0 = 0; r0 < nrows; r0 += chunk) {
     const int nr = std::min(chunk, nrows - r0);
     PassAArgs<T> a{};
-    a.in = in; a.Z = (cx<T> *)c->Z.p; a.tw = Tw<T>::get(c); a.nt = nt;
+    a.in = in; a.Z = (cx<T> *)Zt.p; a.tw = Tw<T>::get(c); a.nt = nt;
     a.in_pitch = in_pitch; a.n_in = n_in; a.N = n; a.first = 0; a.zmod = 1 << 30; a.K2 = K2C;
     a.row0 = (ileave > 1 ? 0 : out_row0) + r0;   // interleaved input rows are numbered from 0
     e = real_in ? dispatch_passA<T, SIGN, MODE_REAL>(c, l2 - 10, a, nr)
                 : dispatch_passA<T, SIGN, MODE_CPLX>(c, l2 - 10, a, nr);
     if (e) return e;
     PassBArgs<T> b{};
-    b.Z = (const cx<T> *)c->Z.p; b.out = out; b.tw = Tw<T>::get(c); b.descs = descs;
+    b.Z = (const cx<T> *)Zt.p; b.out = out; b.tw = Tw<T>::get(c); b.descs = descs;
     b.pitch = out_pitch; b.nout = nout; b.N = n; b.first = first;
     b.epi = grow ? EPI_GAUSS : epi; b.grow = grow; b.post = post; b.zmod = 1 << 30;
     b.pf_dist = 0; b.ny = nr; b.ileave = ileave; b.rev = c->passb_rev;
@@ -923,14 +1052,20 @@ static int chunk_rows(const cwtb_ctx *c, unsigned N, size_t elem_bytes) {
   return (int)std::max<size_t>(1, std::min<size_t>(g, 32768));
 }
 
+static bool class_single(const cwtb_ctx *c, const Job &job, const ClassRun &cl) {
+  return !cl.expand && (cl.log2K <= 10 || (cl.log2K <= c->direct_max_log2 && cl.log2K < job.log2N));
+}
+static bool class_two_kernel(const cwtb_ctx *c, const Job &job, const ClassRun &cl) {
+  return !cl.expand && !class_single(c, job, cl);
+}
+
 // Which band-chunk region / Z buffer / stream a two-kernel class uses: its position among the
 // two-kernel classes modulo the number of chains (dense classes included, they only use Z).
 static int job_chain_region(const cwtb_ctx *c, const Job &job, const ClassRun &cl) {
   int idx = 0;
   for (const ClassRun &o : job.classes) {
     if (&o == &cl) break;
-    const bool single = o.log2K <= 10 || (o.log2K <= c->direct_max_log2 && o.log2K < job.log2N);
-    if (!single) ++idx;
+    if (class_two_kernel(c, job, o)) ++idx;
   }
   return idx % std::max(1, c->n_chains);
 }
@@ -939,9 +1074,36 @@ static int job_chain_region(const cwtb_ctx *c, const Job &job, const ClassRun &c
 static size_t band_chunk_elems(const cwtb_ctx *c, const Job &job, int G) {
   size_t bchunk = 0;
   for (const ClassRun &cl : job.classes)
-    if (cl.log2K > c->direct_max_log2 && cl.log2K < job.log2N)
+    if (class_two_kernel(c, job, cl) && cl.log2K < job.log2N)
       bchunk = std::max(bchunk, (size_t)(c->fused ? cl.count : std::min(G, cl.count)) << cl.log2K);
   return bchunk;
+}
+
+template <typename T, int TAPS>
+static int launch_expand_t(cwtb_ctx *c, const ExpandArgs<T> &a, int rows) {
+  using B = ExpandBody<T, TAPS>;
+  const int R = 1 << a.log2R;
+  const int Nc = (int)(a.N >> a.log2R);
+  const int RB = std::min(R, B::NT), MT = (B::NT / RB) * B::L;
+  return launch<B>(c, (unsigned)((R / RB) * ((Nc + MT - 1) / MT)), rows, a);
+}
+template <typename T>
+static int launch_expand(cwtb_ctx *c, int taps, const ExpandArgs<T> &a, int rows) {
+  if constexpr (std::is_same<T, double>::value) {
+    switch (taps) {
+      case 10: return launch_expand_t<T, 10>(c, a, rows);
+      case 12: return launch_expand_t<T, 12>(c, a, rows);
+      case 14: return launch_expand_t<T, 14>(c, a, rows);
+      case 16: return launch_expand_t<T, 16>(c, a, rows);
+    }
+  } else {
+    switch (taps) {
+      case 6: return launch_expand_t<T, 6>(c, a, rows);
+      case 8: return launch_expand_t<T, 8>(c, a, rows);
+      case 10: return launch_expand_t<T, 10>(c, a, rows);
+    }
+  }
+  return fail(c, CWTB_ERR_STATE, "expansion: unsupported tap count");
 }
 
 // all kernels of one transform: forward FFT of the (device, type T) signal, then every scale
@@ -986,19 +1148,20 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
   if ((e = ensure(c, c->B, (job.b_single + (size_t)std::max(1, c->n_chains) * bchunk) * sizeof(V)))) return e;
   V *Bbuf = (V *)c->B.p;
 
-  // band products of every single-kernel scale in one launch (their descriptors are the tail
-  // of the class-sorted array; blocks beyond a scale's K' exit immediately)
+  // band products of every single-kernel scale in one launch (their descriptors are contiguous
+  // in the class-sorted array; blocks beyond a scale's K' exit immediately)
   {
-    int first = -1, maxlk = 0;
+    int first = -1, maxlk = 0, nrows = 0;
     for (const ClassRun &cl : job.classes)
-      if (cl.log2K <= 10 || (cl.log2K <= c->direct_max_log2 && cl.log2K < job.log2N)) {
+      if (class_single(c, job, cl)) {
         if (first < 0) first = cl.first;
         maxlk = std::max(maxlk, cl.log2K);
+        nrows += cl.count;
       }
     if (first >= 0) {
       BandArgs<T> ba{ddesc, spec, Bbuf, fam, N, first};
       const unsigned Kmax = 1u << maxlk;
-      if ((e = launch<BandBody<T>>(c, (Kmax + NT * BandBody<T>::PER - 1) / (NT * BandBody<T>::PER), S - first, ba)))
+      if ((e = launch<BandBody<T>>(c, (Kmax + NT * BandBody<T>::PER - 1) / (NT * BandBody<T>::PER), nrows, ba)))
         return e;
     }
   }
@@ -1016,11 +1179,53 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
 #else
   const bool split2 = false;
 #endif
+  // ---- expansion classes (kernels.cuh: ExpandBody): coarse band spectra of every expansion row
+  // in one launch, one batched coarse transform per coarse length, one expansion launch per class.
+  // They run on the second stream like the single-kernel classes (own transform intermediate Zx).
+  if (job.coarse_elems) {
+#ifndef CWTB_HOST_EMU
+    if (split) c->cur = c->aux_stream;
+#endif
+    if ((e = ensure(c, c->Cin, job.coarse_elems * sizeof(V)))) return e;
+    if ((e = ensure(c, c->Cout, job.coarse_elems * sizeof(V)))) return e;
+    int first = -1, maxl = 0, nrows = 0;
+    for (const ClassRun &cl : job.classes)
+      if (cl.expand) {
+        if (first < 0) first = cl.first;
+        maxl = std::max(maxl, cl.log2Nc);
+        nrows += cl.count;
+      }
+    ExpandBandArgs<T> xa{ddesc, spec, (V *)c->Cin.p, fam, N, first};
+    constexpr int XPER = ExpandBandBody<T>::PER;
+    if ((e = launch<ExpandBandBody<T>>(c, ((1u << maxl) + NT * XPER - 1) / (NT * XPER), nrows, xa))) return e;
+    c->ztmp = &c->Zx;
+    for (size_t ci = 0; ci < job.classes.size() && !e; ++ci) {
+      const ClassRun &cl = job.classes[ci];
+      if (!cl.expand) continue;
+      // coarse transforms: all classes of this coarse length at once (rows are contiguous)
+      if (ci == 0 || !job.classes[ci - 1].expand || job.classes[ci - 1].log2Nc != cl.log2Nc) {
+        int rows = 0;
+        for (size_t cj = ci; cj < job.classes.size() && job.classes[cj].expand && job.classes[cj].log2Nc == cl.log2Nc; ++cj)
+          rows += job.classes[cj].count;
+        const long long off = job.descs[cl.first].ip_coff;
+        const unsigned Nc = 1u << cl.log2Nc;
+        e = fft_rows<T, +1>(c, (const V *)c->Cin.p + off, 0, Nc, Nc, (V *)c->Cout.p + off, Nc, Nc, rows);
+        if (e) break;
+      }
+      ExpandArgs<T> ea{ddesc, (const V *)c->Cout.p, (const double *)c->wtab.p, W, nt, job.n0, N, cl.first, epi,
+                       job.log2N - cl.log2Nc};
+      e = launch_expand<T>(c, cl.taps, ea, cl.count);
+    }
+    c->ztmp = nullptr;
+    c->cur = c->stream;
+    if (e) return e;
+  }
   int chain_no = 0;
   for (int pass = 0; pass < 2; ++pass)
   for (const ClassRun &cl : job.classes) {
+    if (cl.expand) continue;
     const unsigned K = 1u << cl.log2K;
-    const bool single = cl.log2K <= 10 || (cl.log2K <= c->direct_max_log2 && cl.log2K < job.log2N);
+    const bool single = class_single(c, job, cl);
     if (single != (pass == 0)) continue;   // pass 0: single-kernel classes, pass 1: two-kernel chains
     if (single) {
 #ifndef CWTB_HOST_EMU
@@ -1137,7 +1342,7 @@ static void assign_chunk_offsets(cwtb_ctx *c, Job &job) {
   const int G = chunk_rows(c, job.N, job.precision == CWTB_F64 ? sizeof(double2) : sizeof(float2));
   const size_t bchunk = band_chunk_elems(c, job, G);
   for (const ClassRun &cl : job.classes) {
-    if (cl.log2K <= c->direct_max_log2 || cl.log2K == job.log2N) continue;
+    if (!class_two_kernel(c, job, cl) || cl.log2K == job.log2N) continue;
     const size_t region = (size_t)job_chain_region(c, job, cl) * bchunk;
     for (int i = 0; i < cl.count; ++i)
       job.descs[cl.first + i].boff =
@@ -1147,6 +1352,18 @@ static void assign_chunk_offsets(cwtb_ctx *c, Job &job) {
 
 static int upload_descs(cwtb_ctx *c, Job &job) {
   assign_chunk_offsets(c, job);
+  if (c->wtab_host.size() > c->wtab_uploaded) {   // new expansion weight tables (appended)
+    const size_t bytes = c->wtab_host.size() * sizeof(double);
+    if (c->wtab.bytes < bytes) {
+      RT(rt_sync(c->stream));
+      int e2 = ensure(c, c->wtab, std::max(bytes, (size_t)2 * c->wtab.bytes));
+      if (e2) return e2;
+      c->wtab_uploaded = 0;   // a new allocation: everything again
+    }
+    RT(rt_h2d((char *)c->wtab.p + c->wtab_uploaded * sizeof(double), c->wtab_host.data() + c->wtab_uploaded,
+              (c->wtab_host.size() - c->wtab_uploaded) * sizeof(double), c->stream));
+    c->wtab_uploaded = c->wtab_host.size();
+  }
   int e = ensure(c, c->descs, job.descs.size() * sizeof(ScaleDesc));
   if (e) return e;
   RT(rt_h2d(c->descs.p, job.descs.data(), job.descs.size() * sizeof(ScaleDesc), c->stream));
@@ -1234,6 +1451,9 @@ int cwtb_create(int device, cwtb_ctx **out) {
   if (const char *g = getenv("CWTB_GROUP")) c->group = std::max(0, atoi(g));
   if (const char *g = getenv("CWTB_GROUP_MB")) c->group_bytes = (size_t)std::max(1, atoi(g)) << 20;
   if (const char *g = getenv("CWTB_BAND_EPS")) c->band_eps = atof(g);
+  if (const char *g = getenv("CWTB_EXPAND_EPS")) c->expand_eps = std::max(0.0, atof(g));
+  if (const char *g = getenv("CWTB_EXPAND_EPS32")) c->expand_eps32 = std::max(0.0, atof(g));
+  if (const char *g = getenv("CWTB_EXPAND_MIN_R")) c->expand_min_log2R = std::min(14, std::max(3, atoi(g)));
   if (const char *g = getenv("CWTB_L2_PERSIST")) c->l2_persist = atoi(g);
   if (const char *g = getenv("CWTB_FUSED")) c->fused = atoi(g);
   if (const char *g = getenv("CWTB_PF_DIST")) c->pf_dist = std::max(0, atoi(g));
@@ -1263,7 +1483,7 @@ void cwtb_destroy(cwtb_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
 #endif
-  for (Buf *b : {&c->ctr, &c->sig, &c->sig2, &c->spec, &c->Z, &c->Zc[0], &c->Zc[1], &c->Zc[2], &c->Y, &c->B, &c->W, &c->W2, &c->descs, &c->table, &c->scratch,
+  for (Buf *b : {&c->Zx, &c->Cin, &c->Cout, &c->wtab, &c->ctr, &c->sig, &c->sig2, &c->spec, &c->Z, &c->Zc[0], &c->Zc[1], &c->Zc[2], &c->Y, &c->B, &c->W, &c->W2, &c->descs, &c->table, &c->scratch,
                  &c->C, &c->A12, &c->F, &c->aux, &c->rowd, &c->win, &c->mask, &c->hist, &c->noise, &c->wide, &c->blueA, &c->blueX, &c->blueY})
     if (b->p) rt_free(b->p);
   for (auto &kv : c->ntabs) { rt_free(kv.second.hi); rt_free(kv.second.lo); }
@@ -1291,6 +1511,14 @@ const char *cwtb_last_error(cwtb_ctx *c) { return c ? c->err.c_str() : "null con
 int cwtb_set_band_eps(cwtb_ctx *c, double eps) {
   if (!c || !(eps >= 0) || eps >= 1e-6) return fail(c, CWTB_ERR_ARG, "band eps must be in [0, 1e-6)");
   c->band_eps = eps;
+  return 0;
+}
+
+int cwtb_set_expand_eps(cwtb_ctx *c, double eps64, double eps32) {
+  if (!c || !(eps64 >= 0) || !(eps32 >= 0) || eps64 > 1e-6 || eps32 > 1e-3)
+    return fail(c, CWTB_ERR_ARG, "expansion tolerance must be in [0, 1e-6] (fp64) / [0, 1e-3] (fp32)");
+  c->expand_eps = eps64;
+  c->expand_eps32 = eps32;
   return 0;
 }
 
@@ -1643,7 +1871,7 @@ static bool single_kernel_rows(const cwtb_ctx *c, const Job &job, int *r0) {
   const int S = job.S;
   int lo = S, cnt = 0;
   for (const ClassRun &cl : job.classes) {
-    if (!(cl.log2K <= 10 || (cl.log2K <= c->direct_max_log2 && cl.log2K < job.log2N))) continue;
+    if (!(cl.expand || class_single(c, job, cl))) continue;
     for (int i = cl.first; i < cl.first + cl.count; ++i) {
       lo = std::min(lo, job.descs[i].row);
       ++cnt;

@@ -20,6 +20,15 @@ struct ScaleDesc {
   int chan;        // channel of a batched transform: spectrum at spec + chan*Np
   int pad_;
   long long boff;  // offset of this scale's band product B[] in the band buffer
+  // ---- band-limited expansion path (ip_log2Nc > 0; see ExpandBody) ----
+  int ip_log2Nc;   // coarse grid length Nc = 1 << ip_log2Nc  (0: exact pruned-transform path)
+  int ip_kc;       // centre bin of the band (signed): the coarse grid holds the band shifted to 0
+  int ip_w;        // taps of the interpolation kernel
+  int ip_pad_;
+  long long ip_coff;   // offset of this row's Nc coarse samples in the coarse buffers
+  long long ip_woff;   // offset of the [taps][R] weight table of this row's class
+  double ip_beta;      // Kaiser-Bessel shape parameter
+  double ip_dc;        // I0(beta) / taps: 1 / (transform of the kernel) = ip_dc * z / sinh(z)
 };
 
 struct Fam {
@@ -616,6 +625,151 @@ template <typename T, int K1, int MODE, int SIGN> struct PassABody {
       tile_second<T, K1, SIGN>(sm, a.tw, tid);
     } else {
       pass_last<T, K1, SIGN>(sm, st, tid);
+    }
+  }
+};
+
+// ==================================================================================================
+// Band-limited expansion path.  A scale whose response is confined to the bins [k_lo, k_hi]
+// (Kb of the Np bins) is a trigonometric polynomial of Kb terms: it is fully determined by
+// Nc >= 2 Kb samples.  Instead of running Np/K' pruned transforms of K' points each, the engine
+//   (1) forms the band product shifted to the centre bin kc and divided by the transform of the
+//       interpolation kernel (ExpandBandBody),
+//   (2) inverse-transforms it on the coarse grid of Nc points (the ordinary batched FFT), and
+//   (3) expands the Nc samples to the Np output points with a polyphase Kaiser-Bessel kernel of
+//       `taps` real weights per output and re-modulates by e^{2 pi i kc n / Np} (ExpandBody):
+//         W[R m + rho] = e^{2 pi i kc n/Np} * sum_t c[m + t - (taps/2 - 1)] * h[t][rho],  R = Np / Nc.
+// With phi the kernel and phi^ its transform, sum_m e^{2 pi i k m/Nc} phi(x - m) =
+// sum_l phi^(k/Nc + l) e^{2 pi i (k/Nc + l) x}: the l = 0 term is the exact value after the division
+// by phi^(k/Nc), the others are the aliasing error, bounded on the host by
+// max_{|xi| <= xi_max} sum_{l != 0} |phi^(xi + l)| / |phi^(xi)| (engine.cu: kb_alias_bound).  The host
+// picks (Nc, taps) so that the bound stays below the context's expansion tolerance (default
+// 5e-13: measured error 1e-13, three orders inside the 1e-10 parity gate; 0 = path off).
+// Cost per output point: 2*taps + 8 fp64 FMAs, one 16-byte shared-memory read, one 16-byte store --
+// a streaming kernel bounded by the W store, with no intermediate in global memory.
+// ==================================================================================================
+template <typename T> struct ExpandBandArgs {
+  const ScaleDesc *descs;
+  const cx<T> *spec;
+  cx<T> *Cin;       // coarse spectra, rows at descs[].ip_coff
+  Fam fam;
+  unsigned N;
+  int first;
+};
+template <typename T> struct ExpandBandBody {
+  using V = cx<T>;
+  using Args = ExpandBandArgs<T>;
+  static constexpr int NPHASE = 1;
+  static constexpr size_t SMEM = 0;
+  static constexpr int PER = 4;
+  template <int PH> HD static void phase(const Args &a, int bx, int by, int tid, void *) {
+    const ScaleDesc d = a.descs[a.first + by];
+    const int Nc = 1 << d.ip_log2Nc;
+    const double pw = 3.14159265358979323846 * (double)d.ip_w;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int r = (bx * PER + i) * NT + tid;
+      if (r >= Nc) return;
+      const int kp = r < Nc / 2 ? r : r - Nc;       // signed offset from the centre bin
+      const int k = d.ip_kc + kp;
+      V v = mk<T>(0, 0);
+      if (k >= d.k_lo && k <= d.k_hi) {
+        const V b = band_value<T>(a.fam, d, a.spec, (unsigned)k & (a.N - 1), k, a.N);
+        // 1 / phi^(kp / Nc),  phi^(xi) = taps / I0(beta) * sinh(z) / z,  z = sqrt(beta^2 - (pi taps xi)^2)
+        const double x = pw * ((double)kp / (double)Nc);
+        const double z = sqrt(d.ip_beta * d.ip_beta - x * x);      // > 0: |xi| <= 1/4 < 1 - xi_max
+        const double f = d.ip_dc * (z / sinh(z));
+        v = mk<T>((T)((double)b.x * f), (T)((double)b.y * f));
+      }
+      a.Cin[d.ip_coff + r] = v;
+    }
+  }
+};
+
+template <typename T> struct ExpandArgs {
+  const ScaleDesc *descs;
+  const cx<T> *C;      // coarse samples (inverse transforms of the coarse spectra)
+  const double *wt;    // weight tables [taps][R] (fp64 for both engines)
+  cx<T> *W;            // [rows][n0]
+  NTab nt;
+  long long n0;
+  unsigned N;
+  int first;
+  int epi;             // EPI_STORE / EPI_MULCONJ
+  int log2R;           // R = N / Nc of every row of this launch
+};
+
+// CTA tile: RB = min(R, NT) consecutive phases rho  x  NRUN = NT / RB runs of L consecutive coarse
+// positions m.  A thread keeps its `TAPS` weights (fixed rho) and a sliding window of TAPS coarse
+// samples in registers and walks its run: one new sample (shared-memory read, the same address
+// for the lanes of a run) and one 16-byte store per output; lanes run over rho, so a warp stores
+// min(R, 32) consecutive points per run.
+template <typename T, int TAPS> struct ExpandBody {
+  static constexpr int NTB = TileCfg<T>::NT;
+  static constexpr int NT = NTB;
+  using V = cx<T>;
+  using Args = ExpandArgs<T>;
+  static constexpr int L = 32;                       // coarse positions per run
+  static constexpr int MAXRUN = NT / 8;              // R >= 8
+  static constexpr int STAGE = MAXRUN * L + TAPS;    // staged coarse samples (incl. halo)
+  HD static int skew(int i) { return i + (i >> 5); } // runs start 33 elements apart: no bank conflict
+  static constexpr int NPHASE = 2;
+  static constexpr size_t SMEM = (size_t)(STAGE + STAGE / 32 + 2) * sizeof(V);
+  template <int PH> HD static void phase(const Args &a, int bx, int by, int tid, void *smraw) {
+    V *sm = (V *)smraw;
+    const ScaleDesc d = a.descs[a.first + by];
+    const int R = 1 << a.log2R;
+    const int Nc = (int)(a.N >> a.log2R);
+    const int RB = R < NT ? R : NT;
+    const int NRUN = NT / RB;
+    const int MT = NRUN * L;                         // coarse positions per CTA
+    const int mtiles = (Nc + MT - 1) / MT;
+    const int mt = bx % mtiles, rb = bx / mtiles;
+    const int m0 = mt * MT;
+    if constexpr (PH == 0) {
+      const V *c = a.C + d.ip_coff;
+      for (int i = tid; i < MT + TAPS; i += NT) {
+        const int m = (m0 - (TAPS / 2 - 1) + i) & (Nc - 1);     // periodic on the coarse grid
+        sm[skew(i)] = ldg(&c[m]);
+      }
+    } else {
+      const int rl = tid % RB, j = tid / RB;
+      const int rho = rb * RB + rl;
+      const int ms = m0 + j * L;                     // first coarse position of this thread's run
+      T hw[TAPS];
+      const double *wt = a.wt + d.ip_woff + rho;
+#pragma unroll
+      for (int t = 0; t < TAPS; ++t) hw[t] = (T)ldg(&wt[(size_t)t * R]);
+      V win[TAPS];
+#pragma unroll
+      for (int t = 0; t < TAPS - 1; ++t) win[t] = sm[skew(j * L + t)];
+      // re-modulation e^{2 pi i kc n / Np}, n = R m + rho: table value at the start of the run and
+      // every 16 steps, recurrence (step e^{2 pi i kc R / Np}) in between -- in fp64 for both engines
+      const unsigned kc = (unsigned)d.ip_kc;
+      const double2 stepw = nroot(a.nt, kc * (unsigned)R);
+      double2 tw = make_double2(1.0, 0.0);
+      V *row = a.W + (size_t)d.row * a.n0;
+#pragma unroll
+      for (int s = 0; s < L; ++s) {
+        win[(s + TAPS - 1) % TAPS] = sm[skew(j * L + s + TAPS - 1)];
+        const int m = ms + s;
+        const long long n = (long long)m * R + rho;
+        if ((s & 15) == 0) tw = nroot(a.nt, kc * (unsigned)n);
+        T ar0 = 0, ai0 = 0, ar1 = 0, ai1 = 0;
+#pragma unroll
+        for (int t = 0; t < TAPS; t += 2) {
+          const V c0 = win[(s + t) % TAPS], c1 = win[(s + t + 1) % TAPS];
+          ar0 += c0.x * hw[t]; ai0 += c0.y * hw[t];
+          ar1 += c1.x * hw[t + 1]; ai1 += c1.y * hw[t + 1];
+        }
+        const V acc = mk<T>(ar0 + ar1, ai0 + ai1);
+        const V x = cmul(acc, mk<T>((T)tw.x, (T)tw.y));
+        tw = cmul(tw, stepw);
+        if (m < Nc && n < a.n0) {
+          if (a.epi == EPI_MULCONJ) row[n] = cmul(row[n], cconj(x));
+          else st_stream(&row[n], x);
+        }
+      }
     }
   }
 };

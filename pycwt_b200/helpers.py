@@ -4,7 +4,7 @@ from os import environ, makedirs
 from os.path import exists, expanduser
 
 import numpy as np
-import scipy.fft as fft  # the reference exposes its FFT backend module under this name
+import scipy.fftpack as fft  # the reference's backend module under the reference's name (helpers.py:22)
 
 # True: the reference's scipy branch (helpers.py:22-30), transforms zero-padded to the next power
 # of two.  False: the policy of its pyfftw branch (helpers.py:15-19), transforms at the signal's

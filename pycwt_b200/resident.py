@@ -24,6 +24,19 @@ from .wavelet import (_check_parameter_wavelet, _nan_rows, _precision, _resolve_
 __all__ = ['cwt_resident', 'ResidentTransform']
 
 
+def _live(method):
+    """Product methods run as one engine transaction: check that this transform is still the
+    resident one and evaluate, under the engine lock."""
+    import functools
+
+    @functools.wraps(method)
+    def wrapper(self, *args, **kwargs):
+        with self.engine.lock:
+            self._check_live()
+            return method(self, *args, **kwargs)
+    return wrapper
+
+
 class ResidentTransform(object):
     """W[S, n0] of one `cwt_resident` call, resident on the device."""
 
@@ -72,19 +85,19 @@ class ResidentTransform(object):
         return 1.0 / np.asarray(self.freqs)
 
     # -- the products --------------------------------------------------------------------
+    @_live
     def wave(self):
         """The coefficients themselves (complex128, S x n0): the expensive fetch."""
-        self._check_live()
         return self.engine.get_w(len(self.scales), self.n0, self.precision)
 
+    @_live
     def fft(self):
         """Normalised signal spectrum, as returned by `cwt` (wavelet.py:123)."""
-        self._check_live()
         return self.engine.signal_fft()
 
+    @_live
     def power(self, rectify=False, variance=None):
         """|W|^2, divided by the scale if `rectify` and by `variance` if given."""
-        self._check_live()
         rs = None
         if rectify or variance is not None:
             rs = np.ones(len(self.scales))
@@ -110,19 +123,19 @@ class ResidentTransform(object):
         hi[empty] = lo[empty]
         return lo, hi
 
+    @_live
     def global_power(self, inside_coi=False):
         """Time mean of |W|^2 per scale (`power.mean(axis=1)`); with `inside_coi` only over
         the columns where the period is inside the cone of influence (NaN if there are none)."""
-        self._check_live()
         if not inside_coi:
             return self.engine.global_power(len(self.scales))
         lo, hi = self.coi_ranges()
         return self.engine.global_power_ranges(lo, hi)
 
+    @_live
     def scale_avg_power(self, period_min, period_max, variance=1.0):
         """Scale-averaged power over period_min <= period < period_max (TC98 eq. 24 as in
         simple_sample.py:87-91): variance * dj * dt / Cdelta * sum_j |W_j|^2 / s_j."""
-        self._check_live()
         if self.wavelet.cdelta == -1:
             raise ValueError('Cdelta not defined for this wavelet')
         per = self.period
@@ -131,9 +144,9 @@ class ResidentTransform(object):
         w = w * (variance * self.dj * self.dt / self.wavelet.cdelta)
         return self.engine.scale_avg_power(w)
 
+    @_live
     def icwt(self):
         """Inverse transform of the resident coefficients (wavelet.py:169-170)."""
-        self._check_live()
         red = self.engine.icwt_sum()
         return self.dj * np.sqrt(self.dt) / (self.wavelet.cdelta * self.wavelet.psi(0)) * red
 
@@ -145,8 +158,12 @@ def cwt_resident(signal, dt, dj=1/12, s0=-1, J=-1, wavelet='morlet', freqs=None,
     (Paul at very large scales) are dropped here as well, so `.scales` / `.freqs` equal the
     ones `cwt` returns."""
     wavelet = _check_parameter_wavelet(wavelet)
-    if not hasattr(wavelet, '_engine_spec'):
-        raise TypeError("cwt_resident needs one of the analytic families (Morlet, Paul, DOG)")
+    spec = wavelet._engine_spec() if hasattr(wavelet, '_engine_spec') else None
+    if spec is None:
+        # duck-typed objects, subclasses that override psi_ft, non-integer or out-of-range orders
+        raise TypeError("cwt_resident needs one of the analytic families the engine evaluates "
+                        "itself: Morlet(f0), Paul(m) or DOG(m) with an integer order in [1, 64] "
+                        "and the stock psi_ft")
     n0 = len(signal)
     sj, freqs = _resolve_scales(n0, dt, dj, s0, J, wavelet, freqs)
     npad = fft_kwargs(signal)['n']
@@ -159,10 +176,11 @@ def cwt_resident(signal, dt, dj=1/12, s0=-1, J=-1, wavelet='morlet', freqs=None,
     sig = np.asarray(signal)
     if sig.dtype != np.float32:
         sig = np.asarray(sig, dtype=np.float64)
-    family, param = wavelet._engine_spec()
+    family, param = spec
     precision = _precision()
-    if _sync_padding(eng, n0):
-        precision = _engine.F64
-    eng.cwt(sig, dt, sj, family, param, precision, fetch=False)
-    serial = eng.job_serial()
+    with eng.lock:
+        if _sync_padding(eng, n0):
+            precision = _engine.F64
+        eng.cwt(sig, dt, sj, family, param, precision, fetch=False)
+        serial = eng.job_serial()
     return ResidentTransform(eng, wavelet, n0, dt, dj, sj, freqs, precision, serial)

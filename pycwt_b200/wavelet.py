@@ -48,18 +48,44 @@ def _resolve_scales(n0, dt, dj, s0, J, wavelet, freqs):
 
 
 def _nan_rows(wavelet, sj, npad, dt):
-    """Rows the reference would find all-NaN (wavelet.py:111): psi_ft evaluates to NaN at
-    some bin (Paul: inf*0 once s*pi/dt > 709.78).  Evaluated at the two extreme bins, where
-    overflow happens first; O(S) host work."""
+    """Rows the reference would find all-NaN and drop (wavelet.py:111-115), for the analytic
+    families, in O(S) host work:
+      * psi_ft evaluates to NaN at some bin -- Paul: inf*0 once s*pi/dt > 709.78.  Overflow
+        happens first at the two extreme bins, which are the ones evaluated here;
+      * the scale itself is unusable: a custom `freqs` entry of 0 gives s = inf (inf*0 at bin 0),
+        a negative one gives the square root of a negative normalisation (wavelet.py:103), NaN
+        stays NaN.
+    Duck-typed wavelets do not come here: their rows are classified from the host-evaluated
+    response table (`_response_table`)."""
     # the entries of fft.fftfreq(npad, dt) at the most negative and the most positive bin
     # (k / (npad*dt) with the signed bin number k, computed like numpy does:
     # k * (1.0 / (npad * dt))) without building the array.  Any npad: for an odd length the
     # most negative bin is -(npad-1)/2 at index (npad+1)/2.
     k = np.array([-(npad // 2), (npad - 1) // 2])
     edge = 2 * np.pi * (k * (1.0 / (npad * dt)))
+    sj = np.asarray(sj, dtype=float)
     with np.errstate(all='ignore'):
         resp = wavelet.psi_ft(sj[:, None] * edge[None, :])
-    return np.isnan(resp).any(axis=1)
+        unusable = ~np.isfinite(sj) | (sj < 0)
+        if npad == 2:
+            # fftfreq(2)[1] is negative: the reference's normalisation is NaN for every s > 0
+            unusable = unusable | (sj > 0)
+    return np.isnan(resp).any(axis=1) | unusable
+
+
+def _response_table(wavelet, sj, npad, dt):
+    """sqrt(s*w1*N) * conj(psi_ft(s*w)) on the [S, Np] grid, exactly as wavelet.py:102-104
+    forms it: the host-evaluated path of duck-typed wavelets."""
+    ftfreqs = 2 * np.pi * fft.fftfreq(npad, dt)
+    col = np.asarray(sj)[:, np.newaxis]
+    with np.errstate(all='ignore'):
+        return ((col * ftfreqs[1] * npad) ** .5 *
+                np.conjugate(wavelet.psi_ft(col * ftfreqs))).astype(np.complex128)
+
+
+def _engine_family(wavelet):
+    """(family, param) when the engine evaluates this wavelet analytically, else None."""
+    return wavelet._engine_spec() if hasattr(wavelet, '_engine_spec') else None
 
 
 def _sync_padding(eng, n0):
@@ -69,13 +95,14 @@ def _sync_padding(eng, n0):
     return (not _helpers._FFT_NEXT_POW2) and (n0 & (n0 - 1)) != 0
 
 
-def _transform(signal, dt, sj, wavelet, precision=None, engine=None):
-    """W[S, n0] (complex128) for the given scales; rows are NOT yet NaN-filtered."""
+def _transform(signal, dt, sj, wavelet, precision=None, engine=None, table=None):
+    """W[S, n0] (complex128) for the given scales; rows are NOT yet NaN-filtered.  `table`:
+    rows of `_response_table` for `sj` (duck-typed wavelets).  The caller holds the engine lock."""
     eng = engine or _engine.default_engine()
     precision = _precision() if precision is None else precision
     if _sync_padding(eng, len(signal)):
         precision = _engine.F64      # un-padded transforms run in fp64
-    spec = wavelet._engine_spec() if hasattr(wavelet, '_engine_spec') else None
+    spec = _engine_family(wavelet)
     sig = np.asarray(signal)
     if sig.dtype != np.float32:
         sig = np.asarray(sig, dtype=np.float64)
@@ -85,11 +112,8 @@ def _transform(signal, dt, sj, wavelet, precision=None, engine=None):
     else:
         # duck-typed wavelet: the host evaluates psi_ft on the [S, Np] grid exactly as
         # wavelet.py:102-104 does; the device multiplies and inverse-transforms.
-        npad = fft_kwargs(sig)['n']
-        ftfreqs = 2 * np.pi * fft.fftfreq(npad, dt)
-        col = np.asarray(sj)[:, np.newaxis]
-        table = ((col * ftfreqs[1] * npad) ** .5 *
-                 np.conjugate(wavelet.psi_ft(col * ftfreqs))).astype(np.complex128)
+        if table is None:
+            table = _response_table(wavelet, sj, fft_kwargs(sig)['n'], dt)
         W = eng.cwt(sig, dt, sj, _engine.TABLE, 0.0, precision, table=table)
     return W, eng
 
@@ -99,13 +123,20 @@ def cwt(signal, dt, dj=1/12, s0=-1, J=-1, wavelet='morlet', freqs=None):
 
     Returns (W, sj, freqs, coi, fft, fftfreqs) exactly like the reference: W is
     complex128 of shape (len(sj), len(signal)); scales whose transform is all-NaN
-    (Paul at very large scales) are removed from W, sj and freqs."""
+    (Paul at very large scales, unusable custom frequencies) are removed from W, sj and
+    freqs.  A complex signal is transformed like the reference does (its FFT is linear):
+    real and imaginary parts go through the engine separately."""
     wavelet = _check_parameter_wavelet(wavelet)
     n0 = len(signal)
     sj, freqs = _resolve_scales(n0, dt, dj, s0, J, wavelet, freqs)
     npad = fft_kwargs(signal)['n']
 
-    bad = _nan_rows(wavelet, np.asarray(sj, dtype=float), npad, dt)
+    table = None
+    if _engine_family(wavelet) is None:
+        table = _response_table(wavelet, np.asarray(sj, dtype=float), npad, dt)
+        bad = np.isnan(table).any(axis=1)
+    else:
+        bad = _nan_rows(wavelet, np.asarray(sj, dtype=float), npad, dt)
     keep = ~bad
 
     # O(n0) host-side outputs (cone of influence, Fourier frequencies): for long signals they
@@ -123,15 +154,32 @@ def cwt(signal, dt, dj=1/12, s0=-1, J=-1, wavelet='morlet', freqs=None):
     if n0 >= (1 << 16):
         helper = _threading.Thread(target=host_side)
         helper.start()
+    sig = np.asarray(signal)
+    parts = [sig.real, sig.imag] if np.iscomplexobj(sig) else [sig]
+    eng = _engine.default_engine()
     try:
+        Ws, spectra = [], []
+        for part in parts:
+            # one engine transaction per transform: length policy, transform, coefficients and
+            # the spectrum of the SAME resident job (the default engine is shared by all threads)
+            with eng.lock:
+                if keep.any():
+                    Wp, _ = _transform(part, dt, np.asarray(sj)[keep], wavelet, engine=eng,
+                                       table=None if table is None else table[keep])
+                else:
+                    # every row NaN: the reference keeps them all (np.any(sel) is False)
+                    _transform(part, dt, np.asarray(sj)[:1], wavelet, engine=eng,
+                               table=None if table is None else np.zeros_like(table[:1]))
+                    Wp = np.full((len(sj), n0), np.nan + 1j * np.nan)
+                Ws.append(Wp)
+                spectra.append(eng.signal_fft())
         if keep.any():
-            W, eng = _transform(signal, dt, np.asarray(sj)[keep], wavelet)
             sj, freqs = sj[keep], freqs[keep]
+        if len(parts) == 2:
+            W = Ws[0] + 1j * Ws[1]
+            spectrum = spectra[0] + 1j * spectra[1]
         else:
-            # every row NaN: the reference keeps them all (np.any(sel) is False)
-            _, eng = _transform(signal, dt, np.asarray(sj)[:1], wavelet)
-            W = np.full((len(sj), n0), np.nan + 1j * np.nan)
-        spectrum = eng.signal_fft()
+            W, spectrum = Ws[0], spectra[0]
     finally:
         if helper is not None:
             helper.join()
@@ -246,9 +294,10 @@ def xwt(y1, y2, dt, dj=1/12, s0=-1, J=-1, significance_level=0.95,
     if not keep.any():
         keep[:] = True
     sj, freq = sj[keep], freq[keep]
-    eng = _pair_engine(wavelet)
-    _sync_padding(eng, n0)
-    W12 = eng.xwt(y1n, y2n, dt, sj, *_family_of(wavelet))
+    eng = _engine.default_engine()
+    with eng.lock:
+        _sync_padding(eng, n0)
+        W12 = eng.xwt(y1n, y2n, dt, sj, *_family_of(wavelet))
     coi = (n0 / 2 - np.abs(np.arange(0, n0) - (n0 - 1) / 2))
     coi = wavelet.flambda() * wavelet.coi() * dt * coi
 
@@ -265,15 +314,11 @@ def xwt(y1, y2, dt, dj=1/12, s0=-1, J=-1, significance_level=0.95,
 
 
 def _family_of(wavelet):
-    spec = wavelet._engine_spec() if hasattr(wavelet, '_engine_spec') else None
+    spec = _engine_family(wavelet)
     if spec is None:
         raise NotImplementedError(
             'xwt/wct on the GPU need a Morlet, Paul or DOG mother wavelet')
     return spec
-
-
-def _pair_engine(wavelet):
-    return _engine.default_engine()
 
 
 def _boxcar_len(wavelet, dj):
@@ -301,10 +346,11 @@ def wct(y1, y2, dt, dj=1/12, s0=-1, J=-1, sig=True,
     y2, y2n, _ = _standardise(y2, normalize)
     n0 = y1n.size
     sj, freq = _resolve_scales(n0, dt, dj, s0, J, wavelet, None)
-    eng = _pair_engine(wavelet)
-    _sync_padding(eng, len(y1n))
-    WCT, aWCT = eng.wct(y1n, y2n, dt, dj, sj, *_family_of(wavelet),
-                                          boxcar_len=_boxcar_len(wavelet, dj))
+    eng = _engine.default_engine()
+    with eng.lock:
+        _sync_padding(eng, len(y1n))
+        WCT, aWCT = eng.wct(y1n, y2n, dt, dj, sj, *_family_of(wavelet),
+                            boxcar_len=_boxcar_len(wavelet, dj))
     coi = (n0 / 2 - np.abs(np.arange(0, n0) - (n0 - 1) / 2))
     coi = wavelet.flambda() * wavelet.coi() * dt * coi
     if sig:
@@ -341,8 +387,7 @@ def _mc_histogram(prob, dt, dj, wavelet, draw, indices, progress=False, engine=N
     (reference wavelet.py:609-630), accumulated on the GPU: int64 [S, nbins]."""
     N, sj, nbins = prob['N'], prob['sj'], prob['nbins']
     hist = np.zeros((sj.size, nbins), dtype=np.int64)
-    eng = engine or _pair_engine(wavelet)
-    _sync_padding(eng, N)
+    eng = engine or _engine.default_engine()
     fam = _family_of(wavelet)
     indices = list(indices)
     batch = max(1, min(len(indices), int((256 << 20) // (16 * N)) or 1))
@@ -352,8 +397,10 @@ def _mc_histogram(prob, dt, dj, wavelet, draw, indices, progress=False, engine=N
         noise = np.empty((len(idx), 2, N))
         for k, i in enumerate(idx):
             noise[k, 0], noise[k, 1] = draw(i)
-        eng.wct_mc(noise, dt, dj, sj, fam[0], fam[1], _boxcar_len(wavelet, dj), prob['mask'],
-                   prob['maxscale'], nbins, hist)
+        with eng.lock:
+            _sync_padding(eng, N)
+            eng.wct_mc(noise, dt, dj, sj, fam[0], fam[1], _boxcar_len(wavelet, dj), prob['mask'],
+                       prob['maxscale'], nbins, hist)
         bar.update(len(idx))
     bar.close()
     return hist
@@ -422,10 +469,11 @@ def _smooth_device(W, dt, dj, scales, deltaj0):
         # deltaj0 = -1 (f0 != 6): the reference fails inside rect()
         raise ValueError('smoothing window undefined for this wavelet (deltaj0 = -1)')
     eng = _engine.default_engine()
-    _sync_padding(eng, W.shape[1])
-    if np.isreal(W).all():
-        return eng.smooth(np.ascontiguousarray(W.real, dtype=np.float64), dt, scales, klen)
-    return eng.smooth(np.ascontiguousarray(W, dtype=np.complex128), dt, scales, klen)
+    with eng.lock:
+        _sync_padding(eng, W.shape[1])
+        if np.isreal(W).all():
+            return eng.smooth(np.ascontiguousarray(W.real, dtype=np.float64), dt, scales, klen)
+        return eng.smooth(np.ascontiguousarray(W, dtype=np.complex128), dt, scales, klen)
 
 
 def _check_parameter_wavelet(wavelet):

@@ -42,17 +42,59 @@ def test_cwt_kernels_vs_reference_fixture(emu, name):
 
 
 def test_every_pruned_class_and_dense_path(emu):
+    """Exact mode (expansion off): every pruned length 2^5..2^15 and the dense path."""
     n = 2 ** 15
     t = np.arange(n) / n
     x = np.sin(2 * np.pi * (50 * t + (n / 8) * t ** 2)) + 0.1 * np.random.RandomState(1).randn(n)
     sj = 2.0 * 2 ** (np.arange(0, 27) / 2.0)
-    W = emu.cwt(x, 1.0, sj, 0, 6.0)
-    plan = emu.last_plan(len(sj))
-    assert set(plan) >= set(range(5, 16)), plan   # single, direct (11..13), two-kernel, dense
     Wr = orc.cwt(x, 1.0, wavelet=orc.Morlet(6), freqs=1 / (orc.Morlet(6).flambda() * sj))[0]
-    assert relerr(W, Wr) < 1e-10
-    W32 = emu.cwt(x.astype(np.float32), 1.0, sj, 0, 6.0, precision=1)
-    assert relerr(W32, Wr) < 1e-5
+    emu.set_expand_eps(0.0, 0.0)
+    try:
+        W = emu.cwt(x, 1.0, sj, 0, 6.0)
+        plan = emu.last_plan(len(sj))
+        assert set(plan) >= set(range(5, 16)), plan   # single, direct (11..13), two-kernel, dense
+        assert relerr(W, Wr) < 1e-14
+        W32 = emu.cwt(x.astype(np.float32), 1.0, sj, 0, 6.0, precision=1)
+        assert relerr(W32, Wr) < 1e-5
+    finally:
+        emu.set_expand_eps()
+
+
+def test_expansion_path_every_coarse_length(emu):
+    """Default mode: scales whose band is <= 1/32 of the transform length run as coarse transform +
+    polyphase Kaiser-Bessel expansion (kernels.cuh: ExpandBody); every family, fp64 and fp32,
+    including the cross-product epilogue.  The alias bound is 5e-13; measured ~1e-14."""
+    n = 2 ** 15
+    t = np.arange(n) / n
+    x = np.sin(2 * np.pi * (50 * t + (n / 8) * t ** 2)) + 0.1 * np.random.RandomState(1).randn(n)
+    sj = 2.0 * 2 ** (np.arange(0, 27) / 2.0)
+    for fam, ref, par, s in ((0, orc.Morlet(6), 6.0, sj), (1, orc.Paul(4), 4.0, sj[:14]),
+                             (2, orc.DOG(2), 2.0, sj), (2, orc.DOG(3), 3.0, sj)):
+        Wr = orc.cwt(x, 1.0, wavelet=ref, freqs=1 / (ref.flambda() * s))[0]
+        W = emu.cwt(x, 1.0, s, fam, par)
+        plan = emu.last_plan(len(s))
+        assert min(plan) < 0 and max(plan) == 15 or fam == 1, plan
+        assert relerr(W, Wr) < 2e-13, (fam, relerr(W, Wr))
+        # every expansion row on its own (the class maximum hides the small rows)
+        rows = [i for i, p in enumerate(plan) if p < 0]
+        assert rows
+        for i in rows:
+            assert np.abs(W[i] - Wr[i]).max() < 2e-13 * np.abs(Wr).max()
+        W32 = emu.cwt(x.astype(np.float32), 1.0, s, fam, par, precision=1)
+        assert min(emu.last_plan(len(s))) < 0
+        assert relerr(W32, Wr) < 1e-5
+    # Morlet: coarse lengths 2^6 .. 2^12 all occur
+    emu.cwt(x, 1.0, sj, 0, 6.0)
+    assert set(emu.last_plan(len(sj))) >= set(range(-12, -5)), emu.last_plan(len(sj))
+    # odd length (trimmed output), cross-product epilogue on expansion rows
+    rs = np.random.RandomState(5)
+    y1, y2 = rs.randn(5001), rs.randn(5001)
+    s2 = 2.0 * 2 ** (np.arange(0, 20) / 2.0)
+    m = orc.Morlet(6)
+    W1 = orc.cwt(y1, 1.0, wavelet=m, freqs=1 / (m.flambda() * s2))[0]
+    W2 = orc.cwt(y2, 1.0, wavelet=m, freqs=1 / (m.flambda() * s2))[0]
+    assert relerr(emu.xwt(y1, y2, 1.0, s2, 0, 6.0), W1 * np.conj(W2)) < 2e-13
+    assert min(emu.last_plan(len(s2))) < 0
 
 
 def test_xwt_wct_smooth_kernels(emu):

@@ -121,13 +121,47 @@ def test_lengths_edge_cases(pycwt, n0):
 
 
 def test_all_plan_classes_exercised(pycwt):
-    """One transform that uses every pruned length 2^5..2^16 and the dense path."""
+    """One transform that uses every pruned length 2^5..2^16 and the dense path (exact mode:
+    expansion path off), then the same transform in the default mode (expansion path on)."""
     x = chirp(2 ** 16) + 0.1 * np.random.RandomState(1).randn(2 ** 16)
-    W, sj, *_ = pycwt.cwt(x, 1.0, dj=0.5, s0=2.0, J=30, wavelet=pycwt.Morlet(6))
-    plan = pycwt.default_engine().last_plan(len(sj))
-    assert set(plan) >= set(range(5, 17)), plan
     Wr = orc.cwt(x, 1.0, dj=0.5, s0=2.0, J=30, wavelet=orc.Morlet(6))[0]
-    assert relerr(W, Wr) < TOL64
+    eng = pycwt.default_engine()
+    eng.set_expand_eps(0.0, 0.0)
+    try:
+        W, sj, *_ = pycwt.cwt(x, 1.0, dj=0.5, s0=2.0, J=30, wavelet=pycwt.Morlet(6))
+        plan = eng.last_plan(len(sj))
+        assert set(plan) >= set(range(5, 17)), plan
+        assert relerr(W, Wr) < 1e-14
+    finally:
+        eng.set_expand_eps()
+    W, sj, *_ = pycwt.cwt(x, 1.0, dj=0.5, s0=2.0, J=30, wavelet=pycwt.Morlet(6))
+    plan = eng.last_plan(len(sj))
+    assert set(plan) >= set(range(-13, -5)) and max(plan) == 16, plan   # coarse grids 2^6..2^13
+    assert relerr(W, Wr) < 2e-13
+    for i, p in enumerate(plan):
+        if p < 0:
+            assert np.abs(W[i] - Wr[i]).max() < 2e-13 * np.abs(Wr).max(), (i, p)
+
+
+def test_expansion_path_families_and_precisions(pycwt, monkeypatch):
+    """Expansion rows of every family against the oracle, fp64 (alias bound 5e-13) and fp32."""
+    x = chirp(2 ** 15) + 0.1 * np.random.RandomState(3).randn(2 ** 15)
+    eng = pycwt.default_engine()
+    cases = ((pycwt.Morlet(6), orc.Morlet(6), dict(s0=2.0, dj=0.5, J=26)),
+             (pycwt.Paul(4), orc.Paul(4), dict(s0=2.0, dj=0.5, J=13)),
+             (pycwt.DOG(2), orc.DOG(2), dict(s0=2.0, dj=0.5, J=26)),
+             (pycwt.DOG(3), orc.DOG(3), dict(s0=2.0, dj=0.5, J=26)))
+    for mother, ref, kw in cases:
+        Wr = orc.cwt(x, 1.0, wavelet=ref, **kw)[0]
+        W, sj, *_ = pycwt.cwt(x, 1.0, wavelet=mother, **kw)
+        assert min(eng.last_plan(len(sj))) < 0
+        assert relerr(W, Wr) < 2e-13, (type(mother).__name__, relerr(W, Wr))
+    monkeypatch.setenv("CWTB_PRECISION", "fp32")
+    for mother, ref, kw in cases:
+        Wr = orc.cwt(x, 1.0, wavelet=ref, **kw)[0]
+        W, sj, *_ = pycwt.cwt(x.astype(np.float32), 1.0, wavelet=mother, **kw)
+        assert min(eng.last_plan(len(sj))) < 0
+        assert relerr(W, Wr) < TOL32
 
 
 def test_fp32_engine(pycwt, monkeypatch):
