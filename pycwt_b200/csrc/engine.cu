@@ -61,6 +61,9 @@ static inline int rt_memset(void *d, int v, size_t n, rt_stream st) { return (in
 static inline int rt_sync(rt_stream st) { return (int)cudaStreamSynchronize(st); }
 static inline const char *rt_errstr(int e) { return cudaGetErrorString((cudaError_t)e); }
 
+template <class B, class = void> struct BodyMinB { static constexpr int value = CWTB_MINB; };
+template <class B> struct BodyMinB<B, std::void_t<decltype(B::MINB)>> { static constexpr int value = B::MINB; };
+
 template <class Body, int PH>
 __device__ __forceinline__ void run_phases(const typename Body::Args &a, void *sm) {
   Body::template phase<PH>(a, (int)blockIdx.x, (int)blockIdx.y, (int)threadIdx.x, sm);
@@ -78,7 +81,7 @@ __device__ __forceinline__ void run_phases_at(const typename Body::Args &a, int 
   }
 }
 template <class Body>
-__global__ void __launch_bounds__(BodyNT<Body>::value, CWTB_MINB) k_run(const __grid_constant__ typename Body::Args a) {
+__global__ void __launch_bounds__(BodyNT<Body>::value, BodyMinB<Body>::value) k_run(const __grid_constant__ typename Body::Args a) {
   extern __shared__ __align__(16) unsigned char smraw[];
   run_phases<Body, 0>(a, smraw);
 }
@@ -162,6 +165,7 @@ struct cwtb_ctx {
   int direct_max_log2 = 13;
   int fused = 0;     // experimental: two-kernel scales through one persistent kernel (CWTB_FUSED=1)
   int ring = 3;      // Z ring slots of the fused kernel
+  int pipe_ahead = 2;   // CWTB_FUSED=2: scales the first kernel runs in front of the second (CWTB_AHEAD)
   int num_sms = 148;
   int pf_dist = 148;   // PassB: L2 prefetch distance in tiles (CWTB_PF_DIST)
   int gauss_rec = 1;   // dense Morlet scales: Gaussian by recurrence (CWTB_GAUSS_REC=0: exp per bin)
@@ -952,10 +956,8 @@ __global__ void __launch_bounds__(TileCfg<T>::NT, 3) k_fused(const __grid_consta
     if (isB) run_phases_at<B, 0>(f.b, (int)tile, s, smraw);
     else run_phases_at<A, 0>(f.a, (int)tile, s, smraw);
     __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence();
-      atomicAdd(isB ? &doneB[s] : &doneA[s], 1u);
-    }
+    if (threadIdx.x == 0)   // release-add, no L1 invalidate (see k_pipe)
+      asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(isB ? &doneB[s] : &doneA[s]), "r"(1u) : "memory");
   }
 }
 #endif
@@ -1037,6 +1039,167 @@ static int dispatch_fused(cwtb_ctx *c, int log2K1, const PassAArgs<T> &a, const 
   return fail(c, CWTB_ERR_UNSUPPORTED, "transform longer than 2^20 per row is not supported yet");
 }
 
+// ======================================================================================
+// Pipelined persistent two-pass kernel (CWTB_FUSED=2): like k_fused, but built so that the
+// bookkeeping stays off the critical path.
+//   * static schedule: CTA b runs tiles b, b + grid, b + 2 grid, ... of the global order
+//         A(0) .. A(ahead-1) | A(ahead) B(0) | A(ahead+1) B(1) | ... | B(n-ahead) .. B(n-1)
+//     (no queue atomic); the first kernel runs `ahead` scales in front of the second one, so the
+//     tiles a B(s) tile depends on were handed out >= ahead*tilesA positions earlier -- more than
+//     the number of resident CTAs for ahead = 2 -- and the dependency wait almost never blocks;
+//   * a CTA tests a dependency once per scale (not per tile): counters doneA[s] / doneB[s];
+//   * completion is published by the LAST thread of the CTA (fence + relaxed add) while the
+//     first warp already issues the next tile's bulk copies.
+// Z is a ring of `ring` >= ahead + 2 scale buffers (16 MiB each at Np = 2^20) that stays in L2:
+// the second kernel's tile loads hit L2 and the intermediate never reaches HBM.
+// ======================================================================================
+template <typename T> struct PipeArgs {
+  PassAArgs<T> a;
+  PassBArgs<T> b;
+  unsigned *ctr;    // [0 .. n) doneA, [n .. 2n) doneB
+  int nscales, ring, ahead;
+  unsigned tilesA, tilesB;
+};
+
+HD void pipe_decode(unsigned t, int n, int ahead, unsigned TA, unsigned TB, int *isB, int *s, unsigned *tile) {
+  const int na = ahead < n ? ahead : n;
+  if (t < (unsigned)na * TA) { *isB = 0; *s = (int)(t / TA); *tile = t % TA; return; }
+  t -= (unsigned)na * TA;
+  const unsigned per = TA + TB;
+  const int nmid = n - na;
+  if (t < (unsigned)nmid * per) {
+    const unsigned blk = t / per, off = t % per;
+    if (off < TA) { *isB = 0; *s = na + (int)blk; *tile = off; }
+    else { *isB = 1; *s = (int)blk; *tile = off - TA; }
+    return;
+  }
+  t -= (unsigned)nmid * per;
+  *isB = 1; *s = nmid + (int)(t / TB); *tile = t % TB;
+}
+
+#ifndef CWTB_HOST_EMU
+template <typename T, int K1, int MODE>
+__global__ void __launch_bounds__(TileCfg<T>::NT, 3) k_pipe(const __grid_constant__ PipeArgs<T> f) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  using A = PassABody<T, K1, MODE, +1>;
+  using B = PassBBody<T, +1>;
+  const int n = f.nscales;
+  const unsigned total = (unsigned)n * (f.tilesA + f.tilesB);
+  unsigned *doneA = f.ctr, *doneB = f.ctr + n;
+  int okA = -1, okB = -1;    // dependencies already seen complete by this CTA
+  for (unsigned t = blockIdx.x; t < total; t += gridDim.x) {
+    int isB, s;
+    unsigned tile;
+    pipe_decode(t, n, f.ahead, f.tilesA, f.tilesB, &isB, &s, &tile);
+    const int dep = isB ? s : s - f.ring;          // A(s) reuses the slot of B(s - ring)
+    if (dep >= 0 && dep > (isB ? okA : okB)) {
+      if (threadIdx.x == 0) {
+        const unsigned *flag = isB ? &doneA[dep] : &doneB[dep];
+        const unsigned want = isB ? f.tilesA : f.tilesB;
+        while (ld_acquire_u32(flag) < want) __nanosleep(64);
+        asm volatile("fence.proxy.async;" ::: "memory");
+      }
+      __syncthreads();
+      if (isB) okA = dep; else okB = dep;
+    }
+    if (isB) run_phases_at<B, 0>(f.b, (int)tile, s, smraw);
+    else run_phases_at<A, 0>(f.a, (int)tile, s, smraw);
+    __syncthreads();   // shared memory is free again; every store of the tile has been issued
+    if (threadIdx.x == blockDim.x - 1) {
+      // release-add: orders the tile's stores (made visible to this thread by the barrier) before
+      // the count.  NOT __threadfence(): a gpu-scope fence also invalidates the SM's L1
+      // (SASS CCTL.IVALL) -- once per tile that evicts the twiddle / root tables of every
+      // resident CTA; the release form compiles to MEMBAR.ALL.GPU + REDG only.
+      asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(isB ? &doneB[s] : &doneA[s]), "r"(1u) : "memory");
+    }
+  }
+}
+#endif
+
+template <typename T, int K1, int MODE>
+static int launch_pipe(cwtb_ctx *c, const PassAArgs<T> &a, const PassBArgs<T> &b, int nscales) {
+  using A = PassABody<T, K1, MODE, +1>;
+  using B = PassBBody<T, +1>;
+  PipeArgs<T> f;
+  f.a = a; f.b = b;
+  f.nscales = nscales;
+  f.ring = c->ring;
+  f.ahead = std::max(1, std::min(c->pipe_ahead, c->ring - 1));
+  f.a.zmod = f.b.zmod = c->ring;
+  f.b.rev = 0; f.b.pf_dist = 0; f.a.pf_dist = 0;
+  const unsigned M = a.N / ((unsigned)K1 * K2C);
+  f.tilesA = M * (K2C / A::T2);
+  f.tilesB = (a.N / K2C + Lay<T, K2C>::P - 1) / Lay<T, K2C>::P;
+  int e = ensure(c, c->ctr, (size_t)(2 * nscales) * sizeof(unsigned));
+  if (e) return e;
+  f.ctr = (unsigned *)c->ctr.p;
+  RT(rt_memset(c->ctr.p, 0, (size_t)(2 * nscales) * sizeof(unsigned), c->cur));
+#ifdef CWTB_HOST_EMU
+  std::vector<unsigned char> sm(std::max(A::SMEM, B::SMEM) + 64);
+  const unsigned total = (unsigned)nscales * (f.tilesA + f.tilesB);
+  std::vector<int> seenA(nscales, 0), seenB(nscales, 0);
+  for (unsigned t = 0; t < total; ++t) {
+    int isB, s;
+    unsigned tile;
+    pipe_decode(t, nscales, f.ahead, f.tilesA, f.tilesB, &isB, &s, &tile);
+    // the sequential emulation checks the schedule's invariants instead of waiting
+    if (isB && seenA[s] != (int)f.tilesA) return fail(c, CWTB_ERR_STATE, "pipe schedule: B before its A tiles");
+    if (!isB && s >= f.ring && seenB[s - f.ring] != (int)f.tilesB)
+      return fail(c, CWTB_ERR_STATE, "pipe schedule: Z slot reused before its B tiles");
+    if (isB) { emu_phases<B, 0>(f.b, (int)tile, s, sm.data()); seenB[s]++; }
+    else { emu_phases<A, 0>(f.a, (int)tile, s, sm.data()); seenA[s]++; }
+  }
+  c->launches++;
+  return 0;
+#else
+  const size_t smem = std::max(A::SMEM, B::SMEM);
+  auto kern = k_pipe<T, K1, MODE>;
+  const void *fn = (const void *)kern;
+  if (!c->configured.count(fn)) {
+    RT(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    c->configured.insert(fn);
+  }
+  int occ = 0;
+  RT(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TileCfg<T>::NT, smem));
+  if (occ < 1) return fail(c, CWTB_ERR_CUDA, "pipelined kernel does not fit on an SM");
+  const unsigned total = (unsigned)nscales * (f.tilesA + f.tilesB);
+  // every CTA must be resident (they wait for one another): at most occ per SM
+  const unsigned grid = std::min<unsigned>(total, (unsigned)(occ * c->num_sms));
+  int ev = -1;
+  if (c->profiling) {
+    ev = (int)c->prof.size() * 2;
+    while ((int)c->prof_events.size() < ev + 2) {
+      cudaEvent_t e2;
+      RT(cudaEventCreate(&e2));
+      c->prof_events.push_back(e2);
+    }
+    char nm[64];
+    snprintf(nm, sizeof nm, "PipeAB<%s, %d, %d>", sizeof(T) == 8 ? "double" : "float", K1, MODE);
+    c->prof.push_back({nm, grid, (unsigned)nscales, ev});
+    RT(cudaEventRecord(c->prof_events[ev], c->cur));
+  }
+  kern<<<grid, TileCfg<T>::NT, smem, c->cur>>>(f);
+  RT(cudaGetLastError());
+  if (ev >= 0) RT(cudaEventRecord(c->prof_events[ev + 1], c->cur));
+  c->launches++;
+  return 0;
+#endif
+}
+
+template <typename T, int MODE>
+static int dispatch_pipe(cwtb_ctx *c, int log2K1, const PassAArgs<T> &a, const PassBArgs<T> &b, int n) {
+  switch (log2K1) {
+    case 4: return launch_pipe<T, 16, MODE>(c, a, b, n);
+    case 5: return launch_pipe<T, 32, MODE>(c, a, b, n);
+    case 6: return launch_pipe<T, 64, MODE>(c, a, b, n);
+    case 7: return launch_pipe<T, 128, MODE>(c, a, b, n);
+    case 8: return launch_pipe<T, 256, MODE>(c, a, b, n);
+    case 9: return launch_pipe<T, 512, MODE>(c, a, b, n);
+    case 10: return launch_pipe<T, 1024, MODE>(c, a, b, n);
+  }
+  return fail(c, CWTB_ERR_UNSUPPORTED, "pipelined two-pass kernel: unsupported first-pass length");
+}
+
 template <typename T, int K>
 static int launch_single(cwtb_ctx *c, const SingleArgs<T> &a, int count) {
   constexpr int P = Lay<T, K>::P;
@@ -1058,6 +1221,10 @@ static bool class_single(const cwtb_ctx *c, const Job &job, const ClassRun &cl) 
 static bool class_two_kernel(const cwtb_ctx *c, const Job &job, const ClassRun &cl) {
   return !cl.expand && !class_single(c, job, cl);
 }
+// two-kernel class that runs as ONE persistent launch over a ring of Z buffers
+static bool class_persistent(const cwtb_ctx *c, const ClassRun &cl) {
+  return c->fused == 1 || (c->fused == 2 && cl.log2K >= 14 && cl.log2K <= 20 && cl.count <= 256);
+}
 
 // Which band-chunk region / Z buffer / stream a two-kernel class uses: its position among the
 // two-kernel classes modulo the number of chains (dense classes included, they only use Z).
@@ -1075,7 +1242,7 @@ static size_t band_chunk_elems(const cwtb_ctx *c, const Job &job, int G) {
   size_t bchunk = 0;
   for (const ClassRun &cl : job.classes)
     if (class_two_kernel(c, job, cl) && cl.log2K < job.log2N)
-      bchunk = std::max(bchunk, (size_t)(c->fused ? cl.count : std::min(G, cl.count)) << cl.log2K);
+      bchunk = std::max(bchunk, (size_t)(class_persistent(c, cl) ? cl.count : std::min(G, cl.count)) << cl.log2K);
   return bchunk;
 }
 
@@ -1085,7 +1252,10 @@ static int launch_expand_t(cwtb_ctx *c, const ExpandArgs<T> &a, int rows) {
   const int R = 1 << a.log2R;
   const int Nc = (int)(a.N >> a.log2R);
   const int RB = std::min(R, B::NT), MT = (B::NT / RB) * B::L;
-  return launch<B>(c, (unsigned)((R / RB) * ((Nc + MT - 1) / MT)), rows, a);
+  const unsigned gx = (unsigned)((R / RB) * ((Nc + MT - 1) / MT));
+  if (R < B::MINR) return fail(c, CWTB_ERR_STATE, "expansion factor below the kernel's minimum");
+  if (a.epi == EPI_MULCONJ) return launch<ExpandBody<T, TAPS, EPI_MULCONJ>>(c, gx, rows, a);
+  return launch<B>(c, gx, rows, a);
 }
 template <typename T>
 static int launch_expand(cwtb_ctx *c, int taps, const ExpandArgs<T> &a, int rows) {
@@ -1271,12 +1441,13 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
       }
       continue;
     }
-    const int chunk = c->fused ? cl.count : G;   // fused: the whole class in one persistent launch
+    const bool persistent = class_persistent(c, cl);
+    const int chunk = persistent ? cl.count : G;   // persistent: the whole class in one launch
     // successive two-kernel classes rotate over the chains, each with its own stream, Z buffer
     // and band-chunk region (descriptor offsets already point into the right region)
     const int chain = split2 ? job_chain_region(c, job, cl) : 0;
     Buf &Zb = chain > 0 ? c->Zc[chain - 1] : c->Z;
-    if ((e = ensure(c, Zb, (size_t)(c->fused ? c->ring : G) * N * sizeof(V)))) return e;
+    if ((e = ensure(c, Zb, (size_t)(persistent ? c->ring : G) * N * sizeof(V)))) return e;
 #ifndef CWTB_HOST_EMU
     c->cur = chain > 0 ? c->chain_streams[chain - 1] : c->stream;
 #endif
@@ -1291,7 +1462,7 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
       // (fp32: the 512-point tile has an odd row pitch, its rows would not be 16-byte aligned)
       constexpr bool k512_ok = (Lay<T, 512, true>::PITCH * sizeof(V)) % 16 == 0;
       // 512 pays up to K' = 2^16 (measured per class: first kernel + second kernel per row)
-      const int l2k = (dense || c->fused || cl.log2K > c->k2_512_max_log2 || !k512_ok) ? 10 : c->k2_band_log2;
+      const int l2k = (dense || persistent || cl.log2K > c->k2_512_max_log2 || !k512_ok) ? 10 : c->k2_band_log2;
       a.pf_dist = c->pf_dist_a; a.K2 = 1u << l2k; a.gauss_rec = c->gauss_rec;
       PassBArgs<T> b{};
       b.Z = (const V *)Zb.p; b.out = W; b.tw = Tw<T>::get(c); b.descs = ddesc;
@@ -1303,7 +1474,13 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
         if ((e = launch<BandBody<T>>(c, (K + NT * BandBody<T>::PER - 1) / (NT * BandBody<T>::PER), ng, ba)))
           return e;
       }
-      if (c->fused) {
+      if (c->fused == 2 && persistent) {
+        e = dense ? dispatch_pipe<T, MODE_DENSE>(c, cl.log2K - 10, a, b, ng)
+                  : dispatch_pipe<T, MODE_BAND>(c, cl.log2K - 10, a, b, ng);
+        if (e) return e;
+        continue;
+      }
+      if (c->fused == 1) {
         e = dense ? dispatch_fused<T, MODE_DENSE>(c, cl.log2K - 10, a, b, ng)
                   : dispatch_fused<T, MODE_BAND>(c, cl.log2K - 10, a, b, ng);
         if (e) return e;
@@ -1346,7 +1523,7 @@ static void assign_chunk_offsets(cwtb_ctx *c, Job &job) {
     const size_t region = (size_t)job_chain_region(c, job, cl) * bchunk;
     for (int i = 0; i < cl.count; ++i)
       job.descs[cl.first + i].boff =
-          (long long)(job.b_single + region + (size_t)(c->fused ? i : i % G) * ((size_t)1 << cl.log2K));
+          (long long)(job.b_single + region + (size_t)(class_persistent(c, cl) ? i : i % G) * ((size_t)1 << cl.log2K));
   }
 }
 
@@ -1466,6 +1643,8 @@ int cwtb_create(int device, cwtb_ctx **out) {
   if (const char *g = getenv("CWTB_GAUSS_REC")) c->gauss_rec = atoi(g);
   if (const char *g = getenv("CWTB_BATCH_MB")) c->batch_bytes = (size_t)std::max(1, atoi(g)) << 20;
   if (const char *g = getenv("CWTB_RING")) c->ring = std::max(1, atoi(g));
+  else if (c->fused == 2) c->ring = 4;
+  if (const char *g = getenv("CWTB_AHEAD")) c->pipe_ahead = std::max(1, atoi(g));
 #ifndef CWTB_HOST_EMU
   cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
 #endif

@@ -699,25 +699,30 @@ template <typename T> struct ExpandArgs {
   int log2R;           // R = N / Nc of every row of this launch
 };
 
-// CTA tile: RB = min(R, NT) consecutive phases rho  x  NRUN = NT / RB runs of L consecutive coarse
-// positions m.  A thread keeps its `TAPS` weights (fixed rho) and a sliding window of TAPS coarse
-// samples in registers and walks its run: one new sample (shared-memory read, the same address
-// for the lanes of a run) and one 16-byte store per output; lanes run over rho, so a warp stores
-// min(R, 32) consecutive points per run.
-template <typename T, int TAPS> struct ExpandBody {
+// CTA tile: RB = min(R, NT) consecutive phases rho  x  NRUN = NT / RB runs of L = 32 consecutive
+// coarse positions m.  A thread keeps its `TAPS` weights (fixed rho) and a sliding window of TAPS
+// coarse samples in registers and walks its run (fully unrolled: window slots are compile-time
+// registers): one new sample (shared-memory read, the same address for the lanes of a run) and one
+// 16-byte store per output; lanes run over rho, so a warp stores min(R, 32) consecutive points
+// per run.  Measured on B200 (profiles/r2): the kernel is bound by the fp64 pipe (2 taps + ~12
+// other fp64 instructions per point at 64 lanes per SM and clock); 8 accumulator chains and 4 CTAs
+// per SM keep that pipe 63 % busy, longer runs or fewer chains were slower.
+template <typename T, int TAPS, int EPI = EPI_STORE> struct ExpandBody {
   static constexpr int NTB = TileCfg<T>::NT;
   static constexpr int NT = NTB;
+  static constexpr int MINB = sizeof(T) == 8 ? 4 : 2;   // CTAs per SM the register budget is capped for
   using V = cx<T>;
   using Args = ExpandArgs<T>;
   static constexpr int L = 32;                       // coarse positions per run
-  static constexpr int MAXRUN = NT / 8;              // R >= 8
+  static constexpr int MINR = 8;                     // smallest expansion factor R = Np / Nc
+  static constexpr int MAXRUN = NT / MINR;
   static constexpr int STAGE = MAXRUN * L + TAPS;    // staged coarse samples (incl. halo)
   HD static int skew(int i) { return i + (i >> 5); } // runs start 33 elements apart: no bank conflict
   static constexpr int NPHASE = 2;
   static constexpr size_t SMEM = (size_t)(STAGE + STAGE / 32 + 2) * sizeof(V);
   template <int PH> HD static void phase(const Args &a, int bx, int by, int tid, void *smraw) {
     V *sm = (V *)smraw;
-    const ScaleDesc d = a.descs[a.first + by];
+    const ScaleDesc &d = a.descs[a.first + by];
     const int R = 1 << a.log2R;
     const int Nc = (int)(a.N >> a.log2R);
     const int RB = R < NT ? R : NT;
@@ -733,42 +738,50 @@ template <typename T, int TAPS> struct ExpandBody {
         sm[skew(i)] = ldg(&c[m]);
       }
     } else {
-      const int rl = tid % RB, j = tid / RB;
+      const int rl = tid & (RB - 1), j = tid / RB;
       const int rho = rb * RB + rl;
       const int ms = m0 + j * L;                     // first coarse position of this thread's run
+      // outputs n = R m + rho for m = ms .. ms + L - 1; kept while m < Nc and n < n0
+      const long long nfirst = ((long long)ms << a.log2R) + rho;
+      long long keep = (a.n0 - nfirst + R - 1) >> a.log2R;      // steps with n < n0
+      if (keep > Nc - ms) keep = Nc - ms;
+      const int smax = keep < 0 ? 0 : (keep > L ? L : (int)keep);
+      if (smax == 0) return;
       T hw[TAPS];
       const double *wt = a.wt + d.ip_woff + rho;
 #pragma unroll
       for (int t = 0; t < TAPS; ++t) hw[t] = (T)ldg(&wt[(size_t)t * R]);
+      const V *run = sm + 33 * j;                    // skew(j*L + i) = 33 j + i + (i >> 5), i < L + TAPS
       V win[TAPS];
 #pragma unroll
-      for (int t = 0; t < TAPS - 1; ++t) win[t] = sm[skew(j * L + t)];
-      // re-modulation e^{2 pi i kc n / Np}, n = R m + rho: table value at the start of the run and
-      // every 16 steps, recurrence (step e^{2 pi i kc R / Np}) in between -- in fp64 for both engines
+      for (int t = 0; t < TAPS - 1; ++t) win[t] = run[t + (t >> 5)];
+      // re-modulation e^{2 pi i kc n / Np}: table value at the start of the run and after 16 steps,
+      // recurrence (step e^{2 pi i kc R / Np}) in between -- in fp64 for both engines
       const unsigned kc = (unsigned)d.ip_kc;
-      const double2 stepw = nroot(a.nt, kc * (unsigned)R);
-      double2 tw = make_double2(1.0, 0.0);
-      V *row = a.W + (size_t)d.row * a.n0;
+      const unsigned nlo = (unsigned)nfirst;
+      const double2 stepw = nroot(a.nt, kc << a.log2R);
+      double2 tw = nroot(a.nt, kc * nlo);
+      V *p = a.W + (size_t)d.row * a.n0 + nfirst;
 #pragma unroll
       for (int s = 0; s < L; ++s) {
-        win[(s + TAPS - 1) % TAPS] = sm[skew(j * L + s + TAPS - 1)];
-        const int m = ms + s;
-        const long long n = (long long)m * R + rho;
-        if ((s & 15) == 0) tw = nroot(a.nt, kc * (unsigned)n);
-        T ar0 = 0, ai0 = 0, ar1 = 0, ai1 = 0;
+        win[(s + TAPS - 1) % TAPS] = run[(s + TAPS - 1) + ((s + TAPS - 1) >> 5)];
+        if (s == 16) tw = nroot(a.nt, kc * (nlo + (16u << a.log2R)));
+        // 8 independent chains (4 per component): the fp64 pipe needs that much parallelism per warp
+        T ar[4] = {0, 0, 0, 0}, ai[4] = {0, 0, 0, 0};
 #pragma unroll
-        for (int t = 0; t < TAPS; t += 2) {
-          const V c0 = win[(s + t) % TAPS], c1 = win[(s + t + 1) % TAPS];
-          ar0 += c0.x * hw[t]; ai0 += c0.y * hw[t];
-          ar1 += c1.x * hw[t + 1]; ai1 += c1.y * hw[t + 1];
+        for (int t = 0; t < TAPS; ++t) {
+          const V cv = win[(s + t) % TAPS];
+          ar[t & 3] += cv.x * hw[t];
+          ai[t & 3] += cv.y * hw[t];
         }
-        const V acc = mk<T>(ar0 + ar1, ai0 + ai1);
+        const V acc = mk<T>((ar[0] + ar[1]) + (ar[2] + ar[3]), (ai[0] + ai[1]) + (ai[2] + ai[3]));
         const V x = cmul(acc, mk<T>((T)tw.x, (T)tw.y));
         tw = cmul(tw, stepw);
-        if (m < Nc && n < a.n0) {
-          if (a.epi == EPI_MULCONJ) row[n] = cmul(row[n], cconj(x));
-          else st_stream(&row[n], x);
+        if (s < smax) {
+          if (EPI == EPI_MULCONJ) *p = cmul(*p, cconj(x));
+          else st_stream(p, x);
         }
+        p += R;
       }
     }
   }
