@@ -37,7 +37,8 @@ enum cwtb_status {
   CWTB_ERR_CUDA = -2,      /* CUDA runtime error (see cwtb_last_error)   */
   CWTB_ERR_NOMEM = -3,     /* device / pinned allocation failed          */
   CWTB_ERR_STATE = -4,     /* call sequence error (no transform resident) */
-  CWTB_ERR_UNSUPPORTED = -5
+  CWTB_ERR_UNSUPPORTED = -5,
+  CWTB_ERR_COMM = -6       /* NCCL error / libnccl not loadable           */
 };
 
 /* Mother-wavelet families, pycwt/mothers.py:13-233.  MexicanHat == DOG m=2. */
@@ -211,7 +212,8 @@ int cwtb_cwt_batch_dev(cwtb_ctx *ctx, const void *d_X, int n_chan, int64_t n0, d
 
 /* ---- timing / introspection (bench.py, tests) ----------------------------- */
 /* Device time (ms, CUDA events on the context's stream) of the kernels of the
- * last cwtb_cwt* call, excluding H2D/D2H; and the number of kernel launches. */
+ * last cwtb_cwt* / cwtb_xwt / cwtb_wct / cwtb_wct_mc call, excluding H2D/D2H; and the number
+ * of kernel launches. */
 double cwtb_last_kernel_ms(cwtb_ctx *ctx);
 int cwtb_last_launch_count(cwtb_ctx *ctx);
 /* Fills `out` (capacity n) with one int per scale of the last call:
@@ -239,6 +241,29 @@ int cwtb_sync(cwtb_ctx *ctx);
  * in/out: host complex128 (precision selects the arithmetic). */
 int cwtb_fft_c2c(cwtb_ctx *ctx, const void *in, void *out, int64_t n, int batch,
                  int sign, int precision);
+
+/* ---- multi-GPU (SURVEY.md 8b vii, 8e) ------------------------------------------------------
+ * One context per GPU (one process per GPU, or one host thread per context).  The transform
+ * itself needs no collective: channels (pycwt.cwt per channel, wavelet.py:13-124), scales and
+ * Monte-Carlo surrogate pairs (wavelet.py:609-630) are independent units that the caller
+ * block-partitions over the ranks.  These entry points move the REDUCED products over
+ * NVLink / NVSwitch with NCCL (bound at run time from libnccl.so.2; CWTB_ERR_COMM if absent):
+ * per-channel spectra (all-gather), surrogate histograms (all-reduce), timings (max).
+ * Buffers are host arrays, staged through device memory owned by the context.
+ *   rank 0:  cwtb_comm_unique_id(id);  the host program hands the 128 bytes to every rank
+ *   all:     cwtb_comm_init(ctx, world, rank, id);  ...collectives...;  cwtb_comm_destroy(ctx)
+ * world == 1 needs no NCCL: the collectives are copies / no-ops. */
+int cwtb_comm_unique_id(void *id128);
+int cwtb_comm_init(cwtb_ctx *ctx, int world, int rank, const void *id128);
+int cwtb_comm_destroy(cwtb_ctx *ctx);
+int cwtb_comm_world(cwtb_ctx *ctx);
+int cwtb_comm_rank(cwtb_ctx *ctx);
+/* recv[r*bytes .. (r+1)*bytes) = rank r's `send` (bytes per rank, equal on all ranks) */
+int cwtb_comm_allgather(cwtb_ctx *ctx, const void *send, void *recv, size_t bytes);
+/* in place, every rank gets the result */
+int cwtb_comm_allreduce_sum_i64(cwtb_ctx *ctx, int64_t *buf, size_t count);
+int cwtb_comm_allreduce_max_f64(cwtb_ctx *ctx, double *buf, size_t count);
+int cwtb_comm_broadcast(cwtb_ctx *ctx, void *buf, size_t bytes, int root);
 
 #ifdef __cplusplus
 }

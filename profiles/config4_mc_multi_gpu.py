@@ -24,13 +24,13 @@ eng = _engine.Engine(local)
 dev = torch.device("cuda", local)
 args = (0.3, 0.25, 1.0, 1 / 12, 2.0, 144)
 d = dist if world > 1 else None
-D.wct_significance_sharded(*args, mc_count=2 * world, seed=1, engine=eng, dist=d, device=dev)   # warm-up
+D.wct_significance_sharded(*args, mc_count=2 * world, seed=1, engine=eng, comm=D.TorchComm(d, dev))   # warm-up
 if world > 1:
     dist.barrier(device_ids=[local])
 torch.cuda.synchronize()
 t0 = time.perf_counter()
 sig = D.wct_significance_sharded(*args, significance_level=0.95, wavelet='morlet', mc_count=mc, seed=7,
-                                 engine=eng, dist=d, device=dev)
+                                 engine=eng, comm=D.TorchComm(d, dev))
 torch.cuda.synchronize()
 dt = D.max_over_ranks(time.perf_counter() - t0, d, dev)
 if rank == 0:

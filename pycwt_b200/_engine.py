@@ -66,6 +66,15 @@ _SIGNATURES = {
     "cwtb_wct_mc": (_I, [_P, _P, _I, _I64, _D, _D, _P, _I, _I, _D, _I, _P, _I, _I, _P]),
     "cwtb_cwt_batch": (_I, [_P, _P, _I, _I, _I64, _D, _P, _I, _I, _D, _I, _P, _P]),
     "cwtb_cwt_batch_dev": (_I, [_P, _P, _I, _I64, _D, _P, _I, _I, _D, _I, _P]),
+    "cwtb_comm_unique_id": (_I, [_P]),
+    "cwtb_comm_init": (_I, [_P, _I, _I, _P]),
+    "cwtb_comm_destroy": (_I, [_P]),
+    "cwtb_comm_world": (_I, [_P]),
+    "cwtb_comm_rank": (_I, [_P]),
+    "cwtb_comm_allgather": (_I, [_P, _P, _P, ctypes.c_size_t]),
+    "cwtb_comm_allreduce_sum_i64": (_I, [_P, _P, ctypes.c_size_t]),
+    "cwtb_comm_allreduce_max_f64": (_I, [_P, _P, ctypes.c_size_t]),
+    "cwtb_comm_broadcast": (_I, [_P, _P, ctypes.c_size_t, _I]),
 }
 
 
@@ -580,6 +589,56 @@ class Engine(object):
     @_locked
     def sync(self):
         self._check(self.lib.cwtb_sync(self.h))
+
+    # ---- multi-GPU collectives (NCCL behind the C ABI; no torch) --------------------
+    def comm_unique_id(self):
+        """128-byte NCCL id (rank 0 creates it, the host program distributes it)."""
+        buf = ctypes.create_string_buffer(128)
+        rc = self.lib.cwtb_comm_unique_id(buf)
+        if rc != 0:
+            raise EngineError("cwtb_comm_unique_id failed with status %d (libnccl not loadable?)" % rc)
+        return buf.raw
+
+    @_locked
+    def comm_init(self, world, rank, uid):
+        buf = ctypes.create_string_buffer(bytes(uid), 128)
+        self._check(self.lib.cwtb_comm_init(self.h, int(world), int(rank), buf))
+
+    @_locked
+    def comm_destroy(self):
+        self.lib.cwtb_comm_destroy(self.h)
+
+    def comm_world(self):
+        return int(self.lib.cwtb_comm_world(self.h))
+
+    def comm_rank(self):
+        return int(self.lib.cwtb_comm_rank(self.h))
+
+    @_locked
+    def comm_allgather(self, local):
+        """Every rank contributes an equal-shape array; returns the [world, ...] stack."""
+        local = np.ascontiguousarray(local)
+        out = np.empty((self.comm_world(),) + local.shape, dtype=local.dtype)
+        self._check(self.lib.cwtb_comm_allgather(self.h, _ptr(local), _ptr(out), local.nbytes))
+        return out
+
+    @_locked
+    def comm_allreduce_sum(self, array):
+        a = np.ascontiguousarray(array, dtype=np.int64).copy()
+        self._check(self.lib.cwtb_comm_allreduce_sum_i64(self.h, _ptr(a), a.size))
+        return a
+
+    @_locked
+    def comm_allreduce_max(self, array):
+        a = np.atleast_1d(np.ascontiguousarray(array, dtype=np.float64)).copy()
+        self._check(self.lib.cwtb_comm_allreduce_max_f64(self.h, _ptr(a), a.size))
+        return a
+
+    @_locked
+    def comm_broadcast(self, array, root=0):
+        a = np.ascontiguousarray(array).copy()
+        self._check(self.lib.cwtb_comm_broadcast(self.h, _ptr(a), a.nbytes, int(root)))
+        return a
 
 
 _default = {}

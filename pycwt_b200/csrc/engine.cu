@@ -19,6 +19,9 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#ifndef CWTB_HOST_EMU
+#include <dlfcn.h>
+#endif
 
 #include "../../include/cwt_b200.h"
 #include "kernels.cuh"
@@ -159,6 +162,9 @@ struct cwtb_ctx {
   double expand_eps32 = 2e-7;    // fp32 engine
   int expand_min_log2R = 3;      // expansion needs Np / Nc >= 8 (CWTB_EXPAND_MIN_R: log2)
   Buf *ztmp = nullptr;           // intermediate of two_kernel_rows (set per stream; default Z)
+  void *comm = nullptr;          // ncclComm_t of cwtb_comm_init (one rank per context)
+  int comm_world = 1, comm_rank = 0;
+  Buf comm_send, comm_recv;      // device staging of the host-buffer collectives
   int group = 0;   // rows per two-kernel chunk; 0 = as many as fit in group_bytes of Z (CWTB_GROUP)
   size_t group_bytes = (size_t)512 << 20;
   int l2_persist = 0;
@@ -190,6 +196,9 @@ struct cwtb_ctx {
   std::set<const void *> configured;
   // per-launch event profiling (cwtb_profile_last)
   bool profiling = false;
+  const char *prof_tag = "";     // prefix of the kernel names recorded while profiling: "fwd:" (forward
+                                 // transform of the signal), "coarse:" (coarse-grid transforms of the
+                                 // expansion path); W-writing launches carry no tag
   struct ProfRec { std::string name; unsigned gx, gy; int ev; };
   std::vector<ProfRec> prof;
 #ifndef CWTB_HOST_EMU
@@ -304,7 +313,7 @@ static int launch(cwtb_ctx *c, unsigned gx, unsigned gy, const typename Body::Ar
       RT(cudaEventCreate(&e));
       c->prof_events.push_back(e);
     }
-    c->prof.push_back({body_name(__PRETTY_FUNCTION__), gx, gy, ev});
+    c->prof.push_back({std::string(c->prof_tag) + body_name(__PRETTY_FUNCTION__), gx, gy, ev});
     RT(cudaEventRecord(c->prof_events[ev], c->cur));
   }
   k_run<Body><<<dim3(gx, gy), BodyNT<Body>::value, Body::SMEM, c->cur>>>(a);
@@ -613,7 +622,7 @@ static int build_job(cwtb_ctx *c, Job &job, long long n0, double dt, const doubl
   // (descending coarse length, then taps / weight table)
   auto sort_key = [&](const ScaleDesc &d) -> long long {
     if (!d.ip_log2Nc) return (1ll << 40) + d.log2K;
-    return ((long long)d.ip_log2Nc << 32) - ((long long)d.ip_w << 24) - (d.ip_woff & 0xffffff);
+    return ((long long)(64 - d.ip_w) << 32) + ((long long)d.ip_log2Nc << 24) - (d.ip_woff & 0xffffff);
   };
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return sort_key(ds[a]) > sort_key(ds[b]); });
   job.descs.resize(R);
@@ -1249,11 +1258,10 @@ static size_t band_chunk_elems(const cwtb_ctx *c, const Job &job, int G) {
 template <typename T, int TAPS>
 static int launch_expand_t(cwtb_ctx *c, const ExpandArgs<T> &a, int rows) {
   using B = ExpandBody<T, TAPS>;
-  const int R = 1 << a.log2R;
-  const int Nc = (int)(a.N >> a.log2R);
-  const int RB = std::min(R, B::NT), MT = (B::NT / RB) * B::L;
-  const unsigned gx = (unsigned)((R / RB) * ((Nc + MT - 1) / MT));
-  if (R < B::MINR) return fail(c, CWTB_ERR_STATE, "expansion factor below the kernel's minimum");
+  // tiles per row: (R / RB) * ceil(Nc / MT) with RB = min(R, NT), MT = (NT / RB) * L -- equal to
+  // N / (NT * L) for every coarse length with Nc >= MT; rows with a shorter coarse grid use the
+  // first tiles of the launch only
+  const unsigned gx = std::max<unsigned>(1, a.N / (unsigned)(B::NT * B::L));
   if (a.epi == EPI_MULCONJ) return launch<ExpandBody<T, TAPS, EPI_MULCONJ>>(c, gx, rows, a);
   return launch<B>(c, gx, rows, a);
 }
@@ -1289,7 +1297,7 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
   int e;
   // whatever path leaves this function (also an error in the middle of the fork), the launcher
   // is back on the engine's stream afterwards
-  struct CurGuard { cwtb_ctx *c; ~CurGuard() { c->cur = c->stream; } } cur_guard{c};
+  struct CurGuard { cwtb_ctx *c; ~CurGuard() { c->cur = c->stream; c->prof_tag = ""; c->ztmp = nullptr; } } cur_guard{c};
   if ((e = ensure(c, c->spec, (size_t)job.nbatch * N * sizeof(V)))) return e;
   if (!Wout) {
     if ((e = ensure(c, c->W, (size_t)S * job.n0 * sizeof(V)))) return e;
@@ -1309,7 +1317,10 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
     TinyArgs<T> ta{ddesc, spec, W, fam, job.n0, N, 0, epi};
     return launch<TinyBody<T>>(c, (unsigned)((job.n0 + NT - 1) / NT), S, ta);
   }
-  if ((e = fft_rows<T, -1>(c, dsig, 1, job.n0, job.n0, spec, N, N, job.nbatch))) return e;
+  c->prof_tag = "fwd:";
+  e = fft_rows<T, -1>(c, dsig, 1, job.n0, job.n0, spec, N, N, job.nbatch);
+  c->prof_tag = "";
+  if (e) return e;
 
   NTab nt;
   if ((e = get_ntab(c, N, job.log2N, &nt))) return e;
@@ -1369,10 +1380,11 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
     constexpr int XPER = ExpandBandBody<T>::PER;
     if ((e = launch<ExpandBandBody<T>>(c, ((1u << maxl) + NT * XPER - 1) / (NT * XPER), nrows, xa))) return e;
     c->ztmp = &c->Zx;
+    c->prof_tag = "coarse:";
     for (size_t ci = 0; ci < job.classes.size() && !e; ++ci) {
       const ClassRun &cl = job.classes[ci];
       if (!cl.expand) continue;
-      // coarse transforms: all classes of this coarse length at once (rows are contiguous)
+      // coarse transforms: consecutive classes of one coarse length at once (rows are contiguous)
       if (ci == 0 || !job.classes[ci - 1].expand || job.classes[ci - 1].log2Nc != cl.log2Nc) {
         int rows = 0;
         for (size_t cj = ci; cj < job.classes.size() && job.classes[cj].expand && job.classes[cj].log2Nc == cl.log2Nc; ++cj)
@@ -1380,11 +1392,19 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
         const long long off = job.descs[cl.first].ip_coff;
         const unsigned Nc = 1u << cl.log2Nc;
         e = fft_rows<T, +1>(c, (const V *)c->Cin.p + off, 0, Nc, Nc, (V *)c->Cout.p + off, Nc, Nc, rows);
-        if (e) break;
       }
+    }
+    c->prof_tag = "";
+    // one expansion launch per tap count: classes are sorted by taps first
+    for (size_t ci = 0; ci < job.classes.size() && !e; ++ci) {
+      const ClassRun &cl = job.classes[ci];
+      if (!cl.expand || (ci > 0 && job.classes[ci - 1].expand && job.classes[ci - 1].taps == cl.taps)) continue;
+      int rows = 0;
+      for (size_t cj = ci; cj < job.classes.size() && job.classes[cj].expand && job.classes[cj].taps == cl.taps; ++cj)
+        rows += job.classes[cj].count;
       ExpandArgs<T> ea{ddesc, (const V *)c->Cout.p, (const double *)c->wtab.p, W, nt, job.n0, N, cl.first, epi,
-                       job.log2N - cl.log2Nc};
-      e = launch_expand<T>(c, cl.taps, ea, cl.count);
+                       job.log2N};
+      e = launch_expand<T>(c, cl.taps, ea, rows);
     }
     c->ztmp = nullptr;
     c->cur = c->stream;
@@ -1630,7 +1650,7 @@ int cwtb_create(int device, cwtb_ctx **out) {
   if (const char *g = getenv("CWTB_BAND_EPS")) c->band_eps = atof(g);
   if (const char *g = getenv("CWTB_EXPAND_EPS")) c->expand_eps = std::max(0.0, atof(g));
   if (const char *g = getenv("CWTB_EXPAND_EPS32")) c->expand_eps32 = std::max(0.0, atof(g));
-  if (const char *g = getenv("CWTB_EXPAND_MIN_R")) c->expand_min_log2R = std::min(14, std::max(3, atoi(g)));
+  if (const char *g = getenv("CWTB_EXPAND_MIN_R")) c->expand_min_log2R = std::min(14, std::max(2, atoi(g)));
   if (const char *g = getenv("CWTB_L2_PERSIST")) c->l2_persist = atoi(g);
   if (const char *g = getenv("CWTB_FUSED")) c->fused = atoi(g);
   if (const char *g = getenv("CWTB_PF_DIST")) c->pf_dist = std::max(0, atoi(g));
@@ -1662,7 +1682,8 @@ void cwtb_destroy(cwtb_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
 #endif
-  for (Buf *b : {&c->Zx, &c->Cin, &c->Cout, &c->wtab, &c->ctr, &c->sig, &c->sig2, &c->spec, &c->Z, &c->Zc[0], &c->Zc[1], &c->Zc[2], &c->Y, &c->B, &c->W, &c->W2, &c->descs, &c->table, &c->scratch,
+  cwtb_comm_destroy(c);
+  for (Buf *b : {&c->comm_send, &c->comm_recv, &c->Zx, &c->Cin, &c->Cout, &c->wtab, &c->ctr, &c->sig, &c->sig2, &c->spec, &c->Z, &c->Zc[0], &c->Zc[1], &c->Zc[2], &c->Y, &c->B, &c->W, &c->W2, &c->descs, &c->table, &c->scratch,
                  &c->C, &c->A12, &c->F, &c->aux, &c->rowd, &c->win, &c->mask, &c->hist, &c->noise, &c->wide, &c->blueA, &c->blueX, &c->blueY})
     if (b->p) rt_free(b->p);
   for (auto &kv : c->ntabs) { rt_free(kv.second.hi); rt_free(kv.second.lo); }
@@ -1959,6 +1980,25 @@ int cwtb_fft_c2c(cwtb_ctx *c, const void *in, void *out, int64_t n, int batch, i
 
 extern "C" {
 
+// device time of a kernel sequence on the engine's stream -> cwtb_last_kernel_ms
+static int time_begin(cwtb_ctx *c) {
+#ifndef CWTB_HOST_EMU
+  RT(cudaEventRecord(c->e0, c->stream));
+#endif
+  c->last_ms = 0;
+  return 0;
+}
+static int time_end(cwtb_ctx *c) {
+#ifndef CWTB_HOST_EMU
+  float ms = 0;
+  RT(cudaEventRecord(c->e1, c->stream));
+  RT(cudaEventSynchronize(c->e1));
+  RT(cudaEventElapsedTime(&ms, c->e0, c->e1));
+  c->last_ms = ms;
+#endif
+  return 0;
+}
+
 // ---- helpers for the post-processing entry points ---------------------------------------
 static int upload_doubles(cwtb_ctx *c, Buf &b, const std::vector<double> &v) {
   int e = ensure(c, b, v.size() * sizeof(double));
@@ -2242,8 +2282,10 @@ int cwtb_xwt(cwtb_ctx *c, const double *y1, const double *y2, int64_t n0, double
   if ((e = upload_signal_f64(c, c->sig, y1, n0))) return e;
   if ((e = upload_signal_f64(c, c->sig2, y2, n0))) return e;
   c->launches = 0;
+  if ((e = time_begin(c))) return e;
   if ((e = run_job<double>(c, c->job, (const double *)c->sig.p, nullptr, EPI_STORE))) return e;
   if ((e = run_job<double>(c, c->job, (const double *)c->sig2.p, nullptr, EPI_MULCONJ))) return e;
+  if ((e = time_end(c))) return e;
   c->job_dsig = nullptr;
   if (W12_out) return cwtb_get_w(c, W12_out, 1, 0, n_scales);
   RT(rt_sync(c->stream));
@@ -2266,9 +2308,11 @@ int cwtb_wct(cwtb_ctx *c, const double *y1, const double *y2, int64_t n0, double
   if ((e = ensure(c, c->aux, 2 * cnt * sizeof(double)))) return e;
   double *dW = (double *)c->aux.p, *dA = dW + cnt;
   c->launches = 0;
+  if ((e = time_begin(c))) return e;
   if ((e = wct_core(c, c->job, (const double *)c->sig.p, (const double *)c->sig2.p, boxcar_len, dW,
                     aWCT_out ? dA : nullptr, nullptr, 0, 0, nullptr)))
     return e;
+  if ((e = time_end(c))) return e;
   c->job_dsig = nullptr;
   if (WCT_out) RT(rt_d2h(WCT_out, dW, cnt * sizeof(double), c->stream));
   if (aWCT_out) RT(rt_d2h(aWCT_out, dA, cnt * sizeof(double), c->stream));
@@ -2346,12 +2390,14 @@ int cwtb_wct_mc(cwtb_ctx *c, const double *noise, int n_pairs, int64_t n0, doubl
   RT(rt_h2d(c->noise.p, noise, (size_t)n_pairs * 2 * n0 * sizeof(double), c->stream));
   RT(rt_sync(c->stream));
   c->launches = 0;
+  if ((e = time_begin(c))) return e;
   for (int i = 0; i < n_pairs; ++i) {
     const double *a = (const double *)c->noise.p + (size_t)i * 2 * n0;
     if ((e = wct_core(c, c->job, a, a + n0, boxcar_len, nullptr, nullptr, (const unsigned char *)c->mask.p,
                       maxscale, nbins, (unsigned long long *)c->hist.p)))
       return e;
   }
+  if ((e = time_end(c))) return e;
   c->job_dsig = nullptr;
   std::vector<unsigned long long> h((size_t)n_scales * nbins);
   RT(rt_d2h(h.data(), c->hist.p, hb, c->stream));
@@ -2455,6 +2501,175 @@ int cwtb_cwt_batch_dev(cwtb_ctx *c, const void *d_X, int n_chan, int64_t n0, dou
   if ((e = timed_run(c, d_X, 1, &c->last_ms))) return e;
   if (power_out) return cwtb_global_power(c, power_out);
   return 0;
+}
+
+
+// ======================================================================================
+// Multi-GPU collectives (SURVEY 8b vii / 8e): one context per GPU and process, an NCCL
+// communicator owned by the context.  NCCL is bound at run time (dlopen of libnccl.so.2), so the
+// library has no link-time dependency and single-GPU users never touch it.  The data path of the
+// transform needs no collective (channels / scales / surrogate pairs are independent); what
+// crosses NVLink are the REDUCED products: per-row spectra (all-gather), Monte-Carlo histograms
+// (all-reduce), timings (max).  Buffers are host arrays staged through context-owned device
+// memory: sizes are O(channels x scales), a few MB.
+// ======================================================================================
+#ifndef CWTB_HOST_EMU
+namespace {
+typedef struct { char internal[128]; } nccl_uid;
+struct NcclApi {
+  void *h = nullptr;
+  int (*GetUniqueId)(nccl_uid *) = nullptr;
+  int (*CommInitRank)(void **, int, nccl_uid, int) = nullptr;
+  int (*CommDestroy)(void *) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*Broadcast)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+NcclApi &nccl_api() {
+  static NcclApi a;
+  if (a.h) return a;
+  for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+    a.h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+    if (a.h) break;
+  }
+  if (!a.h) return a;
+  a.GetUniqueId = (int (*)(nccl_uid *))dlsym(a.h, "ncclGetUniqueId");
+  a.CommInitRank = (int (*)(void **, int, nccl_uid, int))dlsym(a.h, "ncclCommInitRank");
+  a.CommDestroy = (int (*)(void *))dlsym(a.h, "ncclCommDestroy");
+  a.AllGather = (int (*)(const void *, void *, size_t, int, void *, cudaStream_t))dlsym(a.h, "ncclAllGather");
+  a.AllReduce = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))dlsym(a.h, "ncclAllReduce");
+  a.Broadcast = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))dlsym(a.h, "ncclBroadcast");
+  a.GetErrorString = (const char *(*)(int))dlsym(a.h, "ncclGetErrorString");
+  a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllGather && a.AllReduce && a.Broadcast;
+  return a;
+}
+enum { NCCL_CHAR = 0, NCCL_INT64 = 4, NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_MAX = 2 };
+}  // namespace
+#define NCCLCHK(call)                                                                               \
+  do {                                                                                              \
+    int r_ = (call);                                                                                \
+    if (r_ != 0)                                                                                    \
+      return fail(c, CWTB_ERR_COMM, std::string(#call) + ": " +                                     \
+                                        (nccl_api().GetErrorString ? nccl_api().GetErrorString(r_) : "NCCL error")); \
+  } while (0)
+#endif
+
+int cwtb_comm_unique_id(void *id128) {
+  if (!id128) return CWTB_ERR_ARG;
+#ifdef CWTB_HOST_EMU
+  memset(id128, 0, 128);
+  return 0;
+#else
+  NcclApi &a = nccl_api();
+  if (!a.ok) return CWTB_ERR_COMM;
+  return a.GetUniqueId((nccl_uid *)id128) == 0 ? 0 : CWTB_ERR_COMM;
+#endif
+}
+
+int cwtb_comm_init(cwtb_ctx *c, int world, int rank, const void *id128) {
+  if (!c || !id128 || world < 1 || rank < 0 || rank >= world) return fail(c, CWTB_ERR_ARG, "comm_init: bad argument");
+  cwtb_comm_destroy(c);
+  c->comm_world = world;
+  c->comm_rank = rank;
+#ifndef CWTB_HOST_EMU
+  if (world == 1) return 0;
+  NcclApi &a = nccl_api();
+  if (!a.ok) return fail(c, CWTB_ERR_COMM, "libnccl.so.2 could not be loaded");
+  RT(cudaSetDevice(c->device));
+  nccl_uid id;
+  memcpy(&id, id128, sizeof id);
+  NCCLCHK(a.CommInitRank(&c->comm, world, id, rank));
+#else
+  if (world != 1) return fail(c, CWTB_ERR_UNSUPPORTED, "the emulation build has no communicator");
+#endif
+  return 0;
+}
+
+int cwtb_comm_destroy(cwtb_ctx *c) {
+  if (!c) return CWTB_ERR_ARG;
+#ifndef CWTB_HOST_EMU
+  if (c->comm) {
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    nccl_api().CommDestroy(c->comm);
+    c->comm = nullptr;
+  }
+#endif
+  c->comm_world = 1;
+  c->comm_rank = 0;
+  return 0;
+}
+
+int cwtb_comm_world(cwtb_ctx *c) { return c ? c->comm_world : -1; }
+int cwtb_comm_rank(cwtb_ctx *c) { return c ? c->comm_rank : -1; }
+
+// recv[r * bytes .. (r+1) * bytes) = rank r's send, for every rank (host buffers)
+int cwtb_comm_allgather(cwtb_ctx *c, const void *send, void *recv, size_t bytes) {
+  if (!c || !send || !recv) return fail(c, CWTB_ERR_ARG, "allgather: null argument");
+  if (c->comm_world == 1) { memmove(recv, send, bytes); return 0; }
+#ifndef CWTB_HOST_EMU
+  int e;
+  RT(cudaSetDevice(c->device));
+  if ((e = ensure(c, c->comm_send, bytes))) return e;
+  if ((e = ensure(c, c->comm_recv, bytes * c->comm_world))) return e;
+  RT(rt_h2d(c->comm_send.p, send, bytes, c->stream));
+  NCCLCHK(nccl_api().AllGather(c->comm_send.p, c->comm_recv.p, bytes, NCCL_CHAR, c->comm, c->stream));
+  RT(rt_d2h(recv, c->comm_recv.p, bytes * c->comm_world, c->stream));
+  RT(rt_sync(c->stream));
+  return 0;
+#else
+  return fail(c, CWTB_ERR_UNSUPPORTED, "no communicator");
+#endif
+}
+
+static int comm_allreduce(cwtb_ctx *c, void *buf, size_t count, int dtype, int op) {
+  if (!c || !buf) return fail(c, CWTB_ERR_ARG, "allreduce: null argument");
+  if (c->comm_world == 1) return 0;
+#ifndef CWTB_HOST_EMU
+  int e;
+  RT(cudaSetDevice(c->device));
+  if ((e = ensure(c, c->comm_send, count * 8))) return e;
+  RT(rt_h2d(c->comm_send.p, buf, count * 8, c->stream));
+  NCCLCHK(nccl_api().AllReduce(c->comm_send.p, c->comm_send.p, count, dtype, op, c->comm, c->stream));
+  RT(rt_d2h(buf, c->comm_send.p, count * 8, c->stream));
+  RT(rt_sync(c->stream));
+  return 0;
+#else
+  (void)count; (void)dtype; (void)op;
+  return fail(c, CWTB_ERR_UNSUPPORTED, "no communicator");
+#endif
+}
+int cwtb_comm_allreduce_sum_i64(cwtb_ctx *c, int64_t *buf, size_t count) {
+#ifndef CWTB_HOST_EMU
+  return comm_allreduce(c, buf, count, NCCL_INT64, NCCL_SUM);
+#else
+  return comm_allreduce(c, buf, count, 0, 0);
+#endif
+}
+int cwtb_comm_allreduce_max_f64(cwtb_ctx *c, double *buf, size_t count) {
+#ifndef CWTB_HOST_EMU
+  return comm_allreduce(c, buf, count, NCCL_FLOAT64, NCCL_MAX);
+#else
+  return comm_allreduce(c, buf, count, 0, 0);
+#endif
+}
+int cwtb_comm_broadcast(cwtb_ctx *c, void *buf, size_t bytes, int root) {
+  if (!c || !buf || root < 0 || root >= c->comm_world) return fail(c, CWTB_ERR_ARG, "broadcast: bad argument");
+  if (c->comm_world == 1) return 0;
+#ifndef CWTB_HOST_EMU
+  int e;
+  RT(cudaSetDevice(c->device));
+  if ((e = ensure(c, c->comm_send, bytes))) return e;
+  if (c->comm_rank == root) RT(rt_h2d(c->comm_send.p, buf, bytes, c->stream));
+  NCCLCHK(nccl_api().Broadcast(c->comm_send.p, c->comm_send.p, bytes, NCCL_CHAR, root, c->comm, c->stream));
+  RT(rt_d2h(buf, c->comm_send.p, bytes, c->stream));
+  RT(rt_sync(c->stream));
+  return 0;
+#else
+  return fail(c, CWTB_ERR_UNSUPPORTED, "no communicator");
+#endif
 }
 
 }  // extern "C"

@@ -696,7 +696,8 @@ template <typename T> struct ExpandArgs {
   unsigned N;
   int first;
   int epi;             // EPI_STORE / EPI_MULCONJ
-  int log2R;           // R = N / Nc of every row of this launch
+  int log2N;           // R = N / Nc = 1 << (log2N - ip_log2Nc) per row: one launch serves every
+                       // coarse length (each row has N / (NT * 32) tiles whatever its R)
 };
 
 // CTA tile: RB = min(R, NT) consecutive phases rho  x  NRUN = NT / RB runs of L = 32 consecutive
@@ -714,7 +715,7 @@ template <typename T, int TAPS, int EPI = EPI_STORE> struct ExpandBody {
   using V = cx<T>;
   using Args = ExpandArgs<T>;
   static constexpr int L = 32;                       // coarse positions per run
-  static constexpr int MINR = 8;                     // smallest expansion factor R = Np / Nc
+  static constexpr int MINR = 4;                     // smallest expansion factor R = Np / Nc
   static constexpr int MAXRUN = NT / MINR;
   static constexpr int STAGE = MAXRUN * L + TAPS;    // staged coarse samples (incl. halo)
   HD static int skew(int i) { return i + (i >> 5); } // runs start 33 elements apart: no bank conflict
@@ -723,13 +724,15 @@ template <typename T, int TAPS, int EPI = EPI_STORE> struct ExpandBody {
   template <int PH> HD static void phase(const Args &a, int bx, int by, int tid, void *smraw) {
     V *sm = (V *)smraw;
     const ScaleDesc &d = a.descs[a.first + by];
-    const int R = 1 << a.log2R;
-    const int Nc = (int)(a.N >> a.log2R);
+    const int log2R = a.log2N - d.ip_log2Nc;
+    const int R = 1 << log2R;
+    const int Nc = 1 << d.ip_log2Nc;
     const int RB = R < NT ? R : NT;
     const int NRUN = NT / RB;
     const int MT = NRUN * L;                         // coarse positions per CTA
     const int mtiles = (Nc + MT - 1) / MT;
     const int mt = bx % mtiles, rb = bx / mtiles;
+    if (rb * RB >= R) return;                        // short coarse grid: fewer tiles than the launch has
     const int m0 = mt * MT;
     if constexpr (PH == 0) {
       const V *c = a.C + d.ip_coff;
@@ -742,8 +745,8 @@ template <typename T, int TAPS, int EPI = EPI_STORE> struct ExpandBody {
       const int rho = rb * RB + rl;
       const int ms = m0 + j * L;                     // first coarse position of this thread's run
       // outputs n = R m + rho for m = ms .. ms + L - 1; kept while m < Nc and n < n0
-      const long long nfirst = ((long long)ms << a.log2R) + rho;
-      long long keep = (a.n0 - nfirst + R - 1) >> a.log2R;      // steps with n < n0
+      const long long nfirst = ((long long)ms << log2R) + rho;
+      long long keep = (a.n0 - nfirst + R - 1) >> log2R;      // steps with n < n0
       if (keep > Nc - ms) keep = Nc - ms;
       const int smax = keep < 0 ? 0 : (keep > L ? L : (int)keep);
       if (smax == 0) return;
@@ -759,13 +762,13 @@ template <typename T, int TAPS, int EPI = EPI_STORE> struct ExpandBody {
       // recurrence (step e^{2 pi i kc R / Np}) in between -- in fp64 for both engines
       const unsigned kc = (unsigned)d.ip_kc;
       const unsigned nlo = (unsigned)nfirst;
-      const double2 stepw = nroot(a.nt, kc << a.log2R);
+      const double2 stepw = nroot(a.nt, kc << log2R);
       double2 tw = nroot(a.nt, kc * nlo);
       V *p = a.W + (size_t)d.row * a.n0 + nfirst;
 #pragma unroll
       for (int s = 0; s < L; ++s) {
         win[(s + TAPS - 1) % TAPS] = run[(s + TAPS - 1) + ((s + TAPS - 1) >> 5)];
-        if (s == 16) tw = nroot(a.nt, kc * (nlo + (16u << a.log2R)));
+        if (s == 16) tw = nroot(a.nt, kc * (nlo + (16u << log2R)));
         // 8 independent chains (4 per component): the fp64 pipe needs that much parallelism per warp
         T ar[4] = {0, 0, 0, 0}, ai[4] = {0, 0, 0, 0};
 #pragma unroll

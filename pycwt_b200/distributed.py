@@ -1,8 +1,23 @@
-"""Multi-GPU plumbing for the batched transform: one process per GPU, channels
-block-partitioned across ranks, no collective on the data path.  torch.distributed (NCCL on
-GPUs, gloo in CPU tests) is used only to gather the *reduced* per-channel products (global
-wavelet spectra [channels, scales]) and to agree on timings; coefficients stay sharded in
-each GPU's HBM."""
+"""Multi-GPU plumbing: one process per GPU, independent units block-partitioned over
+the ranks -- channels of a batched transform, scales of one long signal, surrogate pairs of the
+Monte-Carlo coherence significance -- with NO collective on the data path.  What crosses the
+interconnect are the reduced products: per-channel spectra [channels, scales] (all-gather),
+surrogate histograms [scales, 1000] (one all-reduce), timings (max).
+
+Two communicators with the same three methods (`allgather_rows`, `allreduce_sum`, `max`):
+
+  * `NcclComm(engine)`  -- the product path: NCCL behind the engine's C ABI
+    (include/cwt_b200.h `cwtb_comm_*`, libnccl bound at run time); no PyTorch.  The 128-byte
+    NCCL id travels from rank 0 to the others through a caller-supplied exchange or, by default,
+    a rendezvous file next to MASTER_PORT (ranks of one box).
+  * `TorchComm(dist)`   -- torch.distributed (gloo in the CPU tests of the host logic, where no
+    NCCL exists; any initialised process group works).
+
+Every function below takes `comm=None` for the single-process case.
+"""
+import os
+import time
+
 import numpy as np
 
 
@@ -13,62 +28,168 @@ def shard_range(n_items, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def gather_rows(local, n_total, dist=None, device=None):
-    """All ranks contribute their block of rows (as produced by shard_range); every rank
-    gets the full [n_total, ...] array back.  `dist` is torch.distributed (initialised)."""
-    local = np.ascontiguousarray(local)
-    if dist is None or dist.get_world_size() == 1:
-        return local
-    import torch
-    world = dist.get_world_size()
-    trail = local.shape[1:]
-    sizes = [shard_range(n_total, r, world) for r in range(world)]
-    maxrows = max(hi - lo for lo, hi in sizes)
-    buf = np.zeros((maxrows,) + trail, dtype=local.dtype)
-    buf[:local.shape[0]] = local
-    t = torch.from_numpy(buf)
-    if device is not None:
-        t = t.to(device)
-    outs = [torch.empty_like(t) for _ in range(world)]
-    dist.all_gather(outs, t)
-    parts = [o.cpu().numpy()[:hi - lo] for o, (lo, hi) in zip(outs, sizes)]
-    return np.concatenate(parts, axis=0)
+# ---- communicators -----------------------------------------------------------------------
+class _CommBase(object):
+    rank = 0
+    world = 1
+
+    def allgather_rows(self, local, n_total):
+        """All ranks contribute their block of rows (as produced by shard_range); every rank gets
+        the full [n_total, ...] array back."""
+        local = np.ascontiguousarray(local)
+        if self.world == 1:
+            return local
+        sizes = [shard_range(n_total, r, self.world) for r in range(self.world)]
+        maxrows = max(hi - lo for lo, hi in sizes)
+        buf = np.zeros((maxrows,) + local.shape[1:], dtype=local.dtype)
+        buf[:local.shape[0]] = local
+        stack = self._allgather_equal(buf)
+        return np.concatenate([stack[r][:hi - lo] for r, (lo, hi) in enumerate(sizes)], axis=0)
 
 
-def max_over_ranks(value, dist=None, device=None):
+class NcclComm(_CommBase):
+    """NCCL through the engine's C ABI.  `exchange(uid_or_None) -> uid` hands rank 0's id to
+    every rank (rank 0 passes the id in, the others pass None); default: a rendezvous file."""
+
+    def __init__(self, engine, rank=None, world=None, exchange=None):
+        self.engine = engine
+        self.rank = int(os.environ.get("RANK", "0")) if rank is None else int(rank)
+        self.world = int(os.environ.get("WORLD_SIZE", "1")) if world is None else int(world)
+        if self.world > 1:
+            uid = engine.comm_unique_id() if self.rank == 0 else None
+            uid = (exchange or self._file_exchange)(uid)
+            engine.comm_init(self.world, self.rank, uid)
+
+    def _file_exchange(self, uid):
+        tag = "%s_%s" % (os.environ.get("MASTER_PORT", "0"), os.environ.get("TORCHELASTIC_RUN_ID", "run"))
+        path = os.path.join(os.environ.get("CWTB_COMM_DIR", "/tmp"), "cwtb_comm_%s.id" % tag)
+        if self.rank == 0:
+            tmp = path + ".tmp%d" % os.getpid()
+            with open(tmp, "wb") as f:
+                f.write(uid)
+            os.replace(tmp, path)
+            return uid
+        t0 = time.time()
+        while True:
+            try:
+                with open(path, "rb") as f:
+                    data = f.read()
+                if len(data) == 128 and time.time() - os.path.getmtime(path) < 600:
+                    return data
+            except OSError:
+                pass
+            if time.time() - t0 > 120:
+                raise RuntimeError("NCCL id of rank 0 did not appear at %s" % path)
+            time.sleep(0.01)
+
+    def _allgather_equal(self, buf):
+        return self.engine.comm_allgather(buf)
+
+    def allreduce_sum(self, array):
+        array = np.ascontiguousarray(array)
+        if self.world == 1:
+            return array
+        return self.engine.comm_allreduce_sum(array).reshape(array.shape)
+
+    def max(self, value):
+        if self.world == 1:
+            return float(value)
+        return float(self.engine.comm_allreduce_max([float(value)])[0])
+
+    def close(self):
+        if self.world > 1:
+            self.engine.comm_destroy()
+
+
+class TorchComm(_CommBase):
+    """torch.distributed process group (gloo on CPU, nccl on GPUs)."""
+
+    def __init__(self, dist, device=None):
+        self.dist = dist
+        self.device = device
+        self.rank = dist.get_rank()
+        self.world = dist.get_world_size()
+
+    def _tensor(self, array):
+        import torch
+        t = torch.from_numpy(np.ascontiguousarray(array).copy())
+        return t.to(self.device) if self.device is not None else t
+
+    def _allgather_equal(self, buf):
+        import torch
+        t = self._tensor(buf)
+        outs = [torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(outs, t)
+        return [o.cpu().numpy() for o in outs]
+
+    def allreduce_sum(self, array):
+        if self.world == 1:
+            return np.ascontiguousarray(array)
+        t = self._tensor(array)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return t.cpu().numpy()
+
+    def max(self, value):
+        if self.world == 1:
+            return float(value)
+        t = self._tensor(np.array([float(value)]))
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.cpu().numpy()[0])
+
+    def close(self):
+        pass
+
+
+def _as_comm(comm):
+    """Accept a communicator, a torch.distributed module (legacy callers) or None."""
+    if comm is None or isinstance(comm, _CommBase):
+        return comm
+    return TorchComm(comm)
+
+
+def _rank_world(comm):
+    return (0, 1) if comm is None else (comm.rank, comm.world)
+
+
+# ---- sharded operations --------------------------------------------------------------------
+def gather_rows(local, n_total, comm=None, device=None):
+    comm = _as_comm(comm)
+    if comm is None:
+        return np.ascontiguousarray(local)
+    if device is not None and isinstance(comm, TorchComm):
+        comm.device = device
+    return comm.allgather_rows(local, n_total)
+
+
+def max_over_ranks(value, comm=None, device=None):
     """Maximum of a python float over all ranks (timings are max-over-ranks)."""
-    if dist is None or dist.get_world_size() == 1:
+    comm = _as_comm(comm)
+    if comm is None:
         return float(value)
-    import torch
-    t = torch.tensor([float(value)], dtype=torch.float64)
-    if device is not None:
-        t = t.to(device)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return float(t.item())
+    if device is not None and isinstance(comm, TorchComm):
+        comm.device = device
+    return comm.max(value)
 
 
-def cwt_batch_sharded(X, dt, scales, family, param, precision, engine, dist=None, device=None):
+def sum_over_ranks(array, comm=None, device=None):
+    """Element-wise sum of an integer array over all ranks (every rank gets the total)."""
+    comm = _as_comm(comm)
+    if comm is None:
+        return np.ascontiguousarray(array)
+    if device is not None and isinstance(comm, TorchComm):
+        comm.device = device
+    return comm.allreduce_sum(array)
+
+
+def cwt_batch_sharded(X, dt, scales, family, param, precision, engine, comm=None, device=None):
     """Global wavelet spectra of every channel of X[channels, n0], computed by the rank that
     owns the channel and gathered on all ranks.  X may be the full array (each rank slices
     its block) -- only the [channels, scales] result crosses the interconnect."""
-    rank = 0 if dist is None else dist.get_rank()
-    world = 1 if dist is None else dist.get_world_size()
+    comm = _as_comm(comm)
+    rank, world = _rank_world(comm)
     lo, hi = shard_range(X.shape[0], rank, world)
     power, _ = engine.cwt_batch(X[lo:hi], dt, scales, family, param, precision, want_power=True)
-    return gather_rows(power, X.shape[0], dist, device)
-
-
-def sum_over_ranks(array, dist=None, device=None):
-    """Element-wise sum of an integer/float array over all ranks (every rank gets the total)."""
-    array = np.ascontiguousarray(array)
-    if dist is None or dist.get_world_size() == 1:
-        return array
-    import torch
-    t = torch.from_numpy(array.copy())
-    if device is not None:
-        t = t.to(device)
-    dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    return t.cpu().numpy()
+    return gather_rows(power, X.shape[0], comm, device)
 
 
 def surrogate_pair(seed, index, N, al1, al2):
@@ -85,25 +206,25 @@ def surrogate_pair(seed, index, N, al1, al2):
 
 
 def wct_significance_sharded(al1, al2, dt, dj, s0, J, significance_level=0.95, wavelet='morlet',
-                             mc_count=300, seed=0, engine=None, dist=None, device=None):
+                             mc_count=300, seed=0, engine=None, comm=None, device=None):
     """Monte-Carlo coherence significance (reference wavelet.py:531-647) with the surrogate
     pairs block-partitioned over the ranks: every rank accumulates the [S, 1000]
     int64 histograms of its pairs on its GPU, ONE all-reduce (sum, ~1 MB) combines them and
     every rank evaluates the percentiles.  The result is independent of the world size."""
     from . import wavelet as wv
+    comm = _as_comm(comm)
     mother = wv._check_parameter_wavelet(wavelet)
-    rank = 0 if dist is None else dist.get_rank()
-    world = 1 if dist is None else dist.get_world_size()
+    rank, world = _rank_world(comm)
     prob = wv._mc_problem(dt, dj, s0, J, mother)
     lo, hi = shard_range(mc_count, rank, world)
     hist = wv._mc_histogram(prob, dt, dj, mother,
                             lambda i: surrogate_pair(seed, i, prob['N'], al1, al2),
                             range(lo, hi), progress=False, engine=engine)
-    hist = sum_over_ranks(hist, dist, device)
+    hist = sum_over_ranks(hist, comm, device)
     return wv._mc_levels(prob, hist, significance_level)
 
 
-def cwt_scale_sharded(signal, dt, scales, family, param, precision, engine, dist=None, device=None,
+def cwt_scale_sharded(signal, dt, scales, family, param, precision, engine, comm=None, device=None,
                       fetch=False):
     """One long signal, scales block-partitioned over the ranks.  Every rank
     holds the signal and runs its own forward transform (0.04 ms at N = 2^20 -- cheaper than
@@ -112,8 +233,8 @@ def cwt_scale_sharded(signal, dt, scales, family, param, precision, engine, dist
     (mean_n |W|^2, [S]) is all-gathered so that every rank sees the whole spectrum.
 
     Returns (lo, hi, global_power[S], W_slab or None): rows [lo, hi) are this rank's scales."""
-    rank = 0 if dist is None else dist.get_rank()
-    world = 1 if dist is None else dist.get_world_size()
+    comm = _as_comm(comm)
+    rank, world = _rank_world(comm)
     scales = np.ascontiguousarray(scales, dtype=np.float64)
     lo, hi = shard_range(scales.size, rank, world)
     W = None
@@ -122,5 +243,5 @@ def cwt_scale_sharded(signal, dt, scales, family, param, precision, engine, dist
         local = engine.global_power(hi - lo)
     else:
         local = np.zeros(0)
-    power = gather_rows(local.reshape(-1, 1), scales.size, dist, device).ravel()
+    power = gather_rows(local.reshape(-1, 1), scales.size, comm, device).ravel()
     return lo, hi, power, W

@@ -20,9 +20,9 @@ _engine.Engine.profile_last = lambda self: [
     {"name": "PassABody<double, 1024, 0, 1>", "launches": 1, "ms": 0.25, "rows": 24}]
 import bench  # noqa: E402
 
-bench.N0 = 2 ** 12
+bench.wl.C2["n"] = 2 ** 12
 bench.ClockSampler = type("CS", (), {
     "__init__": lambda s, *a, **k: None, "start": lambda s: None,
     "stop": lambda s: {"sm_mhz": 1965.0, "sm_max_mhz": 1965.0, "samples": 1, "reasons": []}})
-sys.argv = ["bench.py", "--steps", "3", "--warmup", "1"]
+sys.argv = ["bench.py", "--steps", "3", "--warmup", "1", "--configs", "2"]
 bench.main()

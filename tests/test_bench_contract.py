@@ -31,7 +31,26 @@ def test_reference_arm_prints_one_contract_line():
     assert e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0
     assert e2e["value"] == d["value"] and e2e["unit"] == d["unit"]
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    from oracle import make_ref
+    # the unmodified reference package where its copy exists (oracle/_ref, built by
+    # __graft_entry__.build() from /root/reference), else the oracle port; one thread either way
+    assert cb["kind"] == ("reference" if make_ref.available() else "port")
+    assert cb["cores"] == 1 and cb["value"] == d["value"] and cb["sample"]
+
+
+def test_reference_copy_is_the_unmodified_reference():
+    """oracle/_ref/pycwt (the timing arm) is byte-identical to the reference checkout where both exist."""
+    import hashlib
+    from oracle import make_ref
+    src = os.path.join(make_ref.REF_ROOT, "pycwt")
+    if not (make_ref.available() and os.path.isdir(src)):
+        return
+    for f in make_ref.FILES:
+        a = hashlib.sha256(open(os.path.join(src, f), "rb").read()).hexdigest()
+        b = hashlib.sha256(open(os.path.join(make_ref.DST, "pycwt", f), "rb").read()).hexdigest()
+        assert a == b, f
+    mod = make_ref.load()
+    assert mod.__version__ == "0.3.0a22" and mod.cwt.__module__ == "pycwt.wavelet"
 
 
 def test_reference_arm_other_ranks_exit_quietly():
@@ -77,5 +96,7 @@ def test_product_arm_json_assembly_on_the_emulation_build():
         assert k in rf, k
     assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-12
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] == 1 and cb["value"] > 0 and cb["sample"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] == 1 and cb["value"] > 0 and cb["sample"]
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    assert d["e2e"]["resident"]["value"] > 0 and d["configs"] == {}
+    assert rf["kernel"] == "PassBBody<double, 1, 1024>" and rf["source_hash"]

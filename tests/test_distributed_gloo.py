@@ -82,11 +82,11 @@ def _mc_worker(rank, world, port, q):
     try:
         eng = _engine.Engine(0, lib_path=os.path.join(ROOT, "tests", "_emu", "libcwtb200_emu.so"))
         sig = D.wct_significance_sharded(0.2, 0.1, 1.0, 0.5, 2.0, 8, 0.95, 'morlet', mc_count=5,
-                                         seed=42, engine=eng, dist=dist)
+                                         seed=42, engine=eng, comm=D.TorchComm(dist))
         # one signal, scales sharded over the ranks; the global spectrum is gathered
         x = np.random.RandomState(5).randn(3000)
         sj = 2.0 * 2 ** (np.arange(13) / 2.0)
-        lo, hi, power, W = D.cwt_scale_sharded(x, 1.0, sj, 0, 6.0, 0, eng, dist, fetch=True)
+        lo, hi, power, W = D.cwt_scale_sharded(x, 1.0, sj, 0, 6.0, 0, eng, D.TorchComm(dist), fetch=True)
         q.put((rank, sig.tolist(), (lo, hi), power.tolist(), np.abs(W).sum()))
         eng.close()
     finally:
@@ -133,3 +133,39 @@ def test_sharded_wct_significance_gloo():
     for r in (0, 1):
         assert np.allclose(res[r][3], ref, rtol=1e-12)
     assert abs(res[0][4] + res[1][4] - np.abs(Wr).sum()) < 1e-9 * np.abs(Wr).sum()
+
+
+class _FakeCommEngine(object):
+    """Engine stand-in recording the communicator calls of NcclComm (no NCCL on this box)."""
+
+    def __init__(self):
+        self.inited = None
+
+    def comm_unique_id(self):
+        return bytes(range(128))
+
+    def comm_init(self, world, rank, uid):
+        self.inited = (world, rank, bytes(uid))
+
+    def comm_destroy(self):
+        self.inited = None
+
+
+def test_nccl_comm_id_exchange_through_rendezvous_file(tmp_path, monkeypatch):
+    """NcclComm hands rank 0's 128-byte id to the other ranks through a rendezvous file
+    (host-side logic only; the collectives themselves run on the GPU box)."""
+    from pycwt_b200 import distributed as D
+    monkeypatch.setenv("CWTB_COMM_DIR", str(tmp_path))
+    monkeypatch.setenv("MASTER_PORT", "29517")
+    e0, e1 = _FakeCommEngine(), _FakeCommEngine()
+    c0 = D.NcclComm(e0, rank=0, world=2)
+    c1 = D.NcclComm(e1, rank=1, world=2)
+    assert e0.inited == (2, 0, bytes(range(128))) and e1.inited == (2, 1, bytes(range(128)))
+    assert (c0.rank, c0.world, c1.rank) == (0, 2, 1)
+    c0.close(), c1.close()
+    assert e0.inited is None
+    # a single process needs neither NCCL nor a file
+    solo = D.NcclComm(_FakeCommEngine(), rank=0, world=1)
+    assert solo.max(3.5) == 3.5
+    assert np.array_equal(solo.allgather_rows(np.arange(6.0).reshape(3, 2), 3), np.arange(6.0).reshape(3, 2))
+    assert np.array_equal(solo.allreduce_sum(np.arange(4)), np.arange(4))
