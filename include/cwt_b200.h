@@ -192,6 +192,17 @@ int cwtb_wct_mc(cwtb_ctx *ctx, const double *noise, int n_pairs, int64_t n0,
                 double dt, double dj, const double *scales, int n_scales,
                 int family, double param, int boxcar_len, const uint8_t *mask,
                 int maxscale, int nbins, int64_t *hist);
+/* The same accumulation with the surrogates drawn ON THE DEVICE (SURVEY 8b vi "seed"): pair number
+ * first_pair + i is standard-normal white noise from the counter-based Philox4x32-10 stream keyed
+ * by (seed, pair number), so a run does not depend on how the pairs are split over calls, ranks
+ * or GPUs.  Statistically equivalent to the reference's surrogates (which are white noise too,
+ * helpers.py:146-173), not bit-identical to numpy's stream; no host RNG and no H2D of noise. */
+int cwtb_wct_mc_seeded(cwtb_ctx *ctx, uint64_t seed, int64_t first_pair, int n_pairs, int64_t n0,
+                       double dt, const double *scales, int n_scales, int family, double param,
+                       int boxcar_len, const uint8_t *mask, int maxscale, int nbins, int64_t *hist);
+/* Test hook: the surrogates of the seeded mode, out[n_pairs][2][n0]. */
+int cwtb_mc_surrogates(cwtb_ctx *ctx, uint64_t seed, int64_t first_pair, int n_pairs, int64_t n0,
+                       double *out);
 
 /* ---- batched transform of independent channels ------- */
 /* X: host [n_chan, n0] (float or double).  The per-channel transforms stay on

@@ -64,6 +64,8 @@ _SIGNATURES = {
     "cwtb_wct": (_I, [_P, _P, _P, _I64, _D, _D, _P, _I, _I, _D, _I, _P, _P]),
     "cwtb_smooth": (_I, [_P, _P, _I, _I, _I64, _D, _P, _I, _P]),
     "cwtb_wct_mc": (_I, [_P, _P, _I, _I64, _D, _D, _P, _I, _I, _D, _I, _P, _I, _I, _P]),
+    "cwtb_wct_mc_seeded": (_I, [_P, ctypes.c_uint64, _I64, _I, _I64, _D, _P, _I, _I, _D, _I, _P, _I, _I, _P]),
+    "cwtb_mc_surrogates": (_I, [_P, ctypes.c_uint64, _I64, _I, _I64, _P]),
     "cwtb_cwt_batch": (_I, [_P, _P, _I, _I, _I64, _D, _P, _I, _I, _D, _I, _P, _P]),
     "cwtb_cwt_batch_dev": (_I, [_P, _P, _I, _I64, _D, _P, _I, _I, _D, _I, _P]),
     "cwtb_comm_unique_id": (_I, [_P]),
@@ -507,6 +509,29 @@ class Engine(object):
                                              int(maxscale), int(nbins), _ptr(hist)))
             self._resident = None
         return hist
+
+    @_locked
+    def wct_mc_seeded(self, seed, first_pair, n_pairs, n0, dt, scales, family, param, boxcar_len, mask,
+                      maxscale, nbins, hist):
+        """Monte-Carlo coherence histograms of `n_pairs` surrogate pairs drawn on the device
+        (Philox stream keyed by (seed, pair number)); accumulated into `hist`."""
+        sj = np.ascontiguousarray(scales, dtype=np.float64)
+        mask = np.ascontiguousarray(mask, dtype=np.uint8)
+        assert mask.shape == (sj.size, int(n0))
+        assert hist.dtype == np.int64 and hist.flags.c_contiguous and hist.shape == (sj.size, nbins)
+        self._check(self.lib.cwtb_wct_mc_seeded(self.h, int(seed) & (2 ** 64 - 1), int(first_pair), int(n_pairs),
+                                                int(n0), float(dt), _ptr(sj), sj.size, int(family),
+                                                float(param), int(boxcar_len), _ptr(mask), int(maxscale),
+                                                int(nbins), _ptr(hist)))
+        self._resident = None
+        return hist
+
+    @_locked
+    def mc_surrogates(self, seed, first_pair, n_pairs, n0):
+        out = np.empty((int(n_pairs), 2, int(n0)), dtype=np.float64)
+        self._check(self.lib.cwtb_mc_surrogates(self.h, int(seed) & (2 ** 64 - 1), int(first_pair),
+                                                int(n_pairs), int(n0), _ptr(out)))
+        return out
 
     @_locked
     def cwt_batch(self, X, dt, scales, family, param, precision=F64, want_power=True,

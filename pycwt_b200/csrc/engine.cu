@@ -157,6 +157,8 @@ struct cwtb_ctx {
   int d2h_split = 1;             // CWTB_D2H_SPLIT
   std::string err;
   double band_eps = 1e-16;
+  double band_eps32 = 1e-9;      // fp32 engine: pruning threshold matched to the arithmetic (fp32
+                                 // rounding is 6e-8; the dropped terms stay two orders below it)
   double expand_eps = 5e-13;     // fp64 engine: bound on the aliasing error of the expansion path
                                  // (0: path off, every scale through the exact pruned transforms)
   double expand_eps32 = 2e-7;    // fp32 engine
@@ -527,7 +529,9 @@ static int build_job(cwtb_ctx *c, Job &job, long long n0, double dt, const doubl
   const double w1 = 6.283185307179586 * ((N == 2 ? -1.0 : 1.0) * fam.dw);
   double flo = 0, fhi = 0;
   bool pos_only = false;
-  if (family != CWTB_TABLE) family_band(family, param, c->band_eps, &flo, &fhi, &pos_only);
+  // eps = 0 (exact mode) applies to both engines
+  const double beps = (precision == CWTB_F32 && c->band_eps > 0) ? std::max(c->band_eps, c->band_eps32) : c->band_eps;
+  if (family != CWTB_TABLE) family_band(family, param, beps, &flo, &fhi, &pos_only);
 
   std::vector<ScaleDesc> ds(S);
   job.plan_log2K.assign(S, 0);
@@ -1648,6 +1652,7 @@ int cwtb_create(int device, cwtb_ctx **out) {
   if (const char *g = getenv("CWTB_GROUP")) c->group = std::max(0, atoi(g));
   if (const char *g = getenv("CWTB_GROUP_MB")) c->group_bytes = (size_t)std::max(1, atoi(g)) << 20;
   if (const char *g = getenv("CWTB_BAND_EPS")) c->band_eps = atof(g);
+  if (const char *g = getenv("CWTB_BAND_EPS32")) c->band_eps32 = atof(g);
   if (const char *g = getenv("CWTB_EXPAND_EPS")) c->expand_eps = std::max(0.0, atof(g));
   if (const char *g = getenv("CWTB_EXPAND_EPS32")) c->expand_eps32 = std::max(0.0, atof(g));
   if (const char *g = getenv("CWTB_EXPAND_MIN_R")) c->expand_min_log2R = std::min(14, std::max(2, atoi(g)));
@@ -2149,22 +2154,29 @@ int cwtb_cwt_to_host(cwtb_ctx *c, const void *signal, int signal_is_f32, int64_t
   return cwtb_get_w(c, out, out_f64, 0, n_scales);
 }
 
+// rows per block of the column reductions: enough blocks to fill the machine, few enough that the
+// atomics stay negligible
+static int reduction_rows_per_block(int rows) { return rows <= 32 ? rows : 32; }
+
 int cwtb_icwt_sum(cwtb_ctx *c, double *out) {
   if (!c || !c->job.valid || !out) return fail(c, CWTB_ERR_STATE, "no transform resident");
   const Job &job = c->job;
   if (job.nbatch != 1) return fail(c, CWTB_ERR_UNSUPPORTED, "icwt of a batched transform: fetch rows per channel");
   std::vector<double> rs(job.S);
-  for (int j = 0; j < job.S; ++j) rs[j] = std::sqrt(job.scales[j]);
+  for (int j = 0; j < job.S; ++j) rs[j] = 1.0 / std::sqrt(job.scales[j]);
   int e = upload_doubles(c, c->rowd, rs);
   if (e) return e;
   if ((e = ensure(c, c->aux, (size_t)job.n0 * sizeof(double)))) return e;
   const unsigned gx = (unsigned)((job.n0 + NT - 1) / NT);
+  const int rpb = reduction_rows_per_block(job.S);
+  const unsigned gy = (unsigned)((job.S + rpb - 1) / rpb);
+  if (gy > 1) RT(rt_memset(c->aux.p, 0, (size_t)job.n0 * sizeof(double), c->stream));
   if (job.precision == CWTB_F64) {
-    IcwtArgs<double> a{(const double2 *)c->W.p, (const double *)c->rowd.p, (double *)c->aux.p, job.n0, job.n0, job.S, 0};
-    e = launch<IcwtBody<double>>(c, gx, 1, a);
+    IcwtArgs<double> a{(const double2 *)c->W.p, (const double *)c->rowd.p, (double *)c->aux.p, job.n0, job.n0, job.S, 0, rpb};
+    e = launch<IcwtBody<double>>(c, gx, gy, a);
   } else {
-    IcwtArgs<float> a{(const float2 *)c->W.p, (const double *)c->rowd.p, (double *)c->aux.p, job.n0, job.n0, job.S, 0};
-    e = launch<IcwtBody<float>>(c, gx, 1, a);
+    IcwtArgs<float> a{(const float2 *)c->W.p, (const double *)c->rowd.p, (double *)c->aux.p, job.n0, job.n0, job.S, 0, rpb};
+    e = launch<IcwtBody<float>>(c, gx, gy, a);
   }
   if (e) return e;
   RT(rt_d2h(out, c->aux.p, (size_t)job.n0 * sizeof(double), c->stream));
@@ -2175,7 +2187,7 @@ int cwtb_icwt_sum(cwtb_ctx *c, double *out) {
 int cwtb_icwt_sum_host(cwtb_ctx *c, const void *W, const double *scales, int n_scales, int64_t n, double *out) {
   if (!c || !W || !scales || !out || n_scales < 1 || n < 1) return fail(c, CWTB_ERR_ARG, "icwt: bad argument");
   std::vector<double> rs(n_scales);
-  for (int j = 0; j < n_scales; ++j) rs[j] = std::sqrt(scales[j]);
+  for (int j = 0; j < n_scales; ++j) rs[j] = 1.0 / std::sqrt(scales[j]);
   int e = upload_doubles(c, c->rowd, rs);
   if (e) return e;
   if ((e = ensure(c, c->aux, (size_t)n * sizeof(double)))) return e;
@@ -2185,7 +2197,7 @@ int cwtb_icwt_sum_host(cwtb_ctx *c, const void *W, const double *scales, int n_s
   for (int r0 = 0; r0 < n_scales; r0 += chunk) {
     const int nr = std::min(chunk, n_scales - r0);
     RT(rt_h2d(c->scratch.p, (const double2 *)W + (size_t)r0 * n, (size_t)nr * n * sizeof(double2), c->stream));
-    IcwtArgs<double> a{(const double2 *)c->scratch.p, (const double *)c->rowd.p + r0, (double *)c->aux.p, n, n, nr, r0 > 0};
+    IcwtArgs<double> a{(const double2 *)c->scratch.p, (const double *)c->rowd.p + r0, (double *)c->aux.p, n, n, nr, r0 > 0, nr};
     if ((e = launch<IcwtBody<double>>(c, gx, 1, a))) return e;
     RT(rt_sync(c->stream));
   }
@@ -2218,7 +2230,7 @@ static int power_common(cwtb_ctx *c, double *power_out, double *mean_out, const 
     }
     RT(rt_h2d(dlo, rng.data(), rng.size() * sizeof(long long), c->stream));
   }
-  const unsigned gx = (unsigned)((job.n0 + 8 * NT - 1) / (8 * NT));
+  const unsigned gx = (unsigned)((job.n0 + PowerBody<double>::PER * NT - 1) / (PowerBody<double>::PER * NT));
   if (job.precision == CWTB_F64) {
     PowerArgs<double> a{(const double2 *)c->W.p, dpow, dsum, job.n0, row_scale ? dmul : nullptr,
                         rng.empty() ? nullptr : dlo, rng.empty() ? nullptr : dhi};
@@ -2255,17 +2267,28 @@ int cwtb_scale_avg_power(cwtb_ctx *c, const double *weights, double *out) {
   if (!weights || !out) return fail(c, CWTB_ERR_ARG, "null argument");
   const Job &job = c->job;
   if (job.nbatch != 1) return fail(c, CWTB_ERR_UNSUPPORTED, "scale average of a batched transform: fetch rows per channel");
+  // [weights S doubles][selected rows S ints]: rows with a zero weight are not read at all
   std::vector<double> w(weights, weights + job.S);
+  std::vector<int> sel;
+  for (int j = 0; j < job.S; ++j)
+    if (w[j] != 0.0) sel.push_back(j);
+  const int nsel = (int)sel.size();
+  w.resize((size_t)job.S + ((size_t)job.S + 1) / 2);
+  if (nsel) memcpy(w.data() + job.S, sel.data(), sizeof(int) * nsel);
   int e = upload_doubles(c, c->rowd, w);
   if (e) return e;
   if ((e = ensure(c, c->aux, (size_t)job.n0 * sizeof(double)))) return e;
   const unsigned gx = (unsigned)((job.n0 + NT - 1) / NT);
+  const int spb = nsel <= 32 ? std::max(nsel, 1) : 32;
+  const unsigned gy = (unsigned)std::max(1, (nsel + spb - 1) / spb);
+  if (gy > 1) RT(rt_memset(c->aux.p, 0, (size_t)job.n0 * sizeof(double), c->stream));
+  const int *dsel = (const int *)((const double *)c->rowd.p + job.S);
   if (job.precision == CWTB_F64) {
-    ScaleAvgArgs<double> a{(const double2 *)c->W.p, (const double *)c->rowd.p, (double *)c->aux.p, job.n0, job.S};
-    e = launch<ScaleAvgBody<double>>(c, gx, 1, a);
+    ScaleAvgArgs<double> a{(const double2 *)c->W.p, (const double *)c->rowd.p, (double *)c->aux.p, job.n0, job.S, dsel, nsel, spb};
+    e = launch<ScaleAvgBody<double>>(c, gx, gy, a);
   } else {
-    ScaleAvgArgs<float> a{(const float2 *)c->W.p, (const double *)c->rowd.p, (double *)c->aux.p, job.n0, job.S};
-    e = launch<ScaleAvgBody<float>>(c, gx, 1, a);
+    ScaleAvgArgs<float> a{(const float2 *)c->W.p, (const double *)c->rowd.p, (double *)c->aux.p, job.n0, job.S, dsel, nsel, spb};
+    e = launch<ScaleAvgBody<float>>(c, gx, gy, a);
   }
   if (e) return e;
   RT(rt_d2h(out, c->aux.p, (size_t)job.n0 * sizeof(double), c->stream));
@@ -2369,11 +2392,12 @@ int cwtb_smooth(cwtb_ctx *c, const void *in, int is_complex, int n_scales, int64
   return 0;
 }
 
-int cwtb_wct_mc(cwtb_ctx *c, const double *noise, int n_pairs, int64_t n0, double dt, double dj,
-                const double *scales, int n_scales, int family, double param, int boxcar_len,
-                const uint8_t *mask, int maxscale, int nbins, int64_t *hist) {
-  (void)dj;
-  if (!c || !noise || !mask || !hist || n_pairs < 0 || nbins < 1 || maxscale < 0 || maxscale > n_scales)
+// common part of the two Monte-Carlo entry points: `noise` host surrogates [n_pairs][2][n0], or
+// null -> drawn on the device from (seed, pair0 + i)
+static int wct_mc_core(cwtb_ctx *c, const double *noise, unsigned long long seed, long long pair0, int n_pairs,
+                       int64_t n0, double dt, const double *scales, int n_scales, int family, double param,
+                       int boxcar_len, const uint8_t *mask, int maxscale, int nbins, int64_t *hist) {
+  if (!c || !mask || !hist || n_pairs < 0 || nbins < 1 || maxscale < 0 || maxscale > n_scales)
     return fail(c, CWTB_ERR_ARG, "wct_mc: bad argument");
   if (family == CWTB_TABLE) return fail(c, CWTB_ERR_UNSUPPORTED, "wct_mc needs an analytic wavelet family");
   int e = prepare(c, n0, dt, scales, n_scales, family, param, CWTB_F64, nullptr);
@@ -2386,16 +2410,25 @@ int cwtb_wct_mc(cwtb_ctx *c, const double *noise, int n_pairs, int64_t n0, doubl
   const size_t hb = (size_t)n_scales * nbins * sizeof(unsigned long long);
   if ((e = ensure(c, c->hist, hb))) return e;
   RT(rt_memset(c->hist.p, 0, hb, c->stream));
-  if ((e = ensure(c, c->noise, (size_t)n_pairs * 2 * n0 * sizeof(double)))) return e;
-  RT(rt_h2d(c->noise.p, noise, (size_t)n_pairs * 2 * n0 * sizeof(double), c->stream));
+  // surrogates of at most `batch` pairs are resident at a time
+  const int batch = noise ? n_pairs : (int)std::max<size_t>(1, std::min<size_t>((size_t)n_pairs, ((size_t)256 << 20) / ((size_t)2 * n0 * sizeof(double))));
+  if ((e = ensure(c, c->noise, (size_t)std::max(batch, 1) * 2 * n0 * sizeof(double)))) return e;
+  if (noise) RT(rt_h2d(c->noise.p, noise, (size_t)n_pairs * 2 * n0 * sizeof(double), c->stream));
   RT(rt_sync(c->stream));
   c->launches = 0;
   if ((e = time_begin(c))) return e;
-  for (int i = 0; i < n_pairs; ++i) {
-    const double *a = (const double *)c->noise.p + (size_t)i * 2 * n0;
-    if ((e = wct_core(c, c->job, a, a + n0, boxcar_len, nullptr, nullptr, (const unsigned char *)c->mask.p,
-                      maxscale, nbins, (unsigned long long *)c->hist.p)))
-      return e;
+  for (int i0 = 0; i0 < n_pairs; i0 += batch) {
+    const int nb = std::min(batch, n_pairs - i0);
+    if (!noise) {
+      NoiseArgs na{(double *)c->noise.p, seed, pair0 + i0, (long long)n0, nb};
+      if ((e = launch<NoiseBody>(c, (unsigned)(((n0 + 1) / 2 + NT - 1) / NT), (unsigned)(2 * nb), na))) return e;
+    }
+    for (int i = 0; i < nb; ++i) {
+      const double *a = (const double *)c->noise.p + (size_t)i * 2 * n0;
+      if ((e = wct_core(c, c->job, a, a + n0, boxcar_len, nullptr, nullptr, (const unsigned char *)c->mask.p,
+                        maxscale, nbins, (unsigned long long *)c->hist.p)))
+        return e;
+    }
   }
   if ((e = time_end(c))) return e;
   c->job_dsig = nullptr;
@@ -2403,6 +2436,34 @@ int cwtb_wct_mc(cwtb_ctx *c, const double *noise, int n_pairs, int64_t n0, doubl
   RT(rt_d2h(h.data(), c->hist.p, hb, c->stream));
   RT(rt_sync(c->stream));
   for (size_t i = 0; i < h.size(); ++i) hist[i] += (int64_t)h[i];
+  return 0;
+}
+
+int cwtb_wct_mc(cwtb_ctx *c, const double *noise, int n_pairs, int64_t n0, double dt, double dj,
+                const double *scales, int n_scales, int family, double param, int boxcar_len,
+                const uint8_t *mask, int maxscale, int nbins, int64_t *hist) {
+  (void)dj;
+  if (!noise) return fail(c, CWTB_ERR_ARG, "wct_mc: null surrogates");
+  return wct_mc_core(c, noise, 0, 0, n_pairs, n0, dt, scales, n_scales, family, param, boxcar_len, mask,
+                     maxscale, nbins, hist);
+}
+
+int cwtb_wct_mc_seeded(cwtb_ctx *c, uint64_t seed, int64_t first_pair, int n_pairs, int64_t n0, double dt,
+                       const double *scales, int n_scales, int family, double param, int boxcar_len,
+                       const uint8_t *mask, int maxscale, int nbins, int64_t *hist) {
+  return wct_mc_core(c, nullptr, seed, first_pair, n_pairs, n0, dt, scales, n_scales, family, param, boxcar_len,
+                     mask, maxscale, nbins, hist);
+}
+
+// test hook: the surrogates of the seeded mode, [n_pairs][2][n0] to the host
+int cwtb_mc_surrogates(cwtb_ctx *c, uint64_t seed, int64_t first_pair, int n_pairs, int64_t n0, double *out) {
+  if (!c || !out || n_pairs < 1 || n0 < 1) return fail(c, CWTB_ERR_ARG, "mc_surrogates: bad argument");
+  int e = ensure(c, c->noise, (size_t)n_pairs * 2 * n0 * sizeof(double));
+  if (e) return e;
+  NoiseArgs na{(double *)c->noise.p, seed, first_pair, (long long)n0, n_pairs};
+  if ((e = launch<NoiseBody>(c, (unsigned)(((n0 + 1) / 2 + NT - 1) / NT), (unsigned)(2 * n_pairs), na))) return e;
+  RT(rt_d2h(out, c->noise.p, (size_t)n_pairs * 2 * n0 * sizeof(double), c->stream));
+  RT(rt_sync(c->stream));
   return 0;
 }
 

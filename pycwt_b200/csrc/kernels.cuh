@@ -758,17 +758,19 @@ template <typename T, int TAPS, int EPI = EPI_STORE> struct ExpandBody {
       V win[TAPS];
 #pragma unroll
       for (int t = 0; t < TAPS - 1; ++t) win[t] = run[t + (t >> 5)];
-      // re-modulation e^{2 pi i kc n / Np}: table value at the start of the run and after 16 steps,
-      // recurrence (step e^{2 pi i kc R / Np}) in between -- in fp64 for both engines
+      // re-modulation e^{2 pi i kc n / Np}: table value (fp64 roots) every RESEED steps, recurrence
+      // (step e^{2 pi i kc R / Np}) in between, in the engine's arithmetic: fp64 drifts 1e-16 per
+      // step (16 steps), fp32 6e-8 per step (8 steps: 5e-7 of the 1e-5 budget)
+      constexpr int RESEED = sizeof(T) == 8 ? 16 : 8;
       const unsigned kc = (unsigned)d.ip_kc;
       const unsigned nlo = (unsigned)nfirst;
-      const double2 stepw = nroot(a.nt, kc << log2R);
-      double2 tw = nroot(a.nt, kc * nlo);
+      const V stepw = nroot_t<T>(a.nt, kc << log2R);
+      V tw = mk<T>(1, 0);
       V *p = a.W + (size_t)d.row * a.n0 + nfirst;
 #pragma unroll
       for (int s = 0; s < L; ++s) {
         win[(s + TAPS - 1) % TAPS] = run[(s + TAPS - 1) + ((s + TAPS - 1) >> 5)];
-        if (s == 16) tw = nroot(a.nt, kc * (nlo + (16u << log2R)));
+        if (s % RESEED == 0) tw = nroot_t<T>(a.nt, kc * (nlo + ((unsigned)s << log2R)));
         // 8 independent chains (4 per component): the fp64 pipe needs that much parallelism per warp
         T ar[4] = {0, 0, 0, 0}, ai[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -778,7 +780,7 @@ template <typename T, int TAPS, int EPI = EPI_STORE> struct ExpandBody {
           ai[t & 3] += cv.y * hw[t];
         }
         const V acc = mk<T>((ar[0] + ar[1]) + (ar[2] + ar[3]), (ai[0] + ai[1]) + (ai[2] + ai[3]));
-        const V x = cmul(acc, mk<T>((T)tw.x, (T)tw.y));
+        const V x = cmul(acc, tw);
         tw = cmul(tw, stepw);
         if (s < smax) {
           if (EPI == EPI_MULCONJ) *p = cmul(*p, cconj(x));
@@ -968,21 +970,48 @@ template <typename T> struct TinyFwdBody {
 // ---- Body: icwt reduction  out[n] (+)= sum_j Re(W[j,n]) / sqrt(s_j)   (wavelet.py:169-170) ----
 template <typename T> struct IcwtArgs {
   const cx<T> *W;
-  const double *sqrt_s;   // per row
+  const double *inv_sqrt_s;   // per row: 1 / sqrt(s_j)
   double *out;
   long long n, pitch;
   int rows, accumulate;
+  int rows_per_block;         // gridDim.y blocks of rows; > 1 block: partial sums meet in `out` by atomics
 };
+// One column per thread, rows in blocks of `rows_per_block` (blockIdx.y), 8 independent loads in
+// flight per thread: a streaming read of W at HBM rate (4.29 GB at config 2).
 template <typename T> struct IcwtBody {
   using Args = IcwtArgs<T>;
   static constexpr int NPHASE = 1;
   static constexpr size_t SMEM = 0;
-  template <int PH> HD static void phase(const Args &a, int bx, int, int tid, void *) {
+  template <int PH> HD static void phase(const Args &a, int bx, int by, int tid, void *) {
     const long long n = (long long)bx * NT + tid;
     if (n >= a.n) return;
-    double acc = a.accumulate ? a.out[n] : 0.0;
-    for (int j = 0; j < a.rows; ++j) acc += (double)a.W[(size_t)j * a.pitch + n].x / a.sqrt_s[j];
-    a.out[n] = acc;
+    const int j0 = by * a.rows_per_block;
+    const int j1 = j0 + a.rows_per_block < a.rows ? j0 + a.rows_per_block : a.rows;
+    const cx<T> *p = a.W + (size_t)j0 * a.pitch + n;
+    double acc0 = 0, acc1 = 0;
+    int j = j0;
+    for (; j + 8 <= j1; j += 8) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = (double)ldg(&p[(size_t)u * a.pitch]).x;
+#pragma unroll
+      for (int u = 0; u < 8; u += 2) {
+        acc0 += v[u] * a.inv_sqrt_s[j + u];
+        acc1 += v[u + 1] * a.inv_sqrt_s[j + u + 1];
+      }
+      p += (size_t)8 * a.pitch;
+    }
+    for (; j < j1; ++j, p += a.pitch) acc0 += (double)ldg(p).x * a.inv_sqrt_s[j];
+    const double acc = acc0 + acc1;
+    if (a.rows_per_block >= a.rows) {
+      a.out[n] = a.accumulate ? a.out[n] + acc : acc;
+    } else {
+#if defined(__CUDA_ARCH__) && !defined(CWTB_HOST_EMU)
+      atomicAdd(&a.out[n], acc);
+#else
+      a.out[n] += acc;
+#endif
+    }
   }
 };
 
@@ -1011,6 +1040,57 @@ struct WctPrepBody {
     a.C[i] = make_double2((w1.x * w1.x + w1.y * w1.y) / s, (w2.x * w2.x + w2.y * w2.y) / s);
     a.A12[i] = make_double2(w12.x / s, w12.y / s);
     if (a.aWCT) a.aWCT[i] = atan2(w12.y, w12.x);
+  }
+};
+
+// ---- Body: white-noise surrogates on the device (seeded mode of the Monte-Carlo significance) ----
+// Counter-based Philox4x32-10 (Salmon et al. 2011): sample pair (2j, 2j+1) of series `ser` of
+// surrogate pair `pair` is a pure function of (seed, pair, ser, j) -- independent of the launch
+// geometry, of the rank that draws it and of how the pairs are batched.  Two 53-bit uniforms ->
+// two standard normals (Box-Muller).  The reference's surrogates are white noise as well
+// (helpers.py:146-173 filters a length-1 axis); this mode reproduces their
+// distribution, not numpy's bit stream (the host-RNG mode does that).
+struct NoiseArgs {
+  double *out;              // [n_pairs][2][n]
+  unsigned long long seed;
+  long long pair0;          // global index of the first pair
+  long long n;
+  int n_pairs;
+};
+HD void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1, unsigned (&o)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0;
+    const unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c2;
+    const unsigned n0 = (unsigned)(p1 >> 32) ^ c1 ^ k0, n1 = (unsigned)p1;
+    const unsigned n2 = (unsigned)(p0 >> 32) ^ c3 ^ k1, n3 = (unsigned)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
+}
+struct NoiseBody {
+  using Args = NoiseArgs;
+  static constexpr int NPHASE = 1;
+  static constexpr size_t SMEM = 0;
+  template <int PH> HD static void phase(const Args &a, int bx, int by, int tid, void *) {
+    const long long j = (long long)bx * NT + tid;        // sample pair index
+    if (2 * j >= a.n) return;
+    const long long pair = a.pair0 + by / 2;
+    const int ser = by & 1;
+    unsigned o[4];
+    philox4x32_10((unsigned)j, (unsigned)((unsigned long long)j >> 32), (unsigned)pair,
+                  ((unsigned)((unsigned long long)pair >> 32) << 1) | (unsigned)ser,
+                  (unsigned)a.seed, (unsigned)(a.seed >> 32), o);
+    // uniforms in (0, 1): 53 bits from two words, offset by half an ulp so that log() is finite
+    const double u1 = ((double)(o[0] >> 5) * 67108864.0 + (double)(o[1] >> 6) + 0.5) * (1.0 / 9007199254740992.0);
+    const double u2 = ((double)(o[2] >> 5) * 67108864.0 + (double)(o[3] >> 6) + 0.5) * (1.0 / 9007199254740992.0);
+    const double r = sqrt(-2.0 * log(u1));
+    double sn, cs;
+    sincospi_hd(2.0 * u2, &sn, &cs);
+    double *dst = a.out + (size_t)by * a.n + 2 * j;
+    dst[0] = r * cs;
+    if (2 * j + 1 < a.n) dst[1] = r * sn;
   }
 };
 
@@ -1095,17 +1175,25 @@ template <typename T> struct PowerBody {
   using Args = PowerArgs<T>;
   static constexpr int NPHASE = 1;
   static constexpr size_t SMEM = 0;
+  static constexpr int PER = 16;   // columns per thread: 16 independent 16-byte loads in flight
   template <int PH> HD static void phase(const Args &a, int bx, int by, int tid, void *) {
-    // each thread covers 8 columns; one atomic per thread for the row sum
+    // one atomic per warp for the row sum
     double acc = 0;
     const double mul = a.rowmul ? a.rowmul[by] : 1.0;
     const long long lo = a.lo ? a.lo[by] : 0, hi = a.hi ? a.hi[by] : a.n;
-    for (int i = 0; i < 8; ++i) {
-      const long long n = ((long long)bx * 8 + i) * NT + tid;
-      if (n >= a.n) break;
-      const cx<T> w = a.W[(size_t)by * a.n + n];
-      const double p = ((double)w.x * w.x + (double)w.y * w.y) * mul;
-      if (a.power) a.power[(size_t)by * a.n + n] = p;
+    const long long n0 = (long long)bx * PER * NT + tid;
+    const cx<T> *row = a.W + (size_t)by * a.n;
+    cx<T> w[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const long long n = n0 + (long long)i * NT;
+      w[i] = n < a.n ? ldg(&row[n]) : mk<T>(0, 0);
+    }
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const long long n = n0 + (long long)i * NT;
+      const double p = ((double)w[i].x * w[i].x + (double)w[i].y * w[i].y) * mul;
+      if (a.power && n < a.n) st_stream(&a.power[(size_t)by * a.n + n], p);
       if (n >= lo && n < hi) acc += p;
     }
     if (a.rowsum) {
@@ -1129,22 +1217,50 @@ template <typename T> struct ScaleAvgArgs {
   double *out;
   long long n;
   int rows;
+  const int *sel;    // rows with a non-zero weight, ascending (device)
+  int nsel;
+  int sel_per_block; // gridDim.y blocks of selected rows; > 1 block: atomics into `out`
 };
 template <typename T> struct ScaleAvgBody {
   using Args = ScaleAvgArgs<T>;
   static constexpr int NPHASE = 1;
   static constexpr size_t SMEM = 0;
-  template <int PH> HD static void phase(const Args &a, int bx, int, int tid, void *) {
+  template <int PH> HD static void phase(const Args &a, int bx, int by, int tid, void *) {
     const long long n = (long long)bx * NT + tid;
     if (n >= a.n) return;
-    double acc = 0.0;
-    for (int j = 0; j < a.rows; ++j) {
-      const double wj = a.w[j];
-      if (wj == 0.0) continue;
-      const cx<T> v = a.W[(size_t)j * a.n + n];
-      acc += wj * ((double)v.x * v.x + (double)v.y * v.y);
+    const int i0 = by * a.sel_per_block;
+    const int i1 = i0 + a.sel_per_block < a.nsel ? i0 + a.sel_per_block : a.nsel;
+    double acc0 = 0, acc1 = 0;
+    int i = i0;
+    for (; i + 4 <= i1; i += 4) {
+      cx<T> v[4];
+      double wj[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = a.sel[i + u];
+        wj[u] = a.w[j];
+        v[u] = ldg(&a.W[(size_t)j * a.n + n]);
+      }
+      acc0 += wj[0] * ((double)v[0].x * v[0].x + (double)v[0].y * v[0].y);
+      acc1 += wj[1] * ((double)v[1].x * v[1].x + (double)v[1].y * v[1].y);
+      acc0 += wj[2] * ((double)v[2].x * v[2].x + (double)v[2].y * v[2].y);
+      acc1 += wj[3] * ((double)v[3].x * v[3].x + (double)v[3].y * v[3].y);
     }
-    a.out[n] = acc;
+    for (; i < i1; ++i) {
+      const int j = a.sel[i];
+      const cx<T> v = ldg(&a.W[(size_t)j * a.n + n]);
+      acc0 += a.w[j] * ((double)v.x * v.x + (double)v.y * v.y);
+    }
+    const double acc = acc0 + acc1;
+    if (a.sel_per_block >= a.nsel) {
+      a.out[n] = acc;
+    } else {
+#if defined(__CUDA_ARCH__) && !defined(CWTB_HOST_EMU)
+      atomicAdd(&a.out[n], acc);
+#else
+      a.out[n] += acc;
+#endif
+    }
   }
 };
 

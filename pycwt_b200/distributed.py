@@ -206,7 +206,7 @@ def surrogate_pair(seed, index, N, al1, al2):
 
 
 def wct_significance_sharded(al1, al2, dt, dj, s0, J, significance_level=0.95, wavelet='morlet',
-                             mc_count=300, seed=0, engine=None, comm=None, device=None):
+                             mc_count=300, seed=0, engine=None, comm=None, device=None, device_rng=False):
     """Monte-Carlo coherence significance (reference wavelet.py:531-647) with the surrogate
     pairs block-partitioned over the ranks: every rank accumulates the [S, 1000]
     int64 histograms of its pairs on its GPU, ONE all-reduce (sum, ~1 MB) combines them and
@@ -217,9 +217,13 @@ def wct_significance_sharded(al1, al2, dt, dj, s0, J, significance_level=0.95, w
     rank, world = _rank_world(comm)
     prob = wv._mc_problem(dt, dj, s0, J, mother)
     lo, hi = shard_range(mc_count, rank, world)
-    hist = wv._mc_histogram(prob, dt, dj, mother,
-                            lambda i: surrogate_pair(seed, i, prob['N'], al1, al2),
-                            range(lo, hi), progress=False, engine=engine)
+    if device_rng:
+        # surrogates drawn on each rank's GPU from the Philox stream keyed by (seed, pair number)
+        hist = wv._mc_histogram_seeded(prob, dt, dj, mother, seed, lo, hi - lo, engine=engine)
+    else:
+        hist = wv._mc_histogram(prob, dt, dj, mother,
+                                lambda i: surrogate_pair(seed, i, prob['N'], al1, al2),
+                                range(lo, hi), progress=False, engine=engine)
     hist = sum_over_ranks(hist, comm, device)
     return wv._mc_levels(prob, hist, significance_level)
 

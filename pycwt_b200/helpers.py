@@ -45,8 +45,14 @@ def ar1(x):
     series = np.asarray(x)
     n = series.size
     dev = series - series.mean()
-    cov0 = np.dot(dev, dev) / n                     # lag-0 covariance
-    cov1 = np.dot(dev[:-1], dev[1:]) / (n - 1)      # lag-1 covariance
+    if n < 4096:
+        cov0 = np.dot(dev, dev) / n                     # lag-0 covariance
+        cov1 = np.dot(dev[:-1], dev[1:]) / (n - 1)      # lag-1 covariance
+    else:
+        # long series: the threaded BLAS dot costs ~30 ms of thread start-up per call on a
+        # many-core host (more than the GPU transform it precedes); a plain pairwise sum does not
+        cov0 = float(np.sum(dev * dev)) / n
+        cov1 = float(np.sum(dev[:-1] * dev[1:])) / (n - 1)
 
     # unbiased estimate: smaller root of  qa*g^2 + qb*g + qc = 0
     qa = cov0 * n ** 2

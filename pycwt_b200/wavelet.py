@@ -419,17 +419,34 @@ def _mc_levels(prob, hist, significance_level):
     return sig95
 
 
+def _mc_histogram_seeded(prob, dt, dj, wavelet, seed, first, count, engine=None):
+    """The same histograms with the surrogates drawn on the device (Philox stream keyed by
+    (seed, pair number)): no host RNG, no noise H2D."""
+    sj, nbins = prob['sj'], prob['nbins']
+    hist = np.zeros((sj.size, nbins), dtype=np.int64)
+    eng = engine or _engine.default_engine()
+    fam = _family_of(wavelet)
+    with eng.lock:
+        _sync_padding(eng, prob['N'])
+        eng.wct_mc_seeded(seed, first, count, prob['N'], dt, sj, fam[0], fam[1], _boxcar_len(wavelet, dj),
+                          prob['mask'], prob['maxscale'], nbins, hist)
+    return hist
+
+
 def wct_significance(al1, al2, dt, dj, s0, J, significance_level=0.95,
                      wavelet='morlet', mc_count=300, progress=True,
-                     cache=True):
+                     cache=True, seed=None):
     """Monte-Carlo significance level of the wavelet coherence per scale (reference
     wavelet.py:531-647).
 
-    Surrogates are drawn on the host with numpy's global RNG in exactly the reference's
-    order (one set-up draw, then noise1, noise2 per iteration), so a seeded run
-    reproduces the reference's numbers; transforms, smoothing, coherence and the
-    1000-bin histograms are accumulated on the GPU.  The on-disk cache keeps the
-    reference's key and format (~/.cache/pycwt/<key>.gz)."""
+    Default (`seed=None`): surrogates are drawn on the host with numpy's global RNG in exactly
+    the reference's order (one set-up draw, then noise1, noise2 per iteration), so a seeded
+    run reproduces the reference's numbers; transforms, smoothing, coherence and the
+    1000-bin histograms are accumulated on the GPU.  With an integer `seed` (an extension of
+    the reference signature) the surrogates are drawn on the device from a counter-based
+    Philox stream: statistically equivalent white noise, no host RNG or upload, about twice
+    as fast; the result then depends on `seed` only, not on numpy's global state.  The
+    on-disk cache keeps the reference's key and format (~/.cache/pycwt/<key>.gz)."""
     wavelet = _check_parameter_wavelet(wavelet)
     if cache:
         aa = np.round(np.arctanh(np.array([al1, al2]) * 4))
@@ -447,12 +464,15 @@ def wct_significance(al1, al2, dt, dj, s0, J, significance_level=0.95,
 
     prob = _mc_problem(dt, dj, s0, J, wavelet)
     N = prob['N']
-    rednoise(N, al1, 1)  # the reference's set-up draw (its transform only yields sj/freq/coi)
+    if seed is None:
+        rednoise(N, al1, 1)  # the reference's set-up draw (its transform only yields sj/freq/coi)
 
-    def draw(i):
-        return rednoise(N, al1, 1), rednoise(N, al2, 1)
+        def draw(i):
+            return rednoise(N, al1, 1), rednoise(N, al2, 1)
 
-    hist = _mc_histogram(prob, dt, dj, wavelet, draw, range(mc_count), progress)
+        hist = _mc_histogram(prob, dt, dj, wavelet, draw, range(mc_count), progress)
+    else:
+        hist = _mc_histogram_seeded(prob, dt, dj, wavelet, seed, 0, mc_count)
     sig95 = _mc_levels(prob, hist, significance_level)
 
     if cache:

@@ -67,9 +67,11 @@ def test_namespace_matches_reference_surface():
         "(signal, dt, dj=0.08333333333333333, s0=-1, J=-1, wavelet='morlet', freqs=None)"
     assert list(inspect.signature(pycwt.wct).parameters)[:10] == \
         ["y1", "y2", "dt", "dj", "s0", "J", "sig", "significance_level", "wavelet", "normalize"]
-    assert list(inspect.signature(pycwt.wct_significance).parameters) == \
-        ["al1", "al2", "dt", "dj", "s0", "J", "significance_level", "wavelet", "mc_count",
-         "progress", "cache"]
+    # the reference's parameters in the reference's order; `seed` (device-side surrogates) is an
+    # optional trailing extension with a default that keeps the reference behaviour
+    params = inspect.signature(pycwt.wct_significance).parameters
+    assert list(params) == ["al1", "al2", "dt", "dj", "s0", "J", "significance_level", "wavelet", "mc_count",
+                            "progress", "cache", "seed"] and params["seed"].default is None
 
 
 @pytest.mark.parametrize("name", ["nino3_morlet_tutorial", "nino3_morlet_default",

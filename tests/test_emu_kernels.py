@@ -314,3 +314,45 @@ def test_python_side_shape_guards(emu):
     with pytest.raises(ValueError):
         emu.smooth(np.ones((4, 100)), 1.0, sj, 5)
     assert emu.get_w(2, 100).shape == (2, 100) and emu.global_power(3).shape == (3,)
+
+
+def check_seeded_monte_carlo(eng):
+    """Seeded (device-RNG) mode of the Monte-Carlo significance: the Philox surrogates are standard
+    normal white noise, a pure function of (seed, pair number); the histograms do not depend on how
+    the pairs are split over calls; the significance levels agree with the host-RNG mode within
+    the Monte-Carlo scatter."""
+    import pycwt_b200 as pycwt
+    from pycwt_b200 import wavelet as wv
+    z = eng.mc_surrogates(7, 3, 2, 20001)                  # pairs 3 and 4, odd length
+    assert z.shape == (2, 2, 20001) and np.isfinite(z).all()
+    flat = z.ravel()
+    assert abs(flat.mean()) < 4 / np.sqrt(flat.size) and abs(flat.std() - 1) < 0.02
+    assert abs(((flat[:-1] * flat[1:]).mean())) < 4 / np.sqrt(flat.size)       # white
+    assert abs((flat ** 4).mean() - 3) < 0.15 and np.abs(flat).max() < 7        # Gaussian tails
+    assert np.array_equal(eng.mc_surrogates(7, 4, 1, 20001)[0], z[1])          # keyed by pair number
+    assert not np.array_equal(eng.mc_surrogates(8, 3, 1, 20001)[0], z[0])      # and by seed
+    assert abs(np.corrcoef(z[0, 0], z[0, 1])[0, 1]) < 0.05                      # the two series differ
+    m = pycwt.Morlet(6)
+    dt, dj, s0, J = 1.0, 0.5, 2.0, 8
+    prob = wv._mc_problem(dt, dj, s0, J, m)
+    h_all = wv._mc_histogram_seeded(prob, dt, dj, m, 11, 0, 6, engine=eng)
+    h_split = (wv._mc_histogram_seeded(prob, dt, dj, m, 11, 0, 2, engine=eng) +
+               wv._mc_histogram_seeded(prob, dt, dj, m, 11, 2, 4, engine=eng))
+    assert np.array_equal(h_all, h_split) and h_all.sum() > 0
+    # against the host-RNG mode (numpy stream): same distribution, different draws
+    rs = np.random.RandomState(3)
+    tau = int(np.ceil(-2 / np.log(0.3)))
+    h_host = wv._mc_histogram(prob, dt, dj, m, lambda i: (rs.randn(prob['N'] + tau)[tau:], rs.randn(prob['N'] + tau)[tau:]),
+                              range(40), engine=eng)
+    h_dev = wv._mc_histogram_seeded(prob, dt, dj, m, 5, 0, 40, engine=eng)
+    a, b = wv._mc_levels(prob, h_host, 0.95), wv._mc_levels(prob, h_dev, 0.95)
+    ok = np.isfinite(a)
+    assert (np.isfinite(b) == ok).all()
+    # the 95 % level of R^2 from 40 pairs: independent runs scatter by ~0.01 at the small scales
+    # (many independent samples per row) and by several 0.01 at the largest ones (few)
+    d = np.abs(a[ok] - b[ok])
+    assert d[:4].max() < 0.03 and d.max() < 0.15, d
+
+
+def test_seeded_monte_carlo(emu):
+    check_seeded_monte_carlo(emu)

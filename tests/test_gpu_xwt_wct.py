@@ -228,3 +228,14 @@ def test_sharded_wct_significance_matches_oracle(pycwt):
     assert np.array_equal(np.isnan(sig), np.isnan(ref))
     ok = ~np.isnan(ref)
     assert np.abs(sig[ok] - ref[ok]).max() < 1e-12
+
+
+def test_seeded_monte_carlo_device_rng(pycwt):
+    """cwtb_wct_mc_seeded on the GPU: the same checks as on the emulation build, plus the public
+    `wct_significance(..., seed=)` entry."""
+    from test_emu_kernels import check_seeded_monte_carlo
+    check_seeded_monte_carlo(pycwt.default_engine())
+    a = pycwt.wct_significance(0.2, 0.4, 1.0, 0.5, 2.0, 8, mc_count=30, progress=False, cache=False, seed=1)
+    b = pycwt.wct_significance(0.2, 0.4, 1.0, 0.5, 2.0, 8, mc_count=30, progress=False, cache=False, seed=1)
+    c = pycwt.wct_significance(0.2, 0.4, 1.0, 0.5, 2.0, 8, mc_count=30, progress=False, cache=False, seed=2)
+    assert np.array_equal(a, b, equal_nan=True) and not np.array_equal(a, c, equal_nan=True)
