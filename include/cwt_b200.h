@@ -239,6 +239,10 @@ int cwtb_bench_last(cwtb_ctx *ctx, int iters, double *ms_out);
  * launch, on a single stream (the normal run overlaps independent kernel chains on three
  * streams); writes "name|launches|total_ms|rows" lines (rows = scale rows processed) to out. */
 int cwtb_profile_last(cwtb_ctx *ctx, char *out, size_t cap);
+/* The same table for ANY sequence of calls (xwt, wct, wct_mc, smooth, batches): every kernel
+ * launched between begin and end is bracketed by an event pair, on one stream. */
+int cwtb_profile_begin(cwtb_ctx *ctx);
+int cwtb_profile_end(cwtb_ctx *ctx, char *out, size_t cap);
 /* Device memory helpers for benchmarks (inputs resident in HBM). */
 int cwtb_dev_alloc(cwtb_ctx *ctx, size_t bytes, void **out);
 int cwtb_dev_free(cwtb_ctx *ctx, void *p);

@@ -46,6 +46,8 @@ _SIGNATURES = {
     "cwtb_last_plan": (_I, [_P, _P, _I]),
     "cwtb_bench_last": (_I, [_P, _I, ctypes.POINTER(_D)]),
     "cwtb_profile_last": (_I, [_P, ctypes.c_char_p, ctypes.c_size_t]),
+    "cwtb_profile_begin": (_I, [_P]),
+    "cwtb_profile_end": (_I, [_P, ctypes.c_char_p, ctypes.c_size_t]),
     "cwtb_dev_alloc": (_I, [_P, ctypes.c_size_t, ctypes.POINTER(_P)]),
     "cwtb_dev_free": (_I, [_P, _P]),
     "cwtb_memcpy_h2d": (_I, [_P, _P, _P, ctypes.c_size_t]),
@@ -389,7 +391,7 @@ class Engine(object):
         with self.lock:
             if W is None:
                 n0 = self._resident_n0
-                out = np.empty(n0, dtype=np.float64)
+                out = self.result_array((n0,), np.float64)     # pinned when large: D2H at PCIe speed
                 self._check(self.lib.cwtb_icwt_sum(self.h, _ptr(out)))
                 return out
             W = np.ascontiguousarray(W, dtype=np.complex128)
@@ -439,7 +441,7 @@ class Engine(object):
         """sum_j weights[j] |W[j, :]|^2 of the resident transform (TC98 eq. 24)."""
         w = np.ascontiguousarray(weights, dtype=np.float64)
         self._expect_resident(w.size)
-        out = np.empty(self._resident_n0, dtype=np.float64)
+        out = self.result_array((self._resident_n0,), np.float64)
         with self.lock:
             self._check(self.lib.cwtb_scale_avg_power(self.h, _ptr(w), _ptr(out)))
         return out
@@ -610,6 +612,27 @@ class Engine(object):
             name, nl, ms, rows = line.rsplit("|", 3)
             out.append({"name": name, "launches": int(nl), "ms": float(ms), "rows": int(rows)})
         return out
+
+    @staticmethod
+    def _parse_profile(text):
+        out = []
+        for line in text.splitlines():
+            name, nl, ms, rows = line.rsplit("|", 3)
+            out.append({"name": name, "launches": int(nl), "ms": float(ms), "rows": int(rows)})
+        return out
+
+    @_locked
+    def profile_begin(self):
+        """Start recording per-kernel device times of every following call (serialised streams)."""
+        self._check(self.lib.cwtb_profile_begin(self.h))
+
+    @_locked
+    def profile_end(self):
+        buf = ctypes.create_string_buffer(1 << 16)
+        n = self.lib.cwtb_profile_end(self.h, buf, len(buf))
+        if n < 0:
+            self._check(n)
+        return self._parse_profile(buf.value.decode())
 
     @_locked
     def sync(self):

@@ -169,6 +169,7 @@ struct cwtb_ctx {
   Buf comm_send, comm_recv;      // device staging of the host-buffer collectives
   int group = 0;   // rows per two-kernel chunk; 0 = as many as fit in group_bytes of Z (CWTB_GROUP)
   size_t group_bytes = (size_t)512 << 20;
+  size_t rows_chunk_bytes = (size_t)64 << 20;   // CWTB_ROWS_CHUNK_MB
   int l2_persist = 0;
   int direct_max_log2 = 13;
   int fused = 0;     // experimental: two-kernel scales through one persistent kernel (CWTB_FUSED=1)
@@ -198,6 +199,7 @@ struct cwtb_ctx {
   std::set<const void *> configured;
   // per-launch event profiling (cwtb_profile_last)
   bool profiling = false;
+  int prof_saved_streams = 1;
   const char *prof_tag = "";     // prefix of the kernel names recorded while profiling: "fwd:" (forward
                                  // transform of the signal), "coarse:" (coarse-grid transforms of the
                                  // expansion path); W-writing launches carry no tag
@@ -716,7 +718,9 @@ static int two_kernel_rows(cwtb_ctx *c, const void *in, int real_in, long long i
   NTab nt;
   int e = get_ntab(c, n, l2, &nt);
   if (e) return e;
-  const int chunk = std::max(1, std::min(nrows, (int)std::max<size_t>(1, ((size_t)64 << 20) / ((size_t)n * sizeof(cx<T>)))));
+  // rows per chunk: the intermediate of a chunk (rows_chunk_bytes, default 64 MiB) stays in L2
+  // between the two kernels
+  const int chunk = std::max(1, std::min(nrows, (int)std::max<size_t>(1, c->rows_chunk_bytes / ((size_t)n * sizeof(cx<T>)))));
   Buf &Zt = c->ztmp ? *c->ztmp : c->Z;
   if ((e = ensure(c, Zt, (size_t)chunk * n * sizeof(cx<T>)))) return e;
   for (int r0 = 0; r0 < nrows; r0 += chunk) {
@@ -1651,6 +1655,7 @@ int cwtb_create(int device, cwtb_ctx **out) {
   c->cur = c->stream;
   if (const char *g = getenv("CWTB_GROUP")) c->group = std::max(0, atoi(g));
   if (const char *g = getenv("CWTB_GROUP_MB")) c->group_bytes = (size_t)std::max(1, atoi(g)) << 20;
+  if (const char *g = getenv("CWTB_ROWS_CHUNK_MB")) c->rows_chunk_bytes = (size_t)std::max(1, atoi(g)) << 20;
   if (const char *g = getenv("CWTB_BAND_EPS")) c->band_eps = atof(g);
   if (const char *g = getenv("CWTB_BAND_EPS32")) c->band_eps32 = atof(g);
   if (const char *g = getenv("CWTB_EXPAND_EPS")) c->expand_eps = std::max(0.0, atof(g));
@@ -2076,7 +2081,12 @@ static int wct_core(cwtb_ctx *c, const Job &job, const double *dsig1, const doub
   if ((e = smooth_time(c, (double2 *)c->A12.p, S, n0, job.N, d_g))) return e;
   WctFinalArgs fa{(const double2 *)c->C.p, (const double2 *)c->A12.p, (const double *)c->win.p, dWCT,
                   dmask, dhist, n0, S, K, maxscale, nbins};
-  return launch<WctFinalBody>(c, gx, S, fa);
+  if (K > 64) return fail(c, CWTB_ERR_UNSUPPORTED, "scale boxcar longer than 64 taps");
+  const int rows_out = dWCT ? S : maxscale;
+  if (rows_out <= 0) return 0;
+  using F16 = WctFinalBody<16>;
+  const unsigned fx = (unsigned)((n0 + F16::CW - 1) / F16::CW), fy = (unsigned)((rows_out + F16::RS - 1) / F16::RS);
+  return K <= 16 ? launch<F16>(c, fx, fy, fa) : launch<WctFinalBody<64>>(c, fx, fy, fa);
 }
 
 static int upload_row_tables(cwtb_ctx *c, const Job &job) {
@@ -2470,20 +2480,12 @@ int cwtb_mc_surrogates(cwtb_ctx *c, uint64_t seed, int64_t first_pair, int n_pai
 // One pass of the last cwtb_cwt_dev transform with a CUDA event pair around every launch.
 // Writes one line per kernel type: "name,launches,total_ms,rows" (rows = sum of gridDim.y, i.e.
 // scale rows processed) into `out`.  Returns the number of bytes written (<= cap-1) or < 0.
-int cwtb_profile_last(cwtb_ctx *c, char *out, size_t cap) {
-  if (!c || !c->job.valid || !c->job_dsig || !out || cap < 2) return fail(c, CWTB_ERR_STATE, "no transform to profile");
+static int profile_report(cwtb_ctx *c, char *out, size_t cap) {
 #ifdef CWTB_HOST_EMU
-  out[0] = 0;
+  (void)c;
+  if (cap) out[0] = 0;
   return 0;
 #else
-  c->prof.clear();
-  c->profiling = true;
-  const int ts = c->two_streams;
-  c->two_streams = 0;   // kernels one after the other: per-kernel times are not blurred by overlap
-  int e = timed_run(c, c->job_dsig, 1, nullptr);
-  c->two_streams = ts;
-  c->profiling = false;
-  if (e) return e;
   RT(rt_sync(c->stream));
   std::map<std::string, std::array<double, 3>> agg;
   std::vector<std::string> order;
@@ -2506,6 +2508,42 @@ int cwtb_profile_last(cwtb_ctx *c, char *out, size_t cap) {
   out[m] = 0;
   return (int)m;
 #endif
+}
+
+int cwtb_profile_last(cwtb_ctx *c, char *out, size_t cap) {
+  if (!c || !c->job.valid || !c->job_dsig || !out || cap < 2) return fail(c, CWTB_ERR_STATE, "no transform to profile");
+#ifdef CWTB_HOST_EMU
+  out[0] = 0;
+  return 0;
+#else
+  c->prof.clear();
+  c->profiling = true;
+  const int ts = c->two_streams;
+  c->two_streams = 0;   // kernels one after the other: per-kernel times are not blurred by overlap
+  int e = timed_run(c, c->job_dsig, 1, nullptr);
+  c->two_streams = ts;
+  c->profiling = false;
+  if (e) return e;
+  return profile_report(c, out, cap);
+#endif
+}
+
+// Profile ANY sequence of calls (xwt, wct, wct_mc, smooth ...): between begin and end every kernel
+// launch is bracketed by an event pair and the independent chains run on one stream.
+int cwtb_profile_begin(cwtb_ctx *c) {
+  if (!c) return CWTB_ERR_ARG;
+  c->prof.clear();
+  c->profiling = true;
+  c->prof_saved_streams = c->two_streams;
+  c->two_streams = 0;
+  return 0;
+}
+int cwtb_profile_end(cwtb_ctx *c, char *out, size_t cap) {
+  if (!c || !out || cap < 2) return CWTB_ERR_ARG;
+  if (!c->profiling) return fail(c, CWTB_ERR_STATE, "profile_end without profile_begin");
+  c->profiling = false;
+  c->two_streams = c->prof_saved_streams;
+  return profile_report(c, out, cap);
 }
 
 // Batched transform of independent channels: chunks of channels share every kernel launch

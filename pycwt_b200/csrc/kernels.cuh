@@ -1137,27 +1137,78 @@ struct WctFinalArgs {
   long long n;
   int rows, K, maxscale, nbins;
 };
-struct WctFinalBody {
+// Tile: RS = 32 output rows x CW = 32 columns.  Phase 0 stages the RS + K - 1 input rows of both
+// time-smoothed fields for these columns in shared memory (each input element is read from global
+// memory (RS + K - 1) / RS times instead of K times); in phase 1 a thread produces 4 consecutive
+// rows of one column, so every staged value feeds up to four accumulators.
+template <int KMAX_> struct WctFinalBody {
   using Args = WctFinalArgs;
-  static constexpr int NPHASE = 1;
-  static constexpr size_t SMEM = 0;
-  template <int PH> HD static void phase(const Args &a, int bx, int by, int tid, void *) {
-    const long long n = (long long)bx * NT + tid;
-    if (n >= a.n) return;
-    if (!a.WCT && by >= a.maxscale) return;
-    const double2 c = boxcar_at(a.C, a.win, a.K, a.rows, a.n, by, n);
-    const double2 x = boxcar_at(a.A12, a.win, a.K, a.rows, a.n, by, n);
-    const double r2 = (x.x * x.x + x.y * x.y) / (c.x * c.y);
-    const size_t i = (size_t)by * a.n + n;
-    if (a.WCT) a.WCT[i] = r2;
-    if (a.hist && by < a.maxscale && a.mask[i] && r2 == r2) {
-      int bin = (int)floor(r2 * a.nbins);
-      bin = bin < 0 ? 0 : (bin >= a.nbins ? a.nbins - 1 : bin);
+  static constexpr int NPHASE = 2;
+  static constexpr int RS = 32, CW = 32, KMAX = KMAX_, RG = 4;   // KMAX sizes the shared memory
+  static constexpr size_t SMEM = (size_t)2 * (RS + KMAX - 1) * CW * sizeof(double2) + KMAX * sizeof(double);
+  template <int PH> HD static void phase(const Args &a, int bx, int by, int tid, void *smraw) {
+    const int K = a.K, off = (K - 1) / 2;
+    const int nrow = RS + K - 1;
+    double2 *sc = (double2 *)smraw;                   // [nrow][CW] of C
+    double2 *sx = sc + (size_t)(RS + KMAX - 1) * CW;  // [nrow][CW] of A12
+    double *sw = (double *)(sx + (size_t)(RS + KMAX - 1) * CW);
+    const int i0 = by * RS;
+    const long long n0 = (long long)bx * CW;
+    const int rows_out = a.WCT ? a.rows : a.maxscale;  // Monte-Carlo mode: rows below maxscale only
+    if (i0 >= rows_out) return;
+    const int qlo = i0 + off - K + 1;
+    if constexpr (PH == 0) {
+      for (int idx = tid; idx < nrow * CW; idx += NT) {
+        const int r = idx / CW, col = idx % CW;
+        const int q = qlo + r;
+        const long long n = n0 + col;
+        double2 c = make_double2(0.0, 0.0), x = c;
+        if (q >= 0 && q < a.rows && n < a.n) {
+          c = a.C[(size_t)q * a.n + n];
+          x = a.A12[(size_t)q * a.n + n];
+        }
+        sc[idx] = c;
+        sx[idx] = x;
+      }
+      for (int t = tid; t < K; t += NT) sw[t] = a.win[t];
+    } else {
+      for (int task = tid; task < (RS / RG) * CW; task += NT) {
+        const int col = task % CW, g = task / CW;
+        const long long n = n0 + col;
+        if (n >= a.n) continue;
+        double cr[RG] = {0, 0, 0, 0}, ci[RG] = {0, 0, 0, 0}, xr[RG] = {0, 0, 0, 0}, xi[RG] = {0, 0, 0, 0};
+        // staged row u feeds output row i0 + RG g + e with tap t = e + K - 1 - (u - RG g)
+        for (int du = 0; du < K + RG - 1; ++du) {
+          const int u = RG * g + du;
+          const double2 c = sc[u * CW + col], x = sx[u * CW + col];
+#pragma unroll
+          for (int e = 0; e < RG; ++e) {
+            const int t = e + K - 1 - du;
+            if (t >= 0 && t < K) {
+              const double w = sw[t];
+              cr[e] += w * c.x; ci[e] += w * c.y;
+              xr[e] += w * x.x; xi[e] += w * x.y;
+            }
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < RG; ++e) {
+          const int i = i0 + RG * g + e;
+          if (i >= rows_out) break;
+          const double r2 = (xr[e] * xr[e] + xi[e] * xi[e]) / (cr[e] * ci[e]);
+          const size_t o = (size_t)i * a.n + n;
+          if (a.WCT) a.WCT[o] = r2;
+          if (a.hist && i < a.maxscale && a.mask[o] && r2 == r2) {
+            int bin = (int)floor(r2 * a.nbins);
+            bin = bin < 0 ? 0 : (bin >= a.nbins ? a.nbins - 1 : bin);
 #if defined(__CUDA_ARCH__) && !defined(CWTB_HOST_EMU)
-      atomicAdd(&a.hist[(size_t)by * a.nbins + bin], 1ull);
+            atomicAdd(&a.hist[(size_t)i * a.nbins + bin], 1ull);
 #else
-      a.hist[(size_t)by * a.nbins + bin] += 1ull;
+            a.hist[(size_t)i * a.nbins + bin] += 1ull;
 #endif
+          }
+        }
+      }
     }
   }
 };
