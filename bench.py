@@ -579,7 +579,9 @@ def run_config5(args, D, eng, pycwt, _engine, comm=None):
                 "roofline": roofline_block(prof, c["n"] * 8, pts_chunk * 8 + chunk * c["n"] * 4, ms)})
     # end to end: host float32 channels in, per-channel spectra out, gathered over the ranks
     from pycwt_b200 import distributed as Dm
-    Dm.cwt_batch_sharded(X[:64], c["dt"], sj, _engine.MORLET, c["f0"], _engine.F32, eng)     # warm-up
+    # warm-up: engine buffers and the communicator's first collective (NCCL connects lazily)
+    p0, _ = eng.cwt_batch(X[:64], c["dt"], sj, _engine.MORLET, c["f0"], _engine.F32, want_power=True)
+    Dm.gather_rows(p0, 64 * D.world, comm)
     D.barrier()
     t0 = time.perf_counter()
     power, _ = eng.cwt_batch(X, c["dt"], sj, _engine.MORLET, c["f0"], _engine.F32, want_power=True)
@@ -610,14 +612,16 @@ def run_config2_scale_sharded(args, D, eng, pycwt, _engine, comm):
     c = wl.C2
     sj = wl.config2_scales()
     x = wl.config2_signal(0)
-    lo, hi = Dm.shard_range(len(sj), D.rank, D.world)
+    rows = Dm.scale_rows(len(sj), D.rank, D.world)      # cyclic: balances small (costly) and large scales
     dsig = eng.dev_alloc(x.nbytes)
     eng.h2d(dsig, x)
-    eng.cwt_dev(dsig, 0, c["n"], c["dt"], sj[lo:hi], _engine.MORLET, c["f0"], _engine.F64)
+    eng.cwt_dev(dsig, 0, c["n"], c["dt"], sj[rows], _engine.MORLET, c["f0"], _engine.F64)
     eng.bench_last(3)
     D.barrier()
     ms = D.max(eng.bench_last(10))
     eng.dev_free(dsig)
+    Dm.cwt_scale_sharded(x, c["dt"], sj, _engine.MORLET, c["f0"], _engine.F64, eng, comm)   # warm-up
+    D.barrier()
     t0 = time.perf_counter()
     Dm.cwt_scale_sharded(x, c["dt"], sj, _engine.MORLET, c["f0"], _engine.F64, eng, comm)
     t_e2e = D.max(time.perf_counter() - t0)

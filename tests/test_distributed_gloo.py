@@ -86,8 +86,9 @@ def _mc_worker(rank, world, port, q):
         # one signal, scales sharded over the ranks; the global spectrum is gathered
         x = np.random.RandomState(5).randn(3000)
         sj = 2.0 * 2 ** (np.arange(13) / 2.0)
-        lo, hi, power, W = D.cwt_scale_sharded(x, 1.0, sj, 0, 6.0, 0, eng, D.TorchComm(dist), fetch=True)
-        q.put((rank, sig.tolist(), (lo, hi), power.tolist(), np.abs(W).sum()))
+        rows, power, W = D.cwt_scale_sharded(x, 1.0, sj, 0, 6.0, 0, eng, D.TorchComm(dist), fetch=True)
+        rb, pb, _ = D.cwt_scale_sharded(x, 1.0, sj, 0, 6.0, 0, eng, D.TorchComm(dist), layout='block')
+        q.put((rank, sig.tolist(), rows.tolist(), power.tolist(), np.abs(W).sum(), rb.tolist(), pb.tolist()))
         eng.close()
     finally:
         dist.destroy_process_group()
@@ -122,16 +123,17 @@ def test_sharded_wct_significance_gloo():
     res = {g[0]: g for g in got}
     for r in (0, 1):
         assert np.array_equal(np.array(res[r][1]), single, equal_nan=True)
-    # scale-sharded single signal: slabs [0,7) and [7,13), identical gathered spectrum that
-    # matches the oracle
+    # scale-sharded single signal: cyclic rows 0,2,4.. / 1,3,5.. (block: [0,7) / [7,13)), identical
+    # gathered spectrum that matches the oracle
     from oracle import cwt_oracle as orc
     x = np.random.RandomState(5).randn(3000)
     sj = 2.0 * 2 ** (np.arange(13) / 2.0)
     Wr = orc.cwt(x, 1.0, wavelet=orc.Morlet(6), freqs=1 / (orc.Morlet(6).flambda() * sj))[0]
     ref = (np.abs(Wr) ** 2).mean(axis=1)
-    assert res[0][2] == (0, 7) and res[1][2] == (7, 13)
+    assert res[0][2] == list(range(0, 13, 2)) and res[1][2] == list(range(1, 13, 2))
+    assert res[0][5] == list(range(0, 7)) and res[1][5] == list(range(7, 13))
     for r in (0, 1):
-        assert np.allclose(res[r][3], ref, rtol=1e-12)
+        assert np.allclose(res[r][3], ref, rtol=1e-12) and np.allclose(res[r][6], ref, rtol=1e-12)
     assert abs(res[0][4] + res[1][4] - np.abs(Wr).sum()) < 1e-9 * np.abs(Wr).sum()
 
 

@@ -249,3 +249,82 @@ def test_coherence_api_random(api):
     finally:
         helpers.set_fft_padding(True)
         orc.PAD_NEXT_POW2 = True
+
+
+def test_concurrent_cwt_calls_on_the_default_engine(api):
+    """Several Python threads transform signals of different lengths on the SHARED engine: every
+    result is the one of its own call (the engine lock spans policy, transform, fetch and spectrum;
+    without it the resident job of one call was replaced under another's fetch)."""
+    import threading
+    rs = np.random.RandomState(11)
+    sigs = [rs.randn(n) for n in (4096, 300, 20000, 1000)]
+    want = [orc.cwt(x, 1.0, dj=0.5, wavelet=orc.Morlet(6)) for x in sigs]
+    errs = []
+
+    def work(i):
+        try:
+            for _ in range(6):
+                g = api.cwt(sigs[i], 1.0, dj=0.5, wavelet=api.Morlet(6))
+                assert g[0].shape == want[i][0].shape
+                assert rel(g[0], want[i][0]) < 1e-10 and rel(g[4], want[i][4]) < 1e-12
+        except Exception as exc:      # surfaced in the main thread
+            errs.append((i, repr(exc)))
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(sigs))]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errs, errs
+
+
+def test_complex_signal_and_unusable_frequencies(api):
+    """A complex signal goes through the reference's FFT unchanged (linearity): W(re) + i W(im);
+    custom frequencies of 0 (s = inf) or < 0 (NaN norm) give all-NaN rows, which the reference
+    drops from W, sj and freqs (wavelet.py:111-115)."""
+    rs = np.random.RandomState(4)
+    z = rs.randn(300) + 1j * rs.randn(300)
+    for mo, mr in ((api.Morlet(6), orc.Morlet(6)), (api.DOG(3), orc.DOG(3))):
+        r = orc.cwt(z, 0.5, dj=0.5, wavelet=mr)
+        g = api.cwt(z, 0.5, dj=0.5, wavelet=mo)
+        assert g[0].shape == r[0].shape and rel(g[0], r[0]) < 1e-10 and rel(g[4], r[4]) < 1e-12
+    x = rs.randn(500)
+    for fr in ([0.5, 0.1, 0.0, 0.01], [0.5, 0.1, -0.05, 0.01]):
+        fr = np.array(fr)
+        for mo, mr in ((api.Morlet(6), orc.Morlet(6)), (api.Paul(4), orc.Paul(4)), (api.DOG(2), orc.DOG(2))):
+            with np.errstate(all="ignore"), warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                r = orc.cwt(x, 1.0, wavelet=mr, freqs=fr)
+                g = api.cwt(x, 1.0, wavelet=mo, freqs=fr)
+            assert r[0].shape == (3, 500) and g[0].shape == (3, 500)
+            assert np.array_equal(r[1], g[1]) and np.array_equal(r[2], g[2])
+            assert rel(g[0], r[0]) < 1e-10
+
+
+def test_resident_rejects_wavelets_the_engine_cannot_evaluate(api):
+    class MyMorlet(api.Morlet):
+        def psi_ft(self, f):
+            return super().psi_ft(f) * 1.0
+
+    x = np.random.RandomState(1).randn(256)
+    for w in (MyMorlet(6), api.DOG(2.5)):
+        with pytest.raises(TypeError, match="analytic families"):
+            api.cwt_resident(x, 1.0, wavelet=w)
+    # the plain call still works for them (host-evaluated response table)
+    g = api.cwt(x, 1.0, dj=0.5, wavelet=MyMorlet(6))
+    r = orc.cwt(x, 1.0, dj=0.5, wavelet=orc.Morlet(6))
+    assert rel(g[0], r[0]) < 1e-10
+
+
+def test_pinned_pool_is_bounded_and_trimmable(api):
+    from pycwt_b200 import _engine
+    eng = _engine.default_engine()
+    old = eng.POOL_MAX_BYTES
+    eng.POOL_MAX_BYTES = 3 << 20
+    try:
+        arrs = [eng.result_array((1 << 17,), np.complex128) for _ in range(4)]     # 2 MiB each, pinned
+        assert eng._outstanding >= 4
+        del arrs
+        assert eng._pool_bytes <= eng.POOL_MAX_BYTES      # least recently released ones were retired
+        eng.trim()
+        assert eng._pool_bytes == 0 and not eng._pool and not eng._dead
+    finally:
+        eng.POOL_MAX_BYTES = old
