@@ -79,6 +79,14 @@ int cwtb_set_expand_eps(cwtb_ctx *ctx, double eps_fp64, double eps_fp32);
  * the smoothing filter of wct / smooth / wct_mc then is circular at the rows' own length, as in
  * the reference.  Power-of-two lengths are unaffected. */
 int cwtb_set_padding(cwtb_ctx *ctx, int pad_to_pow2);
+/* Time-smoothing filter of cwtb_smooth / cwtb_wct / cwtb_wct_mc.  Default (table == NULL): the
+ * Gaussian exp(-0.5 (s/dt)^2 k^2) of Morlet.smooth (pycwt/mothers.py:83-91).  With a table
+ * [n_rows][n] of real frequency responses (n = the transform length of the rows: next power of
+ * two, or the rows' own length in un-padded mode) the following calls multiply the transforms of
+ * their rows by it instead -- the smoothing operator of wavelets the reference has none for
+ * (Paul, DOG: SURVEY 8f rank 4; pycwt_b200.mothers.enable_generic_smoothing).  The table stays in
+ * force until replaced or cleared; calls whose rows / length differ fail with CWTB_ERR_STATE. */
+int cwtb_set_smooth_filter(cwtb_ctx *ctx, const double *table, int n_rows, int64_t n);
 
 /* Pinned host memory (so D2H of multi-GiB results runs at PCIe speed and can
  * overlap with compute).  numpy wraps the returned pointer. */

@@ -408,3 +408,33 @@ def percentile_from_hist(hist, sig95, maxscale, level):
         P = (P - 0.5) / P[-1]
         sig95[s] = np.interp(level, P, centres[sel])
     return sig95
+
+
+# --------------------------------------------------------------------------
+# Smoothing operator for wavelets the reference has none for.
+# NOT a restatement of reference code (mothers.py:107-222 define no `smooth`): an independent
+# NumPy statement of the general definition (Torrence & Webster 1999; TC98 sec. 6) that the
+# package offers behind `mothers.enable_generic_smoothing()`, so that the GPU path has a checker.
+# --------------------------------------------------------------------------
+def smooth_generic(W, dt, dj, scales, mother):
+    """Time: circular convolution (length = transform_length(n)) with |psi0(t/s)| normalised to unit
+    sum; scale: the boxcar of `smooth` with width 2*deltaj0/dj (same alignment as mothers.py:100-102)."""
+    from scipy.signal import convolve2d
+    m, n = W.shape
+    npad = transform_length(n)
+    idx = np.arange(npad)
+    t = dt * np.where(idx <= npad // 2, idx, idx - npad)
+    T = np.zeros((m, n), dtype=complex)
+    for j in range(m):
+        k = np.abs(mother.psi(t / scales[j]))
+        k = k / k.sum()
+        x = np.zeros(npad, dtype=complex)
+        x[:n] = W[j]
+        # direct O(n^2) would be the purest statement; the FFT of the SAME sampled kernel is exact
+        # to rounding and keeps the test fast
+        T[j] = _sfft.ifft(_sfft.fft(x) * _sfft.fft(k))[:n]
+    if np.isreal(W).all():
+        T = T.real
+    wsize = int(np.round(mother.deltaj0 / dj * 2))
+    win = rect(wsize, normalize=True)
+    return convolve2d(T, win[:, np.newaxis], "same")

@@ -7,7 +7,9 @@ NCU="ncu --set full --clock-control none --import-source on --kernel-name-base d
 cap() { name=$1; shift; timeout 300 $NCU "$@" -o /tmp/prof/$name python bench.py --kernels-only --steps 1 --warmup 0 > /dev/null 2>&1; python profiles/ncu_summary.py /tmp/prof/$name.ncu-rep > gpurun_out/ncu_r2_$name.txt 2>&1; }
 cap expand12 -k 'regex:ExpandBody.*12' -s 1 -c 1
 cap expand14 -k 'regex:ExpandBody.*14' -s 1 -c 1
-cap passB1024 -k 'regex:PassBBody.*int.1.*int.1024' -s 20 -c 1
+# the W-writing launches of the second kernel: captured in exact mode (expansion off), where every
+# launch of this kernel type writes W (with the expansion on, the coarse transforms share the name)
+CWTB_EXPAND_EPS=0 cap passB1024 -k 'regex:PassBBody.*int.1.*int.1024' -s 1 -c 1
 cap passA_dense -k 'regex:PassABody.*int.1024.*int.0.*int.1' -s 1 -c 1
 cap passA_band512 -k 'regex:PassABody.*int.512.*int.1.*int.1' -s 1 -c 1
 python profiles/ncu_traffic.py /tmp/prof/expand12.ncu-rep /tmp/prof/expand14.ncu-rep /tmp/prof/passB1024.ncu-rep > /dev/null 2>&1; cp profiles/traffic.json gpurun_out/traffic.json

@@ -32,6 +32,7 @@ _SIGNATURES = {
     "cwtb_set_band_eps": (_I, [_P, _D]),
     "cwtb_set_expand_eps": (_I, [_P, _D, _D]),
     "cwtb_set_padding": (_I, [_P, _I]),
+    "cwtb_set_smooth_filter": (_I, [_P, _P, _I, _I64]),
     "cwtb_host_alloc": (_I, [_P, ctypes.c_size_t, ctypes.POINTER(_P)]),
     "cwtb_host_free": (_I, [_P, _P]),
     "cwtb_cwt": (_I, [_P, _P, _I, _I64, _D, _P, _I, _I, _D, _I, _P]),
@@ -206,6 +207,16 @@ class Engine(object):
         """Tolerance of the band-limited expansion path (include/cwt_b200.h); 0 switches it off
         (every scale through the exact pruned transforms)."""
         self._check(self.lib.cwtb_set_expand_eps(self.h, float(eps64), float(eps32)))
+
+    @_locked
+    def set_smooth_filter(self, table=None):
+        """Real frequency responses [rows, n] of the time smoothing used by smooth / wct / wct_mc
+        instead of Morlet's Gaussian; None restores the Gaussian."""
+        if table is None:
+            self._check(self.lib.cwtb_set_smooth_filter(self.h, None, 0, 0))
+            return
+        t = np.ascontiguousarray(table, dtype=np.float64)
+        self._check(self.lib.cwtb_set_smooth_filter(self.h, _ptr(t), t.shape[0], t.shape[1]))
 
     @_locked
     def set_padding(self, pad_to_pow2):

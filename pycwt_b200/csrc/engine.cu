@@ -187,6 +187,9 @@ struct cwtb_ctx {
   double2 *tw64 = nullptr;
   float2 *tw32 = nullptr;
   std::map<unsigned, NTabDev> ntabs;
+  Buf filt;                      // caller-supplied time-smoothing responses [S][N] (cwtb_set_smooth_filter)
+  int filt_rows = 0;
+  long long filt_n = 0;
   Buf Zx, Cin, Cout, wtab;       // expansion path: its own transform intermediate, coarse spectra /
                                  // samples, interpolation weight tables
   std::map<std::array<long long, 3>, long long> wtab_index;   // (log2R, taps, round(beta*1e6)) -> offset
@@ -488,6 +491,13 @@ static int build_job(cwtb_ctx *c, Job &job, long long n0, double dt, const doubl
     return fail(c, CWTB_ERR_ARG, "Paul/DOG order must be an integer in [1, 64]");
   if (n0 > (1ll << 28)) return fail(c, CWTB_ERR_UNSUPPORTED, "signal longer than 2^28");
   job = Job();
+  // expansion weight tables are cached across calls; start over if many transform geometries
+  // have piled up more than 256 MiB of them (offsets are per job, assigned below)
+  if (c->wtab_host.size() > ((size_t)32 << 20)) {
+    c->wtab_host.clear();
+    c->wtab_index.clear();
+    c->wtab_uploaded = 0;
+  }
   job.precision = precision;
   job.n0 = n0;
   job.log2N = ilog2((unsigned long long)n0);   // pycwt/helpers.py:27-30
@@ -1694,7 +1704,7 @@ void cwtb_destroy(cwtb_ctx *c) {
   cudaStreamSynchronize(c->stream);
 #endif
   cwtb_comm_destroy(c);
-  for (Buf *b : {&c->comm_send, &c->comm_recv, &c->Zx, &c->Cin, &c->Cout, &c->wtab, &c->ctr, &c->sig, &c->sig2, &c->spec, &c->Z, &c->Zc[0], &c->Zc[1], &c->Zc[2], &c->Y, &c->B, &c->W, &c->W2, &c->descs, &c->table, &c->scratch,
+  for (Buf *b : {&c->filt, &c->comm_send, &c->comm_recv, &c->Zx, &c->Cin, &c->Cout, &c->wtab, &c->ctr, &c->sig, &c->sig2, &c->spec, &c->Z, &c->Zc[0], &c->Zc[1], &c->Zc[2], &c->Y, &c->B, &c->W, &c->W2, &c->descs, &c->table, &c->scratch,
                  &c->C, &c->A12, &c->F, &c->aux, &c->rowd, &c->win, &c->mask, &c->hist, &c->noise, &c->wide, &c->blueA, &c->blueX, &c->blueY})
     if (b->p) rt_free(b->p);
   for (auto &kv : c->ntabs) { rt_free(kv.second.hi); rt_free(kv.second.lo); }
@@ -2047,14 +2057,28 @@ static int smooth_time(cwtb_ctx *c, double2 *X, int S, long long n0, unsigned N,
   if (e) return e;
   double2 *F = (double2 *)c->F.p;
   if (N < 2) return 0;  // single sample: filter is exp(0) = 1
+  const bool table = c->filt_rows > 0;     // caller-supplied responses instead of Morlet's Gaussian
+  if (table && (c->filt_rows != S || c->filt_n != (long long)N))
+    return fail(c, CWTB_ERR_STATE, "smoothing filter table does not match the rows / transform length of this call");
   if ((N & (N - 1)) != 0) {
     // un-padded mode: circular filter at the rows' own length (N == n0), Bluestein transforms
     if ((e = blue_rows(c, X, 0, n0, F, N, N, S, -1, 1.0, N))) return e;
-    BlueGaussArgs ga{F, d_g, (long long)N, N, 1.0 / (double)N};
-    if ((e = launch<BlueGaussBody>(c, (N + NT - 1) / NT, S, ga))) return e;
+    if (table) {
+      FilterMulArgs fa{F, (const double *)c->filt.p, (long long)N, N, 1.0 / (double)N};
+      if ((e = launch<FilterMulBody>(c, (N + NT - 1) / NT, S, fa))) return e;
+    } else {
+      BlueGaussArgs ga{F, d_g, (long long)N, N, 1.0 / (double)N};
+      if ((e = launch<BlueGaussBody>(c, (N + NT - 1) / NT, S, ga))) return e;
+    }
     return blue_rows(c, F, 0, N, X, n0, N, S, +1, 1.0, n0);
   }
-  if ((e = fft_rows<double, -1>(c, X, 0, n0, n0, F, N, N, S, N, d_g, 1.0 / (double)N))) return e;
+  if (table) {
+    if ((e = fft_rows<double, -1>(c, X, 0, n0, n0, F, N, N, S, N))) return e;
+    FilterMulArgs fa{F, (const double *)c->filt.p, (long long)N, N, 1.0 / (double)N};
+    if ((e = launch<FilterMulBody>(c, (N + NT - 1) / NT, S, fa))) return e;
+  } else if ((e = fft_rows<double, -1>(c, X, 0, n0, n0, F, N, N, S, N, d_g, 1.0 / (double)N))) {
+    return e;
+  }
   return fft_rows<double, +1>(c, F, 0, N, N, X, n0, N, S, n0);
 }
 
@@ -2351,6 +2375,26 @@ int cwtb_wct(cwtb_ctx *c, const double *y1, const double *y2, int64_t n0, double
   if (WCT_out) RT(rt_d2h(WCT_out, dW, cnt * sizeof(double), c->stream));
   if (aWCT_out) RT(rt_d2h(aWCT_out, dA, cnt * sizeof(double), c->stream));
   RT(rt_sync(c->stream));
+  return 0;
+}
+
+int cwtb_set_smooth_filter(cwtb_ctx *c, const double *table, int n_rows, int64_t n) {
+  if (!c) return CWTB_ERR_ARG;
+  if (!table || n_rows <= 0 || n <= 0) {   // back to Morlet's Gaussian (mothers.py:83-91)
+    c->filt_rows = 0;
+    c->filt_n = 0;
+    return 0;
+  }
+#ifndef CWTB_HOST_EMU
+  RT(cudaSetDevice(c->device));
+#endif
+  const size_t bytes = (size_t)n_rows * (size_t)n * sizeof(double);
+  int e = ensure(c, c->filt, bytes);
+  if (e) return e;
+  RT(rt_h2d(c->filt.p, table, bytes, c->stream));
+  RT(rt_sync(c->stream));
+  c->filt_rows = n_rows;
+  c->filt_n = n;
   return 0;
 }
 

@@ -1455,6 +1455,22 @@ struct BlueMulBody {
   }
 };
 
+// F[r][k] *= filt[r][k] * post: a caller-supplied real frequency response per row (time smoothing
+// with a filter other than Morlet's Gaussian: cwtb_set_smooth_filter)
+struct FilterMulArgs { double2 *f; const double *filt; long long pitch; unsigned n; double post; };
+struct FilterMulBody {
+  using Args = FilterMulArgs;
+  static constexpr int NPHASE = 1;
+  static constexpr size_t SMEM = 0;
+  template <int PH> HD static void phase(const Args &a, int bx, int by, int tid, void *) {
+    const unsigned k = (unsigned)bx * NT + tid;
+    if (k >= a.n) return;
+    const double m = a.filt[(size_t)by * a.n + k] * a.post;
+    double2 *p = a.f + (size_t)by * a.pitch + k;
+    p->x *= m; p->y *= m;
+  }
+};
+
 // out[row][k] = epilogue(y[r][k] * w_s[k] * scale)
 struct BluePostArgs {
   const double2 *y; double2 *out; const double2 *wm; const ScaleDesc *descs;   // descs may be null

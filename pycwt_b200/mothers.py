@@ -8,12 +8,52 @@ from scipy.special import gamma as _gamma
 from . import _engine
 
 
+#: Opt-in: a smoothing operator for Paul and DOG.  The reference defines
+#: `smooth` for Morlet only (mothers.py:61-104; `wct` with Paul/DOG raises AttributeError there,
+#: and here while this is off).  When on, Paul/DOG objects expose `smooth` with the general
+#: definition of Torrence & Webster (1999) / TC98 sec. 6 that Morlet's Gaussian is the special
+#: case of: in time a filter given by the absolute value of the wavelet function at each scale,
+#: normalised to unit weight; in scale a boxcar of width deltaj0 (TC98 table 2).
+_GENERIC_SMOOTHING = False
+
+
+def enable_generic_smoothing(on=True):
+    """Give Paul and DOG a `smooth` method (see `_GENERIC_SMOOTHING`); returns the old setting."""
+    global _GENERIC_SMOOTHING
+    old, _GENERIC_SMOOTHING = _GENERIC_SMOOTHING, bool(on)
+    return old
+
+
+def time_filter_table(wavelet, scales, dt, npad):
+    """Real frequency responses [S, npad] of the time smoothing |psi0(t/s)| / sum: the DFT of the
+    wavelet modulus sampled on the circular grid of `npad` points (for Morlet this is the sampled
+    counterpart of the Gaussian exp(-0.5 (s/dt)^2 k^2) of mothers.py:83-91)."""
+    n = np.arange(npad)
+    t = dt * np.where(n <= npad // 2, n, n - npad)
+    out = np.empty((len(scales), npad))
+    for j, s in enumerate(np.asarray(scales, dtype=float)):
+        k = np.abs(wavelet.psi(t / s))
+        out[j] = np.fft.fft(k / k.sum()).real
+    return out
+
+
 class _Base(object):
     #: engine family id and the attribute holding its parameter
     _family = None
     cdelta = -1
     gamma = -1
     deltaj0 = -1
+
+    @property
+    def smooth(self):
+        """Only with `enable_generic_smoothing()`: see `_GENERIC_SMOOTHING`."""
+        if not _GENERIC_SMOOTHING:
+            raise AttributeError("'{}' object has no attribute 'smooth'".format(type(self).__name__))
+        return self._smooth_generic
+
+    def _smooth_generic(self, W, dt, dj, scales):
+        from .wavelet import _smooth_device
+        return _smooth_device(W, dt, dj, scales, self.deltaj0, wavelet=self)
 
     def _engine_spec(self):
         """(family, param) if the engine evaluates this wavelet analytically, else None."""

@@ -321,6 +321,28 @@ def _family_of(wavelet):
     return spec
 
 
+class _smoothing_filter(object):
+    """Within the engine lock: install the time-smoothing responses of a non-Morlet wavelet
+    (mothers.time_filter_table) for the calls inside the block, restore Morlet's Gaussian after."""
+
+    def __init__(self, eng, wavelet, scales, dt, n):
+        self.eng = eng
+        self.table = None
+        if not isinstance(wavelet, Morlet):
+            from .mothers import time_filter_table
+            self.table = time_filter_table(wavelet, scales, dt, fft_kwargs(range(n))['n'])
+
+    def __enter__(self):
+        if self.table is not None:
+            self.eng.set_smooth_filter(self.table)
+        return self
+
+    def __exit__(self, *exc):
+        if self.table is not None:
+            self.eng.set_smooth_filter(None)
+        return False
+
+
 def _boxcar_len(wavelet, dj):
     """Number of taps of the scale-axis boxcar, int(round(2*deltaj0/dj)) (mothers.py:100)."""
     return int(np.round(wavelet.deltaj0 / dj * 2))
@@ -347,10 +369,13 @@ def wct(y1, y2, dt, dj=1/12, s0=-1, J=-1, sig=True,
     n0 = y1n.size
     sj, freq = _resolve_scales(n0, dt, dj, s0, J, wavelet, None)
     eng = _engine.default_engine()
+    klen = _boxcar_len(wavelet, dj)
+    if klen < 1:
+        raise ValueError('smoothing window undefined for this wavelet (deltaj0 = -1)')
     with eng.lock:
         _sync_padding(eng, len(y1n))
-        WCT, aWCT = eng.wct(y1n, y2n, dt, dj, sj, *_family_of(wavelet),
-                            boxcar_len=_boxcar_len(wavelet, dj))
+        with _smoothing_filter(eng, wavelet, sj, dt, len(y1n)):
+            WCT, aWCT = eng.wct(y1n, y2n, dt, dj, sj, *_family_of(wavelet), boxcar_len=klen)
     coi = (n0 / 2 - np.abs(np.arange(0, n0) - (n0 - 1) / 2))
     coi = wavelet.flambda() * wavelet.coi() * dt * coi
     if sig:
@@ -399,8 +424,9 @@ def _mc_histogram(prob, dt, dj, wavelet, draw, indices, progress=False, engine=N
             noise[k, 0], noise[k, 1] = draw(i)
         with eng.lock:
             _sync_padding(eng, N)
-            eng.wct_mc(noise, dt, dj, sj, fam[0], fam[1], _boxcar_len(wavelet, dj), prob['mask'],
-                       prob['maxscale'], nbins, hist)
+            with _smoothing_filter(eng, wavelet, sj, dt, N):
+                eng.wct_mc(noise, dt, dj, sj, fam[0], fam[1], _boxcar_len(wavelet, dj), prob['mask'],
+                           prob['maxscale'], nbins, hist)
         bar.update(len(idx))
     bar.close()
     return hist
@@ -428,8 +454,9 @@ def _mc_histogram_seeded(prob, dt, dj, wavelet, seed, first, count, engine=None)
     fam = _family_of(wavelet)
     with eng.lock:
         _sync_padding(eng, prob['N'])
-        eng.wct_mc_seeded(seed, first, count, prob['N'], dt, sj, fam[0], fam[1], _boxcar_len(wavelet, dj),
-                          prob['mask'], prob['maxscale'], nbins, hist)
+        with _smoothing_filter(eng, wavelet, sj, dt, prob['N']):
+            eng.wct_mc_seeded(seed, first, count, prob['N'], dt, sj, fam[0], fam[1], _boxcar_len(wavelet, dj),
+                              prob['mask'], prob['maxscale'], nbins, hist)
     return hist
 
 
@@ -480,8 +507,9 @@ def wct_significance(al1, al2, dt, dj, s0, J, significance_level=0.95,
     return sig95
 
 
-def _smooth_device(W, dt, dj, scales, deltaj0):
-    """Morlet.smooth on the GPU (reference mothers.py:61-104)."""
+def _smooth_device(W, dt, dj, scales, deltaj0, wavelet=None):
+    """Morlet.smooth on the GPU (reference mothers.py:61-104); with `wavelet` (Paul / DOG, opt-in)
+    the same operator with that wavelet's time filter."""
     W = np.asarray(W)
     scales = np.asarray(scales, dtype=float)
     klen = int(np.round(deltaj0 / dj * 2))
@@ -491,9 +519,10 @@ def _smooth_device(W, dt, dj, scales, deltaj0):
     eng = _engine.default_engine()
     with eng.lock:
         _sync_padding(eng, W.shape[1])
-        if np.isreal(W).all():
-            return eng.smooth(np.ascontiguousarray(W.real, dtype=np.float64), dt, scales, klen)
-        return eng.smooth(np.ascontiguousarray(W, dtype=np.complex128), dt, scales, klen)
+        with _smoothing_filter(eng, wavelet if wavelet is not None else Morlet(6), scales, dt, W.shape[1]):
+            if np.isreal(W).all():
+                return eng.smooth(np.ascontiguousarray(W.real, dtype=np.float64), dt, scales, klen)
+            return eng.smooth(np.ascontiguousarray(W, dtype=np.complex128), dt, scales, klen)
 
 
 def _check_parameter_wavelet(wavelet):

@@ -356,3 +356,55 @@ def check_seeded_monte_carlo(eng):
 
 def test_seeded_monte_carlo(emu):
     check_seeded_monte_carlo(emu)
+
+
+def check_generic_smoothing(eng_patch_api):
+    """Opt-in smoothing for Paul / DOG: off by default (`wct` raises AttributeError
+    like the reference); when enabled, `smooth` and `wct(sig=False)` match the independent NumPy
+    statement of the same definition (oracle.smooth_generic)."""
+    pycwt = eng_patch_api
+    from pycwt_b200 import mothers
+    rs = np.random.RandomState(21)
+    n = 700
+    y1 = rs.randn(n).cumsum() * 0.1 + rs.randn(n)
+    y2 = 0.5 * y1 + rs.randn(n)
+    dt, dj = 0.5, 0.25
+    with pytest.raises(AttributeError):
+        pycwt.wct(y1, y2, dt, dj, sig=False, wavelet=pycwt.Paul(4))
+    old = mothers.enable_generic_smoothing(True)
+    try:
+        for mo, mr in ((pycwt.Paul(4), orc.Paul(4)), (pycwt.DOG(2), orc.DOG(2)), (pycwt.DOG(6), orc.DOG(6))):
+            Wc = rs.randn(9, 300) + 1j * rs.randn(9, 300)
+            sj = 1.0 * 2 ** (np.arange(9) * dj)
+            ref = orc.smooth_generic(Wc, dt, dj, sj, mr)
+            assert relerr(mo.smooth(Wc, dt, dj, sj), ref) < 1e-10
+            refr = orc.smooth_generic(np.abs(Wc) ** 2, dt, dj, sj, mr)
+            got = mo.smooth(np.abs(Wc) ** 2, dt, dj, sj)
+            assert not np.iscomplexobj(got) and relerr(got, refr) < 1e-10
+            # coherence with this operator: oracle pipeline (wavelet.py:498-514) with the generic smooth
+            WCT, aWCT, coi, freq, sig = pycwt.wct(y1, y2, dt, dj, s0=2 * dt, J=20, sig=False, wavelet=mo)
+            y1n, y2n = (y1 - y1.mean()) / y1.std(), (y2 - y2.mean()) / y2.std()
+            W1, s, *_ = orc.cwt(y1n, dt, dj, 2 * dt, 20, mr)
+            W2 = orc.cwt(y2n, dt, dj, 2 * dt, 20, mr)[0]
+            inv = 1.0 / s[:, None]
+            S1 = orc.smooth_generic(np.abs(W1) ** 2 * inv, dt, dj, s, mr)
+            S2 = orc.smooth_generic(np.abs(W2) ** 2 * inv, dt, dj, s, mr)
+            S12 = orc.smooth_generic(W1 * W2.conj() * inv, dt, dj, s, mr)
+            assert relerr(WCT, np.abs(S12) ** 2 / (S1 * S2)) < 1e-9, type(mo).__name__
+        with pytest.raises(ValueError):          # no deltaj0 tabulated for this order
+            pycwt.wct(y1, y2, dt, dj, sig=False, wavelet=pycwt.Paul(3))
+    finally:
+        mothers.enable_generic_smoothing(old)
+    # Morlet keeps the reference's Gaussian whatever the switch
+    assert hasattr(pycwt.Morlet(6), "smooth")
+
+
+def test_generic_smoothing_for_paul_and_dog(emu):
+    import pycwt_b200 as pycwt
+    from pycwt_b200 import _engine
+    saved = _engine.default_engine
+    _engine.default_engine = lambda *a, **k: emu
+    try:
+        check_generic_smoothing(pycwt)
+    finally:
+        _engine.default_engine = saved

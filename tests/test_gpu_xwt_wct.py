@@ -239,3 +239,8 @@ def test_seeded_monte_carlo_device_rng(pycwt):
     b = pycwt.wct_significance(0.2, 0.4, 1.0, 0.5, 2.0, 8, mc_count=30, progress=False, cache=False, seed=1)
     c = pycwt.wct_significance(0.2, 0.4, 1.0, 0.5, 2.0, 8, mc_count=30, progress=False, cache=False, seed=2)
     assert np.array_equal(a, b, equal_nan=True) and not np.array_equal(a, c, equal_nan=True)
+
+
+def test_generic_smoothing_for_paul_and_dog_gpu(pycwt):
+    from test_emu_kernels import check_generic_smoothing
+    check_generic_smoothing(pycwt)
