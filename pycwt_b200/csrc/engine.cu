@@ -142,6 +142,11 @@ struct cwtb_ctx {
   int device = 0;
   rt_stream stream{};
   rt_stream aux_stream{};        // single-kernel classes run here, concurrently with the two-kernel chains
+  rt_stream prio_stream{};       // highest-priority stream: the chain of small launches in front of the
+                                 // expansion kernels (band products + coarse transforms) -- its CTAs are
+                                 // dispatched before the pending CTAs of the big launches on the other streams
+  int prio_mode = 1;             // CWTB_PRIO: 0 = no priority stream, 1 = coarse chain, 2 = coarse chain and
+                                 // the expansion kernels
   rt_stream chain_streams[3]{};  // two-kernel classes rotate over the engine's stream and these (own Z
                                  // and band-chunk region per chain)
   int n_chains = 2;              // chains in use, 1..4 (CWTB_CHAINS)
@@ -215,7 +220,7 @@ struct cwtb_ctx {
   std::set<void *> pinned, devallocs;
 #ifndef CWTB_HOST_EMU
   cudaEvent_t e0{}, e1{};
-  cudaEvent_t ev_fork{}, ev_join{}, ev_joinc[3]{};
+  cudaEvent_t ev_fork{}, ev_join{}, ev_joinc[3]{}, ev_coarse{};
 #endif
 };
 
@@ -1384,7 +1389,11 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
   // They run on the second stream like the single-kernel classes (own transform intermediate Zx).
   if (job.coarse_elems) {
 #ifndef CWTB_HOST_EMU
-    if (split) c->cur = c->aux_stream;
+    // the ~30 small launches in front of the expansion kernels go to the priority stream: queued
+    // behind the big launches of the other streams they would only advance in those launches' tails
+    const bool prio = split && c->prio_mode > 0;
+    if (prio) RT(cudaStreamWaitEvent(c->prio_stream, c->ev_fork, 0));
+    if (split) c->cur = prio ? c->prio_stream : c->aux_stream;
 #endif
     if ((e = ensure(c, c->Cin, job.coarse_elems * sizeof(V)))) return e;
     if ((e = ensure(c, c->Cout, job.coarse_elems * sizeof(V)))) return e;
@@ -1414,6 +1423,13 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
       }
     }
     c->prof_tag = "";
+#ifndef CWTB_HOST_EMU
+    if (prio && c->prio_mode == 1) {   // expansion kernels: ordinary priority, after the coarse chain
+      RT(cudaEventRecord(c->ev_coarse, c->prio_stream));
+      RT(cudaStreamWaitEvent(c->aux_stream, c->ev_coarse, 0));
+      c->cur = c->aux_stream;
+    }
+#endif
     // one expansion launch per tap count: classes are sorted by taps first
     for (size_t ci = 0; ci < job.classes.size() && !e; ++ci) {
       const ClassRun &cl = job.classes[ci];
@@ -1426,6 +1442,12 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
       e = launch_expand<T>(c, cl.taps, ea, rows);
     }
     c->ztmp = nullptr;
+#ifndef CWTB_HOST_EMU
+    if (prio && c->prio_mode == 2 && !e) {   // later work of the second stream and the join follow the priority stream
+      RT(cudaEventRecord(c->ev_coarse, c->prio_stream));
+      RT(cudaStreamWaitEvent(c->aux_stream, c->ev_coarse, 0));
+    }
+#endif
     c->cur = c->stream;
     if (e) return e;
   }
@@ -1656,6 +1678,13 @@ int cwtb_create(int device, cwtb_ctx **out) {
   cudaEventCreate(&c->e1);
   for (auto &st : c->copy_streams) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking);
+  {
+    int lo = 0, hi = 0;   // numerically lower = higher priority
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    cudaStreamCreateWithPriority(&c->prio_stream, cudaStreamNonBlocking, hi);
+  }
+  cudaEventCreateWithFlags(&c->ev_coarse, cudaEventDisableTiming);
+  if (const char *g = getenv("CWTB_PRIO")) c->prio_mode = std::min(2, std::max(0, atoi(g)));
   for (auto &st : c->chain_streams) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
   for (auto &ev : c->ev_joinc) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
@@ -1719,6 +1748,8 @@ void cwtb_destroy(cwtb_ctx *c) {
   cudaStreamDestroy(c->stream);
   for (auto &st : c->copy_streams) cudaStreamDestroy(st);
   cudaStreamDestroy(c->aux_stream);
+  cudaStreamDestroy(c->prio_stream);
+  cudaEventDestroy(c->ev_coarse);
   for (auto &st : c->chain_streams) cudaStreamDestroy(st);
   for (auto &ev : c->ev_joinc) cudaEventDestroy(ev);
   cudaEventDestroy(c->ev_fork);

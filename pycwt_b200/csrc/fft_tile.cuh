@@ -202,6 +202,33 @@ struct TileBarrier {
   }
 };
 
+// Ampere-style asynchronous copy global -> shared of one element (8 or 16 bytes) that bypasses the
+// register file: a thread can have its whole share of a tile in flight at once instead of
+// compiler-sized batches of loads followed by stores.  Measured on B200 for the first kernel of the
+// band scales (profiles/r2/split_b.txt): SLOWER than batches of four LDG.128 + STS.128 (13.6 -> 14.8 us
+// per row; the element-wise LDGSTS scatter costs more than the extra loads in flight gain): off.  cp_async_wait() makes the thread's own
+// copies visible to itself; the CTA barrier that follows publishes them.  Host emulation: plain copy.
+#ifndef CWTB_PASSA_ASYNC
+#define CWTB_PASSA_ASYNC 0
+#endif
+template <typename V> HD void cp_async(V *dst, const V *src) {
+#if defined(__CUDA_ARCH__) && !defined(CWTB_HOST_EMU)
+  static_assert(sizeof(V) == 16 || sizeof(V) == 8, "cp_async: 8- or 16-byte elements");
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  if constexpr (sizeof(V) == 16)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+#else
+  *dst = *src;
+#endif
+}
+HD void cp_async_wait() {
+#if defined(__CUDA_ARCH__) && !defined(CWTB_HOST_EMU)
+  asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
+
 template <typename V> HD V ldg(const V *p) {
 #if defined(__CUDA_ARCH__) && !defined(CWTB_HOST_EMU)
   return __ldg(p);

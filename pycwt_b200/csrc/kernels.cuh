@@ -603,6 +603,24 @@ template <typename T, int K1, int MODE, int SIGN> struct PassABody {
           }
           sm[LY::phys(b, pos)] = v;
         }
+      } else if (CWTB_PASSA_ASYNC && MODE == MODE_BAND) {
+        // band products are copied as they are (multi-pass plans apply the twist in pass 1):
+        // asynchronous copies, the thread's 32 elements in flight together
+        const V *base = a.Bbuf + src.d.boff + r20;
+        for (int idx = tid; idx < K1 * T2; idx += NT) {
+          const int b = idx % T2, pos = idx / T2;
+          cp_async(&sm[LY::phys(b, pos)], base + (size_t)pos * a.K2 + b);
+        }
+        cp_async_wait();
+      } else if (CWTB_PASSA_ASYNC && MODE == MODE_CPLX) {
+        const V *row = (const V *)a.in + (size_t)(a.row0 + by) * a.in_pitch;
+        for (int idx = tid; idx < K1 * T2; idx += NT) {
+          const int b = idx % T2, pos = idx / T2;
+          const unsigned r = (unsigned)pos * a.K2 + (unsigned)(r20 + b);
+          if ((long long)r < a.n_in) cp_async(&sm[LY::phys(b, pos)], row + r);
+          else sm[LY::phys(b, pos)] = mk<T>(0, 0);
+        }
+        cp_async_wait();
       } else
       for (int idx = tid; idx < K1 * T2; idx += NT) {
         const int b = idx % T2, pos = idx / T2;
