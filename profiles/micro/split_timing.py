@@ -31,6 +31,9 @@ def main():
     parts = [("full 0..255", slice(0, 256)), ("dense 0..23", slice(0, 24)), ("band 24..71", slice(24, 72)),
              ("exact 0..71", slice(0, 72)), ("expand 72..255", slice(72, 256)),
              ("expand w12 117..255", slice(117, 256))]
+    if os.environ.get("SPLIT_PARTS"):   # e.g. SPLIT_PARTS=full,exact
+        keep = os.environ["SPLIT_PARTS"].split(",")
+        parts = [p for p in parts if p[0].split()[0] in keep]
     for lib in libs:
         eng = _engine.Engine(0, lib_path=lib)
         dsig = eng.dev_alloc(x.nbytes)

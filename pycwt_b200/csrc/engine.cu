@@ -167,6 +167,8 @@ struct cwtb_ctx {
   double expand_eps = 5e-13;     // fp64 engine: bound on the aliasing error of the expansion path
                                  // (0: path off, every scale through the exact pruned transforms)
   double expand_eps32 = 2e-7;    // fp32 engine
+  int dense_margin = 2;          // pruned lengths within this many octaves of Np run as dense scales
+                                 // (CWTB_DENSE_MARGIN; config 2: 1.710 -> 1.686 ms, profiles/r2/sweep_e.txt)
   int expand_min_log2R = 3;      // expansion needs Np / Nc >= 8 (CWTB_EXPAND_MIN_R: log2)
   Buf *ztmp = nullptr;           // intermediate of two_kernel_rows (set per stream; default Z)
   void *comm = nullptr;          // ncclComm_t of cwtb_comm_init (one rank per context)
@@ -587,6 +589,10 @@ static int build_job(cwtb_ctx *c, Job &job, long long n0, double dt, const doubl
       lk = std::max(c->direct_max_log2 + 1, ilog2((unsigned long long)(hi - lo + 1)));
     }
     if (lk > 20) lk = job.log2N;   // pruned lengths above 2^20 are not built: treat as dense
+    // a pruned length of 2^18 or more within `dense_margin` octaves of the full one saves nothing
+    // over the dense kernel pair (first kernels of 256 / 512 points cost what the 1024-point dense
+    // one does once the band-product launch is counted): treat as dense (CWTB_DENSE_MARGIN)
+    if (lk >= 18 && lk < job.log2N && job.log2N - lk <= c->dense_margin && job.log2N <= 20) lk = job.log2N;
     if (lk >= job.log2N) {  // dense
       lk = job.log2N;
       d.rsplit = (int)half;
@@ -1701,6 +1707,7 @@ int cwtb_create(int device, cwtb_ctx **out) {
   if (const char *g = getenv("CWTB_EXPAND_EPS")) c->expand_eps = std::max(0.0, atof(g));
   if (const char *g = getenv("CWTB_EXPAND_EPS32")) c->expand_eps32 = std::max(0.0, atof(g));
   if (const char *g = getenv("CWTB_EXPAND_MIN_R")) c->expand_min_log2R = std::min(14, std::max(2, atoi(g)));
+  if (const char *g = getenv("CWTB_DENSE_MARGIN")) c->dense_margin = std::max(0, atoi(g));
   if (const char *g = getenv("CWTB_L2_PERSIST")) c->l2_persist = atoi(g);
   if (const char *g = getenv("CWTB_FUSED")) c->fused = atoi(g);
   if (const char *g = getenv("CWTB_PF_DIST")) c->pf_dist = std::max(0, atoi(g));

@@ -585,7 +585,10 @@ template <typename T, int K1, int MODE, int SIGN> struct PassABody {
           const int k = (int)r - (r >= a.N / 2 ? (int)a.N : 0);
           V v = mk<T>(0, 0);
           if (k >= d.k_lo && k <= d.k_hi) {
-            if (since >= 16 || (long long)k != kprev + D) {
+            // (a value in the subnormal range has lost its relative precision: with band_eps = 0 the
+            // band reaches bins where exp() is below 1e-308, and the recurrence would carry that
+            // error up to the peak -- re-seed until the value is a normal number again)
+            if (since >= 16 || (long long)k != kprev + D || g < 1e-290) {
               const double f = d.s * (6.283185307179586 * ((double)k * a.fam.dw));
               const double dd = f - a.fam.f0;
               g = exp(-0.5 * dd * dd);

@@ -61,6 +61,29 @@ def test_config2_every_row(pycwt):
     assert relerr(fft, ref_fft) < 1e-12
 
 
+def test_config2_widest_band_mode(pycwt):
+    """band_eps = 0 (every representable bin kept) with the expansion off at N = 2^20: the dense
+    kernel's Gaussian recurrence must not start from subnormal values (rows 41, 54, 57 were off by
+    2e-10 of max|W| before the re-seeding rule of kernels.cuh: PassABody, dense Morlet)."""
+    from pycwt_b200 import _engine
+    c = wl.C2
+    x = wl.config2_signal()
+    sj = wl.config2_scales()
+    rows = np.array([0, 23, 39, 41, 51, 54, 57, 71, 100])
+    eng = pycwt.default_engine()
+    eng.set_band_eps(0.0)
+    eng.set_expand_eps(0.0, 0.0)
+    try:
+        W = eng.cwt(x, c["dt"], sj[rows], _engine.MORLET, c["f0"])
+    finally:
+        eng.set_band_eps(1e-16)
+        eng.set_expand_eps()
+    Wr = _oracle_rows(x, c["dt"], orc.Morlet(c["f0"]), sj, rows)
+    err = np.abs(W - Wr).max(axis=1) / np.abs(Wr).max()
+    print("config 2, band_eps = 0: worst row error %.2e" % err.max())
+    assert (err < 1e-12).all(), err
+
+
 @pytest.mark.parametrize("family", ["paul", "dog"])
 def test_config3_every_row_fp32(pycwt, monkeypatch, family):
     """Config 3: Paul(4) / DOG(2), N = 2^18, 128 scales, float32 chirp, fp32 engine; every row."""
