@@ -15,6 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 import workloads as wl          # noqa: E402
 from pycwt_b200 import _engine  # noqa: E402
+from bench import pin_to_gpu_numa_node  # noqa: E402
 
 
 def timed(eng, dsig, n, dt, sj, f0, iters=20):
@@ -24,6 +25,7 @@ def timed(eng, dsig, n, dt, sj, f0, iters=20):
 
 
 def main():
+    pin_to_gpu_numa_node(0)   # like bench.py: launch latency depends on the CPU node
     libs = sys.argv[1:] or [None]
     c = wl.C2
     sj = wl.config2_scales()

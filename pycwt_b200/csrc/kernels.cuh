@@ -64,6 +64,28 @@ HD double amp_eval(const Fam &fp, double s, int k) {
   }
 }
 
+// the same in the engine's arithmetic: the fp32 engine forms f = s*w in double (w spans 2^18 bins)
+// and evaluates the power and the exponential in float (the caller keeps orders above 8 in double:
+// their powers overflow float).  fp64 instructions run at half the fp32 rate on B200: one double exp per band product made
+// the band-product launches and the generating first kernel fp64-pipe bound in the fp32 engine.
+template <typename T> HD T amp_eval_t(const Fam &fp, double s, int k) {
+  if constexpr (sizeof(T) == 8) {
+    return amp_eval(fp, s, k);
+  } else {
+    const double w = 6.283185307179586 * ((double)k * fp.dw);
+    const double f = s * w;
+    if (fp.family == 0) {
+      const float d = (float)(f - fp.f0);
+      return expf(-0.5f * d * d);
+    }
+    const float ff = (float)f;
+    float r = 1.0f, b = ff;
+    for (int e = fp.m; e; e >>= 1) { if (e & 1) r *= b; b *= b; }
+    if (fp.family == 1) return ff > 0.0f ? r * expf(-ff) : 0.0f;
+    return r * expf(-0.5f * ff * ff);
+  }
+}
+
 template <typename T> HD cx<T> rot_unit(cx<T> v, int unit) {
   switch (unit & 3) {
     case 1: return mk<T>(-v.y, v.x);
@@ -82,7 +104,9 @@ HD cx<T> band_value(const Fam &fp, const ScaleDesc &d, const cx<T> *spec, unsign
     cx<T> tt = mk<T>((T)(t.x * d.amp), (T)(t.y * d.amp));
     return cmul(v, tt);
   }
-  const T a = (T)(amp_eval(fp, d.s, k) * d.amp);
+  // (orders above 8: value and normalisation only combine to a float-range number in double)
+  const T a = (sizeof(T) == 8 || (fp.family != 0 && fp.m > 8)) ? (T)(amp_eval(fp, d.s, k) * d.amp)
+                                                               : (T)(amp_eval_t<T>(fp, d.s, k) * (T)d.amp);
   return rot_unit<T>(cscale(v, a), fp.unit);
 }
 
@@ -462,6 +486,9 @@ template <typename T, int SIGN, int K2 = K2C> struct PassBBody {
 };
 
 // ---- Body: first kernel of the two-kernel path: K1-point transforms over r1 --------
+// (Measured and dropped, profiles/r2/sweep_k.txt: band scales that evaluate x^ * conj(psi^) * norm while the
+// tile is filled instead of reading the band buffer -- the first kernel of Np/K' = 2 scales got 55 % slower,
+// more than the band-product launch it saves: config 5 7.83 -> 7.92 ms, config 3 Paul 0.283 -> 0.321 ms.)
 enum { MODE_DENSE = 0, MODE_BAND = 1, MODE_REAL = 2, MODE_CPLX = 3 };
 
 template <typename T> struct PassAArgs {

@@ -270,3 +270,63 @@ def cwt_scale_sharded(signal, dt, scales, family, param, precision, engine, comm
         rr = scale_rows(scales.size, r, world, layout)
         power[rr] = np.asarray(stack[r])[:rr.size]
     return rows, power, W
+
+
+def wct_halo(boxcar_len):
+    """Scale rows below / above a block that its coherence needs: the scale boxcar of
+    `Morlet.smooth` (reference mothers.py:96-102, convolve2d 'same' with zero fill) makes output row
+    i depend on the time-smoothed rows q with i + (K-1)//2 - (K-1) <= q <= i + (K-1)//2."""
+    K = int(boxcar_len)
+    return K - 1 - (K - 1) // 2, (K - 1) // 2
+
+
+def wct_scale_sharded(y1, y2, dt, dj=1 / 12, s0=-1, J=-1, wavelet='morlet', normalize=True,
+                      engine=None, comm=None, device=None):
+    """Deterministic part of the wavelet coherence (reference wavelet.py:422-516) with the SCALES
+    block-partitioned over the ranks.  The transforms and the time smoothing are
+    per scale; only the scale boxcar couples neighbouring rows, so every rank computes its block
+    plus a halo of `wct_halo` rows on either side (redundant work of at most K-1 scales per rank
+    instead of a halo exchange of S x n0 fields) and keeps the interior.  At the ends of the scale
+    ladder the block ends where the reference's zero fill starts, so the result equals the
+    single-GPU one row for row.  No collective on the data path: the coherence slabs stay with
+    their rank; the per-scale mean coherence [S] is all-gathered.
+
+    Returns (lo, hi, WCT[lo:hi], aWCT[lo:hi], mean_wct[S], freq[S])."""
+    from . import wavelet as wv
+    from . import _engine
+    comm = _as_comm(comm)
+    rank, world = _rank_world(comm)
+    mother = wv._check_parameter_wavelet(wavelet)
+    if not hasattr(mother, 'smooth'):
+        raise AttributeError("'{}' object has no attribute 'smooth'".format(type(mother).__name__))
+    y1 = np.asarray(y1)
+    y2 = np.asarray(y2)
+    if s0 == -1:
+        s0 = 2 * dt / mother.flambda()
+    if J == -1:
+        J = int(np.round(np.log2(y1.size * dt / s0) / dj))
+    _, y1n, _ = wv._standardise(y1, normalize)
+    _, y2n, _ = wv._standardise(y2, normalize)
+    n0 = y1n.size
+    sj, freq = wv._resolve_scales(n0, dt, dj, s0, J, mother, None)
+    klen = wv._boxcar_len(mother, dj)
+    if klen < 1:
+        raise ValueError('smoothing window undefined for this wavelet (deltaj0 = -1)')
+    S = sj.size
+    lo, hi = shard_range(S, rank, world)
+    below, above = wct_halo(klen)
+    a, b = max(0, lo - below), min(S, hi + above)
+    eng = engine or _engine.default_engine()
+    if hi > lo:
+        with eng.lock:
+            wv._sync_padding(eng, n0)
+            with wv._smoothing_filter(eng, mother, sj[a:b], dt, n0):
+                WCT, aWCT = eng.wct(y1n, y2n, dt, dj, sj[a:b], *wv._family_of(mother), boxcar_len=klen)
+        WCT, aWCT = WCT[lo - a:hi - a], aWCT[lo - a:hi - a]
+        local = WCT.mean(axis=1)
+    else:
+        WCT = np.zeros((0, n0))
+        aWCT = np.zeros((0, n0))
+        local = np.zeros(0)
+    mean = gather_rows(local, S, comm, device)
+    return lo, hi, WCT, aWCT, mean, freq

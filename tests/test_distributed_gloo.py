@@ -171,3 +171,82 @@ def test_nccl_comm_id_exchange_through_rendezvous_file(tmp_path, monkeypatch):
     assert solo.max(3.5) == 3.5
     assert np.array_equal(solo.allgather_rows(np.arange(6.0).reshape(3, 2), 3), np.arange(6.0).reshape(3, 2))
     assert np.array_equal(solo.allreduce_sum(np.arange(4)), np.arange(4))
+
+
+def test_wct_halo_rows():
+    """Rows of the scale boxcar's footprint: K = 14 (dj = 1/12) reaches 7 rows down and 6 up, like
+    scipy's convolve2d(..., 'same') of the reference (mothers.py:96-102)."""
+    from scipy.signal import convolve2d
+    from pycwt_b200 import distributed as D
+    for K in (1, 2, 5, 14, 15):
+        T = np.zeros((40, 1))
+        T[20] = 1.0
+        out = convolve2d(T, np.ones((K, 1)), 'same')[:, 0]
+        hit = np.flatnonzero(out)
+        below, above = D.wct_halo(K)
+        # an impulse at row 20 reaches outputs 20 - above .. 20 + below
+        assert (hit.min(), hit.max()) == (20 - above, 20 + below), K
+
+
+def _wct_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from pycwt_b200 import distributed as D, _engine
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        eng = _engine.Engine(0, lib_path=os.path.join(ROOT, "tests", "_emu", "libcwtb200_emu.so"))
+        rs = np.random.RandomState(3)
+        t = np.arange(700)
+        y1 = np.sin(2 * np.pi * t / 23.0) + 0.5 * rs.randn(700)
+        y2 = np.sin(2 * np.pi * t / 23.0 + 0.6) + 0.5 * rs.randn(700)
+        lo, hi, WCT, aWCT, mean, freq = D.wct_scale_sharded(y1, y2, 1.0, dj=0.25, s0=2.0, J=27, engine=eng,
+                                                            comm=D.TorchComm(dist))
+        q.put((rank, lo, hi, WCT, aWCT, mean))
+        eng.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_wct_scale_sharded_gloo():
+    """World size 3: every rank's coherence slab (block + halo computed, interior kept) equals the
+    rows of the single-process result bit for bit, and the gathered mean coherence is complete."""
+    pytest.importorskip("torch")
+    import torch.multiprocessing as mp
+    from pycwt_b200 import build as _build, _engine, distributed as D
+    lib = _build.build_emulation(os.path.join(ROOT, "tests", "_emu"))
+    eng = _engine.Engine(0, lib_path=lib)
+    rs = np.random.RandomState(3)
+    t = np.arange(700)
+    y1 = np.sin(2 * np.pi * t / 23.0) + 0.5 * rs.randn(700)
+    y2 = np.sin(2 * np.pi * t / 23.0 + 0.6) + 0.5 * rs.randn(700)
+    lo, hi, W1, A1, mean1, _ = D.wct_scale_sharded(y1, y2, 1.0, dj=0.25, s0=2.0, J=27, engine=eng)
+    eng.close()
+    assert (lo, hi) == (0, 28) and W1.shape == (28, 700)
+    # the single-process result is the oracle's coherence
+    from oracle import cwt_oracle as orc
+    Wr, Ar = orc.wct(y1, y2, 1.0, dj=0.25, s0=2.0, J=27, sig=False, wavelet=orc.Morlet(6))[:2]
+    assert np.abs(W1 - Wr).max() < 1e-10 and np.abs(np.angle(np.exp(1j * (A1 - Ar)))).max() < 1e-8
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    world = 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_wct_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = {g[0]: g for g in (q.get(timeout=300) for _ in procs)}
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    covered = []
+    for r in range(world):
+        _, lo, hi, W, A, mean = got[r]
+        assert (lo, hi) == D.shard_range(28, r, world)
+        assert np.array_equal(W, W1[lo:hi]) and np.array_equal(A, A1[lo:hi])
+        assert np.allclose(mean, mean1, rtol=0, atol=0)
+        covered += list(range(lo, hi))
+    assert covered == list(range(28))
