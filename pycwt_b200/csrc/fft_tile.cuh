@@ -47,6 +47,13 @@ namespace cwtb {
 #define CWTB_STR_(x) #x
 #define CWTB_STR(x) CWTB_STR_(x)
 #define CWTB_PRAGMA_UNROLL_B _Pragma(CWTB_STR(unroll CWTB_UNROLL_B))
+#ifndef CWTB_PASSA_BATCH
+#define CWTB_PASSA_BATCH 8     // spectrum loads in flight per thread while a dense first-kernel tile is filled
+#endif
+#ifndef CWTB_UNROLL_A
+#define CWTB_UNROLL_A 4        // loads in flight per thread while a band / row tile of the first kernel is filled
+#endif
+#define CWTB_PRAGMA_UNROLL_A _Pragma(CWTB_STR(unroll CWTB_UNROLL_A))
 constexpr int NT = CWTB_NT;  // threads per CTA
 // Pass twiddle tables: for a pass of radix R on sub-transforms of length L the factor
 // w_L^{j c} (c = 1..R-1, j < L/R) is stored at  tw[tw_offset(L) + (c-1)*(L/R) + j], i.e. lanes

@@ -607,31 +607,51 @@ template <typename T, int K1, int MODE, int SIGN> struct PassABody {
         double g = 0, rho = 0;
         long long kprev = 0;
         int since = 1 << 30;
-        for (int pos = tid / T2; pos < K1; pos += DPOS) {
-          const unsigned r = (unsigned)pos * a.K2 + (unsigned)(r20 + b);
-          const int k = (int)r - (r >= a.N / 2 ? (int)a.N : 0);
-          V v = mk<T>(0, 0);
-          if (k >= d.k_lo && k <= d.k_hi) {
-            // (a value in the subnormal range has lost its relative precision: with band_eps = 0 the
-            // band reaches bins where exp() is below 1e-308, and the recurrence would carry that
-            // error up to the peak -- re-seed until the value is a normal number again)
-            if (since >= 16 || (long long)k != kprev + D || g < 1e-290) {
-              const double f = d.s * (6.283185307179586 * ((double)k * a.fam.dw));
-              const double dd = f - a.fam.f0;
-              g = exp(-0.5 * dd * dd);
-              rho = exp(-aa * dd - 0.5 * aa * aa);
-              since = 0;
-            } else {
-              g *= rho;
-              rho *= q;
-              ++since;
-            }
-            kprev = k;
-            v = cscale(ldg(&a.spec[(size_t)d.chan * a.N + r]), (T)(g * d.amp));
-          } else {
-            since = 1 << 30;
+        // Batches of UB bins: the spectrum loads of a batch are issued together (independent of the
+        // recurrence), then the Gaussian values follow one another.  One load per iteration, as the
+        // plain loop compiles, leaves every thread waiting a full L2 round trip 32 times per tile.
+        constexpr int UB = CWTB_PASSA_BATCH;
+        const V *sp = a.spec + (size_t)d.chan * a.N + (unsigned)(r20 + b);
+        for (int pos0 = tid / T2; pos0 < K1; pos0 += DPOS * UB) {
+          V raw[UB];
+          int kk[UB];
+#pragma unroll
+          for (int u = 0; u < UB; ++u) {
+            const int pos = pos0 + u * DPOS;
+            const unsigned r = (unsigned)pos * a.K2 + (unsigned)(r20 + b);
+            const int k = (int)r - (r >= a.N / 2 ? (int)a.N : 0);
+            const bool in = pos < K1 && k >= d.k_lo && k <= d.k_hi;
+            kk[u] = in ? k : (int)0x7fffffff;
+            raw[u] = in ? ldg(&sp[(size_t)pos * a.K2]) : mk<T>(0, 0);
           }
-          sm[LY::phys(b, pos)] = v;
+#pragma unroll
+          for (int u = 0; u < UB; ++u) {
+            const int pos = pos0 + u * DPOS;
+            if (pos >= K1) break;
+            V v = mk<T>(0, 0);
+            if (kk[u] != (int)0x7fffffff) {
+              const int k = kk[u];
+              // (a value in the subnormal range has lost its relative precision: with band_eps = 0 the
+              // band reaches bins where exp() is below 1e-308, and the recurrence would carry that
+              // error up to the peak -- re-seed until the value is a normal number again)
+              if (since >= 16 || (long long)k != kprev + D || g < 1e-290) {
+                const double f = d.s * (6.283185307179586 * ((double)k * a.fam.dw));
+                const double dd = f - a.fam.f0;
+                g = exp(-0.5 * dd * dd);
+                rho = exp(-aa * dd - 0.5 * aa * aa);
+                since = 0;
+              } else {
+                g *= rho;
+                rho *= q;
+                ++since;
+              }
+              kprev = k;
+              v = cscale(raw[u], (T)(g * d.amp));
+            } else {
+              since = 1 << 30;
+            }
+            sm[LY::phys(b, pos)] = v;
+          }
         }
       } else if (CWTB_PASSA_ASYNC && MODE == MODE_BAND) {
         // band products are copied as they are (multi-pass plans apply the twist in pass 1):
@@ -651,10 +671,13 @@ template <typename T, int K1, int MODE, int SIGN> struct PassABody {
           else sm[LY::phys(b, pos)] = mk<T>(0, 0);
         }
         cp_async_wait();
-      } else
-      for (int idx = tid; idx < K1 * T2; idx += NT) {
-        const int b = idx % T2, pos = idx / T2;
-        sm[LY::phys(b, pos)] = src.get(pos, r20 + b);
+      } else {
+        // (the compiler batches four loads per round trip on its own; eight in flight measured ...)
+        CWTB_PRAGMA_UNROLL_A
+        for (int idx = tid; idx < K1 * T2; idx += NT) {
+          const int b = idx % T2, pos = idx / T2;
+          sm[LY::phys(b, pos)] = src.get(pos, r20 + b);
+        }
       }
     } else if constexpr (PH == 1) {
       if (MODE == MODE_BAND && p != 0) {
