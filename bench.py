@@ -201,7 +201,7 @@ def dominant_writer(prof, bytes_per_row):
     Writers carry `bytes_per_row` algorithmic bytes per scale row; "fwd:" / "coarse:" launches and
     the first kernels of the two-kernel scales are intermediate work (0 algorithmic bytes)."""
     writers = [k for k in prof if ":" not in k["name"] and k["name"].split("<")[0] in
-               ("SingleBody", "DirectBody", "PassBBody", "ExpandBody", "PipeAB") and ", -1" not in k["name"]]
+               ("SingleBody", "DirectBody", "PassBBody", "ExpandBody", "ExpandMmaBody", "PipeAB") and ", -1" not in k["name"]]
     if not writers:
         return None
     kern_ms = sum(k["ms"] for k in prof)

@@ -167,6 +167,7 @@ struct cwtb_ctx {
   double expand_eps = 5e-13;     // fp64 engine: bound on the aliasing error of the expansion path
                                  // (0: path off, every scale through the exact pruned transforms)
   double expand_eps32 = 2e-7;    // fp32 engine
+  int expand_mma = 1;            // fp64 expansion kernels with DMMA tap sums (CWTB_EXPAND_MMA=0: scalar kernel)
   int dense_margin = 2;          // pruned lengths within this many octaves of Np run as dense scales
                                  // (CWTB_DENSE_MARGIN; config 2: 1.710 -> 1.686 ms, profiles/r2/sweep_e.txt)
   int expand_min_log2R = 3;      // expansion needs Np / Nc >= 8 (CWTB_EXPAND_MIN_R: log2)
@@ -1286,29 +1287,41 @@ static size_t band_chunk_elems(const cwtb_ctx *c, const Job &job, int G) {
 }
 
 template <typename T, int TAPS>
-static int launch_expand_t(cwtb_ctx *c, const ExpandArgs<T> &a, int rows) {
+static int launch_expand_t(cwtb_ctx *c, const ExpandArgs<T> &a, int rows, int min_log2Nc) {
   using B = ExpandBody<T, TAPS>;
   // tiles per row: (R / RB) * ceil(Nc / MT) with RB = min(R, NT), MT = (NT / RB) * L -- equal to
   // N / (NT * L) for every coarse length with Nc >= MT; rows with a shorter coarse grid use the
   // first tiles of the launch only
   const unsigned gx = std::max<unsigned>(1, a.N / (unsigned)(B::NT * B::L));
+#ifndef CWTB_HOST_EMU
+  // fp64: tap sums on the tensor cores (kernels.cuh: ExpandMmaBody) whenever every row expands by 8 or more
+  if constexpr (std::is_same<T, double>::value) {
+    if (c->expand_mma && c->expand_min_log2R >= 3 && a.N >= (unsigned)ExpandMmaBody<TAPS>::OUT_PER_CTA) {
+      // tiles per row: N / (32 L); a row whose coarse grid is shorter than one run (Nc < L, R > 32) needs
+      // one tile per 32 phases instead
+      const unsigned gm = a.N / (32u * std::min<unsigned>(ExpandMmaBody<TAPS>::L, 1u << min_log2Nc));
+      if (a.epi == EPI_MULCONJ) return launch<ExpandMmaBody<TAPS, EPI_MULCONJ>>(c, gm, rows, a);
+      return launch<ExpandMmaBody<TAPS>>(c, gm, rows, a);
+    }
+  }
+#endif
   if (a.epi == EPI_MULCONJ) return launch<ExpandBody<T, TAPS, EPI_MULCONJ>>(c, gx, rows, a);
   return launch<B>(c, gx, rows, a);
 }
 template <typename T>
-static int launch_expand(cwtb_ctx *c, int taps, const ExpandArgs<T> &a, int rows) {
+static int launch_expand(cwtb_ctx *c, int taps, const ExpandArgs<T> &a, int rows, int min_log2Nc) {
   if constexpr (std::is_same<T, double>::value) {
     switch (taps) {
-      case 10: return launch_expand_t<T, 10>(c, a, rows);
-      case 12: return launch_expand_t<T, 12>(c, a, rows);
-      case 14: return launch_expand_t<T, 14>(c, a, rows);
-      case 16: return launch_expand_t<T, 16>(c, a, rows);
+      case 10: return launch_expand_t<T, 10>(c, a, rows, min_log2Nc);
+      case 12: return launch_expand_t<T, 12>(c, a, rows, min_log2Nc);
+      case 14: return launch_expand_t<T, 14>(c, a, rows, min_log2Nc);
+      case 16: return launch_expand_t<T, 16>(c, a, rows, min_log2Nc);
     }
   } else {
     switch (taps) {
-      case 6: return launch_expand_t<T, 6>(c, a, rows);
-      case 8: return launch_expand_t<T, 8>(c, a, rows);
-      case 10: return launch_expand_t<T, 10>(c, a, rows);
+      case 6: return launch_expand_t<T, 6>(c, a, rows, min_log2Nc);
+      case 8: return launch_expand_t<T, 8>(c, a, rows, min_log2Nc);
+      case 10: return launch_expand_t<T, 10>(c, a, rows, min_log2Nc);
     }
   }
   return fail(c, CWTB_ERR_STATE, "expansion: unsupported tap count");
@@ -1440,12 +1453,14 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
     for (size_t ci = 0; ci < job.classes.size() && !e; ++ci) {
       const ClassRun &cl = job.classes[ci];
       if (!cl.expand || (ci > 0 && job.classes[ci - 1].expand && job.classes[ci - 1].taps == cl.taps)) continue;
-      int rows = 0;
-      for (size_t cj = ci; cj < job.classes.size() && job.classes[cj].expand && job.classes[cj].taps == cl.taps; ++cj)
+      int rows = 0, minl = 30;
+      for (size_t cj = ci; cj < job.classes.size() && job.classes[cj].expand && job.classes[cj].taps == cl.taps; ++cj) {
         rows += job.classes[cj].count;
+        minl = std::min(minl, job.classes[cj].log2Nc);
+      }
       ExpandArgs<T> ea{ddesc, (const V *)c->Cout.p, (const double *)c->wtab.p, W, nt, job.n0, N, cl.first, epi,
                        job.log2N};
-      e = launch_expand<T>(c, cl.taps, ea, rows);
+      e = launch_expand<T>(c, cl.taps, ea, rows, minl);
     }
     c->ztmp = nullptr;
 #ifndef CWTB_HOST_EMU
@@ -1707,6 +1722,7 @@ int cwtb_create(int device, cwtb_ctx **out) {
   if (const char *g = getenv("CWTB_EXPAND_EPS")) c->expand_eps = std::max(0.0, atof(g));
   if (const char *g = getenv("CWTB_EXPAND_EPS32")) c->expand_eps32 = std::max(0.0, atof(g));
   if (const char *g = getenv("CWTB_EXPAND_MIN_R")) c->expand_min_log2R = std::min(14, std::max(2, atoi(g)));
+  if (const char *g = getenv("CWTB_EXPAND_MMA")) c->expand_mma = atoi(g) != 0;
   if (const char *g = getenv("CWTB_DENSE_MARGIN")) c->dense_margin = std::max(0, atoi(g));
   if (const char *g = getenv("CWTB_L2_PERSIST")) c->l2_persist = atoi(g);
   if (const char *g = getenv("CWTB_FUSED")) c->fused = atoi(g);

@@ -863,6 +863,120 @@ template <typename T, int TAPS, int EPI = EPI_STORE> struct ExpandBody {
   }
 };
 
+#ifndef CWTB_HOST_EMU
+// ---- the fp64 expansion with the tap sums on the tensor cores ---------------------------------------
+// The tap sum  acc[m][rho] = sum_t c[m + t - (taps/2 - 1)] * h[t][rho]  is a Toeplitz product: for 8
+// consecutive coarse positions m and 8 consecutive phases rho it is an (8 x taps) x (taps x 8) real
+// matrix product per component, i.e. taps/4 `mma.sync.m8n8k4.f64` (SASS DMMA.8x8x4) for the real and
+// as many for the imaginary part.  DMMA shares the fp64 pipe with DFMA on B200 (profiles/r2/
+// dmma_vs_dfma.txt: times add) but moves 20 % more FMAs through it, and the accumulation happens
+// inside the instruction: the scalar kernel's 2 x taps DFMA + 6 DADD per point (of ~38 fp64
+// instructions, the pipe that bounds it) become taps/2 DMMA per 64 points.
+//   A fragment (8 x 4, row m, column t):  lane holds c[m0 + lane/4 + 4 ks + lane%4]   (shared memory)
+//   B fragment (4 x 8, row t, column rho): lane holds h[4 ks + lane%4][rho0 + lane/4] (registers)
+//   C fragment (8 x 8): lane holds acc[m0 + lane/4][rho0 + 2 (lane%4) + {0, 1}]: two adjacent outputs,
+//                       stored as one 32-byte access when the row is 32-byte aligned.
+// A warp owns 8 phases and a run of L coarse positions; a CTA (4 warps) covers min(R, 32) phases
+// x 4 L / (min(R, 32) / 8) coarse positions = 32 L outputs.  Tap counts 10 and 14 are padded to 12 / 16
+// with zero weights.  Not part of the host-emulation build (warp-collective instruction): the
+// emulated tests run the scalar ExpandBody, which stays the fp32 engine's kernel and the fallback.
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+template <int TAPS, int EPI = EPI_STORE> struct ExpandMmaBody {
+  static constexpr int NTB = 128;
+  static constexpr int NT = NTB;
+  static constexpr int MINB = 4;
+  using V = double2;
+  using Args = ExpandArgs<double>;
+#ifndef CWTB_MMA_L
+#define CWTB_MMA_L 128
+#endif
+  static constexpr int L = CWTB_MMA_L;              // coarse positions per warp run (8 L outputs per warp)
+  static constexpr int KS = (TAPS + 3) / 4;         // k-steps of four taps
+  static constexpr int TP = 4 * KS;                 // padded tap count
+  static constexpr int OUT_PER_CTA = 32 * L;
+  static constexpr int STAGE = 4 * L + TP;          // staged coarse samples incl. halo (R = 8: 4 runs)
+  static constexpr int NPHASE = 2;
+  static constexpr size_t SMEM = (size_t)STAGE * sizeof(V);
+  template <int PH> __device__ static void phase(const Args &a, int bx, int by, int tid, void *smraw) {
+    V *sm = (V *)smraw;
+    const ScaleDesc &d = a.descs[a.first + by];
+    const int log2R = a.log2N - d.ip_log2Nc;
+    const int R = 1 << log2R;
+    const int Nc = 1 << d.ip_log2Nc;
+    const int wpb = (R < 32 ? R : 32) >> 3;         // warps side by side in rho: 1, 2 or 4
+    const int nrun = 4 / wpb;                       // runs of L coarse positions per CTA
+    const int MT = nrun * L;
+    const int mtiles = (Nc + MT - 1) / MT;
+    const int mt = bx % mtiles, rb = bx / mtiles;
+    if (rb * 32 >= R && rb > 0) return;             // short rows use the first tiles of the launch only
+    const int m0 = mt * MT;
+    if constexpr (PH == 0) {
+      const V *c = a.C + d.ip_coff;
+      for (int i = tid; i < MT + TP; i += NT) sm[i] = ldg(&c[(m0 - (TAPS / 2 - 1) + i) & (Nc - 1)]);
+    } else {
+      const int wid = tid >> 5, lane = tid & 31;
+      const int g = lane >> 2, q = lane & 3;
+      const int pb = wid % wpb, j = wid / wpb;
+      const int rho0 = rb * 32 + pb * 8;
+      const int ms = m0 + j * L;
+      double bf[KS];
+      const double *wt = a.wt + d.ip_woff + rho0 + g;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const int t = 4 * ks + q;
+        bf[ks] = t < TAPS ? ldg(&wt[(size_t)t * R]) : 0.0;
+      }
+      // re-modulation e^{2 pi i kc n / Np} of this lane's two outputs: table values for the first
+      // block of eight coarse positions, then three steps of e^{2 pi i kc 8 R / Np}
+      const unsigned kc = (unsigned)d.ip_kc;
+      const unsigned n00 = ((unsigned)(ms + g) << log2R) + (unsigned)(rho0 + 2 * q);
+      V tw0 = nroot(a.nt, kc * n00);
+      V tw1 = cmul(tw0, nroot(a.nt, kc));
+      const V step8 = nroot(a.nt, kc << (log2R + 3));
+      const V *run = sm + j * L + g + q;
+      V *rowp = a.W + (size_t)d.row * a.n0;
+      const bool wide = (((size_t)d.row * (size_t)a.n0) & 1) == 0;   // 32-byte aligned pairs
+#pragma unroll 4
+      for (int mb = 0; mb < L / 8; ++mb) {
+        if (ms + 8 * mb >= Nc) break;                 // warp-uniform: short coarse grids end inside the run
+        double cr0 = 0, cr1 = 0, ci0 = 0, ci1 = 0;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          const V s = run[8 * mb + 4 * ks];
+          dmma884(cr0, cr1, s.x, bf[ks]);
+          dmma884(ci0, ci1, s.y, bf[ks]);
+        }
+        const int m = ms + 8 * mb + g;
+        const long long n = ((long long)m << log2R) + rho0 + 2 * q;
+        V x0 = cmul(make_double2(cr0, ci0), tw0);
+        V x1 = cmul(make_double2(cr1, ci1), tw1);
+        tw0 = cmul(tw0, step8);
+        tw1 = cmul(tw1, step8);
+        if (m < Nc && n < a.n0) {
+          V *p = rowp + n;
+          const bool two = n + 1 < a.n0;
+          if (EPI == EPI_MULCONJ) {
+            x0 = cmul(p[0], cconj(x0));
+            if (two) x1 = cmul(p[1], cconj(x1));
+            p[0] = x0;
+            if (two) p[1] = x1;
+          } else if (wide && two) {
+            asm volatile("st.global.cs.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(x0.x), "d"(x0.y), "d"(x1.x), "d"(x1.y)
+                         : "memory");
+          } else {
+            st_stream(p, x0);
+            if (two) st_stream(p + 1, x1);
+          }
+        }
+      }
+    }
+  }
+};
+#endif
+
 // ---- Body: band product B[r] = x^[k] * conj(psi_ft) * norm / Np for pruned scales ------
 template <typename T> struct BandArgs {
   const ScaleDesc *descs;
