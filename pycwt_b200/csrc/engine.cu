@@ -447,27 +447,64 @@ static double kb_alias_bound(double xi_b, int w) {
   }
   return worst;
 }
-static const double kExpandXi[] = {1.0 / 16, 3.0 / 32, 1.0 / 8, 5.0 / 32, 3.0 / 16, 7.0 / 32, 1.0 / 4};
-static const int kExpandTaps64[] = {10, 12, 14, 16};
+// Buckets of the relative band half-width xi = (band half-width) / Nc and the tap counts tried for
+// them.  Beyond xi = 1/4 (coarse grid less than 2x oversampled) the kernel needs 16..20 taps for
+// the fp64 tolerance: affordable only where the tap sums run on the tensor cores (ExpandMmaBody),
+// `max_taps` says how far the caller may go (16 for the scalar kernels).  The buckets stop at 11/32:
+// the coarse spectrum is the band product divided by phi^(xi), and phi^(0) / phi^(xi_b) -- the factor by
+// which the rounding noise of the coarse transform can exceed the signal when the energy of the band
+// sits at its edge -- is 9 at xi_b = 1/4 (16 taps), 450 at 11/32 (20 taps), 1e4 at 3/8 (24 taps) and
+// 1e9 at 7/16 (32 taps; measured on the emulation: 4e-9 error for a Paul scale whose peak is
+// off-centre).  450 x 1e-16 stays below the alias tolerance for every signal.
+static const double kExpandXi[] = {1.0 / 16, 3.0 / 32, 1.0 / 8, 5.0 / 32, 3.0 / 16, 7.0 / 32, 1.0 / 4,
+                                   9.0 / 32, 5.0 / 16, 11.0 / 32};
+static const int kExpandBuckets = 10;
+static const int kExpandTaps64[] = {10, 12, 14, 16, 20};
 static const int kExpandTaps32[] = {6, 8, 10};
 
 // smallest tap count whose alias bound at the bucket of `xi` is <= eps; 0 if none.  *xi_b: bucket.
-static int expand_taps(double xi, double eps, bool f32, double *xi_b) {
+static int expand_taps(double xi, double eps, bool f32, int max_taps, double *xi_b) {
   static std::map<std::pair<int, int>, double> cache;   // (bucket, taps) -> bound
   int b = -1;
-  for (int i = 0; i < 7; ++i)
+  for (int i = 0; i < kExpandBuckets; ++i)
     if (xi <= kExpandXi[i] * (1 + 1e-12)) { b = i; break; }
   if (b < 0) return 0;
   *xi_b = kExpandXi[b];
   const int *taps = f32 ? kExpandTaps32 : kExpandTaps64;
-  const int ntaps = f32 ? 3 : 4;
-  for (int i = 0; i < ntaps; ++i) {
+  const int ntaps = f32 ? 3 : 5;
+  for (int i = 0; i < ntaps && taps[i] <= max_taps; ++i) {
     auto key = std::make_pair(b, taps[i]);
     auto it = cache.find(key);
     if (it == cache.end()) it = cache.emplace(key, kb_alias_bound(kExpandXi[b], taps[i])).first;
     if (it->second <= eps) return taps[i];
   }
   return 0;
+}
+
+// Dynamic-range check of a candidate (coarse length, taps) beyond xi_b = 1/4: the coarse spectrum is
+// the band product divided by phi^(xi); the rounding noise of the coarse transform, relative to the
+// largest coarse component, comes back multiplied by up to phi^(0).  Returns
+// max_k |psi^(k)| / max|psi^| * phi^(0) / phi^(xi_k) over the band: ~1 when the response peaks at the
+// band centre (Morlet, DOG), large when it peaks near an edge (Paul: one-sided band, peak at f = m).
+static double expand_gain(const Fam &fam, double s, long long klo, long long khi, long long kc, int log2Nc,
+                          int w, double beta) {
+  const double Nc = (double)(1ll << log2Nc);
+  double peak_amp = 0, worst = 0;
+  const double at_centre = beta / std::sinh(beta);
+  for (int pass = 0; pass < 2; ++pass)
+    for (int i = 0; i <= 256; ++i) {
+      const long long k = klo + (long long)std::llround((double)(khi - klo) * i / 256.0);
+      const double amp = std::fabs(amp_eval(fam, s, (int)k));
+      const double x = M_PI * w * ((double)(k - kc) / Nc);
+      const double z = std::sqrt(std::max(beta * beta - x * x, 1e-30));
+      const double inv_phi = z / std::sinh(z);          // 1 / phi^ up to a constant
+      if (pass == 0) {
+        if (amp > peak_amp) peak_amp = amp;
+      } else if (peak_amp > 0) {
+        worst = std::max(worst, (amp / peak_amp) * (inv_phi / at_centre));
+      }
+    }
+  return worst;
 }
 
 // weight table of one class: h[t][rho] = phi(rho / R - (t - (w/2 - 1))), t < w, rho < R (doubles,
@@ -610,15 +647,29 @@ static int build_job(cwtb_ctx *c, Job &job, long long n0, double dt, const doubl
     if (xeps > 0 && !job.exact && family != CWTB_TABLE && khi >= klo && job.log2N >= 9 && lk < job.log2N) {
       const long long kc = (klo + khi) / 2 - (((klo + khi) % 2 != 0 && (klo + khi) < 0) ? 1 : 0);   // floor
       const long long hw = std::max(khi - kc, kc - klo);
-      int lmin = std::max(6, ilog2((unsigned long long)std::max<long long>(4 * hw, 1)));
+      // the tensor-core kernel (fp64, Np >= 4096, every row expanding by 8 or more) makes 20 taps
+      // affordable: coarse grids down to 32/11 of the band half-width instead of 4x
+#ifdef CWTB_HOST_EMU
+      const bool mma = false;
+      const int max_taps = precision == CWTB_F64 ? 20 : 10;   // the emulated scalar kernel has every tap count
+#else
+      const bool mma = precision == CWTB_F64 && c->expand_mma && c->expand_min_log2R >= 3 && job.log2N >= 12;
+      const int max_taps = mma ? 20 : (precision == CWTB_F64 ? 16 : 10);
+#endif
+      const long long need = max_taps > 16 ? (32 * hw + 10) / 11 : 4 * hw;
+      int lmin = std::max(6, ilog2((unsigned long long)std::max<long long>(need, 1)));
       lmin = std::max(lmin, job.log2N - 14);          // weight tables of at most 2^14 phases
       double best = 1e300;
       for (int l = lmin; l <= lmin + 2 && job.log2N - l >= c->expand_min_log2R; ++l) {
         double xi_b = 0;
-        const int w = expand_taps((double)hw / (double)(1ll << l), xeps, precision != CWTB_F64, &xi_b);
+        const int w = expand_taps((double)hw / (double)(1ll << l), xeps, precision != CWTB_F64, max_taps, &xi_b);
         if (!w) continue;
-        // cost model (us at Np = 2^20): fp64 work of the expansion + the coarse transform
-        const double cost = 0.06 * (2 * w + 8) + 12.0 * (double)(1ll << l) / (double)N;
+        if (xi_b > 0.25 && expand_gain(fam, s, klo, khi, kc, l, w, M_PI * w * (1.0 - xi_b)) > 64.0) continue;
+        // cost model (us at Np = 2^20): the expansion kernel + the coarse transform.  Scalar kernel: its
+        // fp64 work; tensor-core kernel: the W store until the DMMA steps of four taps exceed it
+        // (measured, profiles/r2/sweep_r.txt: 2.72 us with three DMMA steps of four taps, 3.33 with four, 4.1 with five)
+        const double xcost = mma ? std::max(2.72, 0.83 * ((w + 3) / 4)) : 0.06 * (2 * w + 8);
+        const double cost = xcost + 12.0 * (double)(1ll << l) / (double)N;
         if (cost < best) {
           best = cost;
           d.ip_log2Nc = l; d.ip_kc = (int)kc; d.ip_w = w;
@@ -1296,6 +1347,7 @@ static int launch_expand_t(cwtb_ctx *c, const ExpandArgs<T> &a, int rows, int mi
 #ifndef CWTB_HOST_EMU
   // fp64: tap sums on the tensor cores (kernels.cuh: ExpandMmaBody) whenever every row expands by 8 or more
   if constexpr (std::is_same<T, double>::value) {
+    static_assert(ExpandMmaBody<TAPS>::OUT_PER_CTA == 4096, "the planner assumes the tensor-core kernel from Np = 2^12");
     if (c->expand_mma && c->expand_min_log2R >= 3 && a.N >= (unsigned)ExpandMmaBody<TAPS>::OUT_PER_CTA) {
       // tiles per row: N / (32 L); a row whose coarse grid is shorter than one run (Nc < L, R > 32) needs
       // one tile per 32 phases instead
@@ -1305,8 +1357,15 @@ static int launch_expand_t(cwtb_ctx *c, const ExpandArgs<T> &a, int rows, int mi
     }
   }
 #endif
-  if (a.epi == EPI_MULCONJ) return launch<ExpandBody<T, TAPS, EPI_MULCONJ>>(c, gx, rows, a);
-  return launch<B>(c, gx, rows, a);
+#ifndef CWTB_HOST_EMU
+  if constexpr (TAPS > 16) {
+    return fail(c, CWTB_ERR_STATE, "expansion: tap counts above 16 exist on the tensor-core kernel only");
+  } else
+#endif
+  {
+    if (a.epi == EPI_MULCONJ) return launch<ExpandBody<T, TAPS, EPI_MULCONJ>>(c, gx, rows, a);
+    return launch<B>(c, gx, rows, a);
+  }
 }
 template <typename T>
 static int launch_expand(cwtb_ctx *c, int taps, const ExpandArgs<T> &a, int rows, int min_log2Nc) {
@@ -1316,6 +1375,7 @@ static int launch_expand(cwtb_ctx *c, int taps, const ExpandArgs<T> &a, int rows
       case 12: return launch_expand_t<T, 12>(c, a, rows, min_log2Nc);
       case 14: return launch_expand_t<T, 14>(c, a, rows, min_log2Nc);
       case 16: return launch_expand_t<T, 16>(c, a, rows, min_log2Nc);
+      case 20: return launch_expand_t<T, 20>(c, a, rows, min_log2Nc);
     }
   } else {
     switch (taps) {
