@@ -187,6 +187,7 @@ struct cwtb_ctx {
   int num_sms = 148;
   int pf_dist = 148;   // PassB: L2 prefetch distance in tiles (CWTB_PF_DIST)
   int gauss_rec = 1;   // dense Morlet scales: Gaussian by recurrence (CWTB_GAUSS_REC=0: exp per bin)
+  int pf_rows_a = 32, pf_rows_b = 32;   // the same for the batched row transforms (CWTB_PF_ROWS_A / _B; wct 4.35 -> 4.25 ms)
   int pf_dist_a = 148;  // PassA (band): L2 prefetch distance in tiles (CWTB_PF_DIST_A)
   int k2_512_max_log2 = 16;  // largest K' that uses the 512-point second pass (CWTB_K2_512_MAX)
   int passb_rev = 1;    // second kernel walks the rows of a launch last-to-first (CWTB_PASSB_REV)
@@ -627,6 +628,7 @@ static int build_job(cwtb_ctx *c, Job &job, long long n0, double dt, const doubl
       lk = std::max(c->direct_max_log2 + 1, ilog2((unsigned long long)(hi - lo + 1)));
     }
     if (lk > 20) lk = job.log2N;   // pruned lengths above 2^20 are not built: treat as dense
+    const bool band_limited = lk < job.log2N;   // (before the promotion below: such a scale may still expand)
     // a pruned length of 2^18 or more within `dense_margin` octaves of the full one saves nothing
     // over the dense kernel pair (first kernels of 256 / 512 points cost what the 1024-point dense
     // one does once the band-product launch is counted): treat as dense (CWTB_DENSE_MARGIN)
@@ -644,7 +646,7 @@ static int build_job(cwtb_ctx *c, Job &job, long long n0, double dt, const doubl
     d.ip_log2Nc = 0; d.ip_kc = 0; d.ip_w = 0; d.ip_pad_ = 0; d.ip_coff = 0; d.ip_woff = 0;
     d.ip_beta = 0; d.ip_dc = 0;
     const double xeps = precision == CWTB_F64 ? c->expand_eps : c->expand_eps32;
-    if (xeps > 0 && !job.exact && family != CWTB_TABLE && khi >= klo && job.log2N >= 9 && lk < job.log2N) {
+    if (xeps > 0 && !job.exact && family != CWTB_TABLE && khi >= klo && job.log2N >= 9 && band_limited) {
       const long long kc = (klo + khi) / 2 - (((klo + khi) % 2 != 0 && (klo + khi) < 0) ? 1 : 0);   // floor
       const long long hw = std::max(khi - kc, kc - klo);
       // the tensor-core kernel (fp64, Np >= 4096, every row expanding by 8 or more) makes 20 taps
@@ -653,14 +655,18 @@ static int build_job(cwtb_ctx *c, Job &job, long long n0, double dt, const doubl
       const bool mma = false;
       const int max_taps = precision == CWTB_F64 ? 20 : 10;   // the emulated scalar kernel has every tap count
 #else
-      const bool mma = precision == CWTB_F64 && c->expand_mma && c->expand_min_log2R >= 3 && job.log2N >= 12;
+      const bool mma = precision == CWTB_F64 && c->expand_mma && job.log2N >= 12;
       const int max_taps = mma ? 20 : (precision == CWTB_F64 ? 16 : 10);
 #endif
       const long long need = max_taps > 16 ? (32 * hw + 10) / 11 : 4 * hw;
       int lmin = std::max(6, ilog2((unsigned long long)std::max<long long>(need, 1)));
       lmin = std::max(lmin, job.log2N - 14);          // weight tables of at most 2^14 phases
       double best = 1e300;
-      for (int l = lmin; l <= lmin + 2 && job.log2N - l >= c->expand_min_log2R; ++l) {
+      // smallest expansion factor: 8.  Both kernels also run R = 4 (CWTB_EXPAND_MIN_R=2), but the coarse
+      // transform of Np/4 points is a two-kernel one itself: measured no gain (config 2 1.480 -> 1.496 ms,
+      // xwt 1.00 -> 1.18 ms, profiles/r2/sweep_t_r4.txt)
+      const int min_log2R = c->expand_min_log2R;
+      for (int l = lmin; l <= lmin + 2 && job.log2N - l >= min_log2R; ++l) {
         double xi_b = 0;
         const int w = expand_taps((double)hw / (double)(1ll << l), xeps, precision != CWTB_F64, max_taps, &xi_b);
         if (!w) continue;
@@ -668,8 +674,9 @@ static int build_job(cwtb_ctx *c, Job &job, long long n0, double dt, const doubl
         // cost model (us at Np = 2^20): the expansion kernel + the coarse transform.  Scalar kernel: its
         // fp64 work; tensor-core kernel: the W store until the DMMA steps of four taps exceed it
         // (measured, profiles/r2/sweep_r.txt: 2.72 us with three DMMA steps of four taps, 3.33 with four, 4.1 with five)
-        const double xcost = mma ? std::max(2.72, 0.83 * ((w + 3) / 4)) : 0.06 * (2 * w + 8);
-        const double cost = xcost + 12.0 * (double)(1ll << l) / (double)N;
+        const int ksteps = job.log2N - l == 2 ? (w + 4) / 4 : (w + 3) / 4;   // R = 4 needs one more tap column
+        const double xcost = mma ? std::max(2.72, 0.83 * ksteps) : 0.06 * (2 * w + 8);
+        const double cost = xcost + (mma ? 18.0 : 12.0) * (double)(1ll << l) / (double)N;
         if (cost < best) {
           best = cost;
           d.ip_log2Nc = l; d.ip_kc = (int)kc; d.ip_w = w;
@@ -803,6 +810,7 @@ static int two_kernel_rows(cwtb_ctx *c, const void *in, int real_in, long long i
     a.in = in; a.Z = (cx<T> *)Zt.p; a.tw = Tw<T>::get(c); a.nt = nt;
     a.in_pitch = in_pitch; a.n_in = n_in; a.N = n; a.first = 0; a.zmod = 1 << 30; a.K2 = K2C;
     a.row0 = (ileave > 1 ? 0 : out_row0) + r0;   // interleaved input rows are numbered from 0
+    a.pf_dist = c->pf_rows_a;
     e = real_in ? dispatch_passA<T, SIGN, MODE_REAL>(c, l2 - 10, a, nr)
                 : dispatch_passA<T, SIGN, MODE_CPLX>(c, l2 - 10, a, nr);
     if (e) return e;
@@ -810,7 +818,7 @@ static int two_kernel_rows(cwtb_ctx *c, const void *in, int real_in, long long i
     b.Z = (const cx<T> *)Zt.p; b.out = out; b.tw = Tw<T>::get(c); b.descs = descs;
     b.pitch = out_pitch; b.nout = nout; b.N = n; b.first = first;
     b.epi = grow ? EPI_GAUSS : epi; b.grow = grow; b.post = post; b.zmod = 1 << 30;
-    b.pf_dist = 0; b.ny = nr; b.ileave = ileave; b.rev = c->passb_rev;
+    b.pf_dist = c->pf_rows_b; b.ny = nr; b.ileave = ileave; b.rev = c->passb_rev;
     if (ileave > 1) { b.row0 = out_row0; b.by0 = r0; } else { b.row0 = out_row0 + r0; b.by0 = 0; }
     e = launch<PassBBody<T, SIGN>>(c, (n / K2C + Lay<T, K2C>::P - 1) / Lay<T, K2C>::P, nr, b);
     if (e) return e;
@@ -1348,7 +1356,7 @@ static int launch_expand_t(cwtb_ctx *c, const ExpandArgs<T> &a, int rows, int mi
   // fp64: tap sums on the tensor cores (kernels.cuh: ExpandMmaBody) whenever every row expands by 8 or more
   if constexpr (std::is_same<T, double>::value) {
     static_assert(ExpandMmaBody<TAPS>::OUT_PER_CTA == 4096, "the planner assumes the tensor-core kernel from Np = 2^12");
-    if (c->expand_mma && c->expand_min_log2R >= 3 && a.N >= (unsigned)ExpandMmaBody<TAPS>::OUT_PER_CTA) {
+    if (c->expand_mma && a.N >= (unsigned)ExpandMmaBody<TAPS>::OUT_PER_CTA) {
       // tiles per row: N / (32 L); a row whose coarse grid is shorter than one run (Nc < L, R > 32) needs
       // one tile per 32 phases instead
       const unsigned gm = a.N / (32u * std::min<unsigned>(ExpandMmaBody<TAPS>::L, 1u << min_log2Nc));
@@ -1789,6 +1797,8 @@ int cwtb_create(int device, cwtb_ctx **out) {
   if (const char *g = getenv("CWTB_PF_DIST")) c->pf_dist = std::max(0, atoi(g));
   if (const char *g = getenv("CWTB_CHAINS")) c->n_chains = std::min(4, std::max(1, atoi(g)));
   if (const char *g = getenv("CWTB_FFT_PAD")) c->pad_pow2 = atoi(g) != 0;
+  if (const char *g = getenv("CWTB_PF_ROWS_A")) c->pf_rows_a = std::max(0, atoi(g));
+  if (const char *g = getenv("CWTB_PF_ROWS_B")) c->pf_rows_b = std::max(0, atoi(g));
   if (const char *g = getenv("CWTB_PF_DIST_A")) c->pf_dist_a = std::max(0, atoi(g));
   if (const char *g = getenv("CWTB_K2_BAND")) c->k2_band_log2 = atoi(g) == 10 ? 10 : 9;
   if (const char *g = getenv("CWTB_K2_512_MAX")) c->k2_512_max_log2 = std::min(19, atoi(g));

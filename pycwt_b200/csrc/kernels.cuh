@@ -592,6 +592,17 @@ template <typename T, int K1, int MODE, int SIGN> struct PassABody {
             TileBarrier::prefetch_l2(base + (size_t)pos * a.K2, (unsigned)(T2 * sizeof(V)));
         }
       }
+      // the same for the rows of a batched row transform (coherence smoothing, coarse transforms): the
+      // tile `pf_dist` blocks ahead of this one in the same row
+      if (MODE == MODE_CPLX && a.pf_dist > 0 && T2 * sizeof(V) >= 256) {
+        const int t = bx + a.pf_dist;
+        if (t < M * NTILE2) {
+          const V *row = (const V *)a.in + (size_t)(a.row0 + by) * a.in_pitch + (t % NTILE2) * T2;
+          for (int pos = tid; pos < K1; pos += NT)
+            if ((long long)pos * a.K2 + (t % NTILE2) * T2 + T2 <= a.n_in)
+              TileBarrier::prefetch_l2(row + (size_t)pos * a.K2, (unsigned)(T2 * sizeof(V)));
+        }
+      }
       if (MODE == MODE_DENSE && a.fam.family == 0 && a.gauss_rec && T2 <= NT) {
         // Morlet, dense scale: a thread's bins are k0, k0 + D, k0 + 2D, ... (D = (NT/T2)*K2), so
         //   g(k + D) = g(k) * rho(k),  rho(k + D) = rho(k) * exp(-a^2),  a = s * w_D,
@@ -842,15 +853,19 @@ template <typename T, int TAPS, int EPI = EPI_STORE> struct ExpandBody {
       for (int s = 0; s < L; ++s) {
         win[(s + TAPS - 1) % TAPS] = run[(s + TAPS - 1) + ((s + TAPS - 1) >> 5)];
         if (s % RESEED == 0) tw = nroot_t<T>(a.nt, kc * (nlo + ((unsigned)s << log2R)));
-        // 8 independent chains (4 per component): the fp64 pipe needs that much parallelism per warp
+        // 8 independent chains (4 per component): the fp64 pipe needs that much parallelism per warp;
+        // the fp32 kernel is bound by instruction issue (ncu: 70 % issue slots busy, 49 instructions per
+        // point for 24 useful ones) and runs two chains per component
+        constexpr int NCH = sizeof(T) == 8 ? 4 : 2;
         T ar[4] = {0, 0, 0, 0}, ai[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int t = 0; t < TAPS; ++t) {
           const V cv = win[(s + t) % TAPS];
-          ar[t & 3] += cv.x * hw[t];
-          ai[t & 3] += cv.y * hw[t];
+          ar[t & (NCH - 1)] += cv.x * hw[t];
+          ai[t & (NCH - 1)] += cv.y * hw[t];
         }
-        const V acc = mk<T>((ar[0] + ar[1]) + (ar[2] + ar[3]), (ai[0] + ai[1]) + (ai[2] + ai[3]));
+        const V acc = NCH == 4 ? mk<T>((ar[0] + ar[1]) + (ar[2] + ar[3]), (ai[0] + ai[1]) + (ai[2] + ai[3]))
+                               : mk<T>(ar[0] + ar[1], ai[0] + ai[1]);
         const V x = cmul(acc, tw);
         tw = cmul(tw, stepw);
         if (s < smax) {
@@ -895,66 +910,80 @@ template <int TAPS, int EPI = EPI_STORE> struct ExpandMmaBody {
 #endif
   static constexpr int L = CWTB_MMA_L;              // coarse positions per warp run (8 L outputs per warp)
   static constexpr int KS = (TAPS + 3) / 4;         // k-steps of four taps
-  static constexpr int TP = 4 * KS;                 // padded tap count
+  static constexpr int KS4 = (TAPS + 4) / 4;        // R = 4: one more tap column (see body<.., true>)
   static constexpr int OUT_PER_CTA = 32 * L;
-  static constexpr int STAGE = 4 * L + TP;          // staged coarse samples incl. halo (R = 8: 4 runs)
+  static constexpr int STAGE = 8 * L + 4 * KS4;     // staged coarse samples incl. halo (R = 4: 4 runs of 2 L)
   static constexpr int NPHASE = 2;
   static constexpr size_t SMEM = (size_t)STAGE * sizeof(V);
   template <int PH> __device__ static void phase(const Args &a, int bx, int by, int tid, void *smraw) {
-    V *sm = (V *)smraw;
     const ScaleDesc &d = a.descs[a.first + by];
+    if (a.log2N - d.ip_log2Nc == 2) body<PH, true>(a, d, bx, tid, (V *)smraw);
+    else body<PH, false>(a, d, bx, tid, (V *)smraw);
+  }
+  // R4 = false (R >= 8): MMA rows = 8 consecutive coarse positions, columns = 8 consecutive phases.
+  // R4 = true  (R == 4): the 8 columns are 2 coarse positions x 4 phases, the rows step by two coarse
+  //   positions: acc[m0 + 2 i + dm][rho] = sum_t' c[m0 + 2 i + t' - (taps/2 - 1)] * h[t' - dm][rho],
+  //   t' < taps + 1 (B holds the weights shifted by dm, zero outside).  A warp then covers 16 coarse
+  //   positions per MMA block and runs over 2 L of them: the same 8 L outputs per warp.
+  template <int PH, bool R4>
+  __device__ static void body(const Args &a, const ScaleDesc &d, int bx, int tid, V *sm) {
+    constexpr int KSr = R4 ? KS4 : KS;
+    constexpr int Lr = R4 ? 2 * L : L;              // coarse positions per warp run
+    constexpr int MB = R4 ? 16 : 8;                 // coarse positions per MMA block
     const int log2R = a.log2N - d.ip_log2Nc;
     const int R = 1 << log2R;
     const int Nc = 1 << d.ip_log2Nc;
-    const int wpb = (R < 32 ? R : 32) >> 3;         // warps side by side in rho: 1, 2 or 4
-    const int nrun = 4 / wpb;                       // runs of L coarse positions per CTA
-    const int MT = nrun * L;
+    const int wpb = R4 ? 1 : ((R < 32 ? R : 32) >> 3);   // warps side by side in rho: 1, 2 or 4
+    const int nrun = 4 / wpb;                       // runs per CTA
+    const int MT = nrun * Lr;
     const int mtiles = (Nc + MT - 1) / MT;
     const int mt = bx % mtiles, rb = bx / mtiles;
     if (rb * 32 >= R && rb > 0) return;             // short rows use the first tiles of the launch only
     const int m0 = mt * MT;
     if constexpr (PH == 0) {
       const V *c = a.C + d.ip_coff;
-      for (int i = tid; i < MT + TP; i += NT) sm[i] = ldg(&c[(m0 - (TAPS / 2 - 1) + i) & (Nc - 1)]);
+      for (int i = tid; i < MT + 4 * KSr; i += NT) sm[i] = ldg(&c[(m0 - (TAPS / 2 - 1) + i) & (Nc - 1)]);
     } else {
       const int wid = tid >> 5, lane = tid & 31;
       const int g = lane >> 2, q = lane & 3;
       const int pb = wid % wpb, j = wid / wpb;
-      const int rho0 = rb * 32 + pb * 8;
-      const int ms = m0 + j * L;
-      double bf[KS];
-      const double *wt = a.wt + d.ip_woff + rho0 + g;
+      const int rho0 = R4 ? 0 : rb * 32 + pb * 8;
+      const int ms = m0 + j * Lr;
+      double bf[KSr];
 #pragma unroll
-      for (int ks = 0; ks < KS; ++ks) {
-        const int t = 4 * ks + q;
-        bf[ks] = t < TAPS ? ldg(&wt[(size_t)t * R]) : 0.0;
+      for (int ks = 0; ks < KSr; ++ks) {
+        const int t = 4 * ks + q - (R4 ? (g >> 2) : 0);
+        const int rho = R4 ? (g & 3) : rho0 + g;
+        bf[ks] = (t >= 0 && t < TAPS) ? ldg(&a.wt[d.ip_woff + (size_t)t * R + rho]) : 0.0;
       }
       // re-modulation e^{2 pi i kc n / Np} of this lane's two outputs: table values for the first
-      // block of eight coarse positions, then three steps of e^{2 pi i kc 8 R / Np}
+      // block, then steps of e^{2 pi i kc 64 / Np ... } = one MMA block of coarse positions further
       const unsigned kc = (unsigned)d.ip_kc;
-      const unsigned n00 = ((unsigned)(ms + g) << log2R) + (unsigned)(rho0 + 2 * q);
+      const int mlane = R4 ? 2 * g + (q >> 1) : g;              // coarse position of this lane inside a block
+      const int rlane = R4 ? 2 * (q & 1) : rho0 + 2 * q;        // first of its two adjacent phases
+      const unsigned n00 = ((unsigned)(ms + mlane) << log2R) + (unsigned)rlane;
       V tw0 = nroot(a.nt, kc * n00);
       V tw1 = cmul(tw0, nroot(a.nt, kc));
-      const V step8 = nroot(a.nt, kc << (log2R + 3));
-      const V *run = sm + j * L + g + q;
+      const V stepb = nroot(a.nt, (kc * (unsigned)MB) << log2R);
+      const V *run = sm + j * Lr + (R4 ? 2 * g : g) + q;
       V *rowp = a.W + (size_t)d.row * a.n0;
       const bool wide = (((size_t)d.row * (size_t)a.n0) & 1) == 0;   // 32-byte aligned pairs
 #pragma unroll 4
-      for (int mb = 0; mb < L / 8; ++mb) {
-        if (ms + 8 * mb >= Nc) break;                 // warp-uniform: short coarse grids end inside the run
+      for (int mb = 0; mb < Lr / MB; ++mb) {
+        if (ms + MB * mb >= Nc) break;                // warp-uniform: short coarse grids end inside the run
         double cr0 = 0, cr1 = 0, ci0 = 0, ci1 = 0;
 #pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-          const V s = run[8 * mb + 4 * ks];
+        for (int ks = 0; ks < KSr; ++ks) {
+          const V s = run[MB * mb + 4 * ks];
           dmma884(cr0, cr1, s.x, bf[ks]);
           dmma884(ci0, ci1, s.y, bf[ks]);
         }
-        const int m = ms + 8 * mb + g;
-        const long long n = ((long long)m << log2R) + rho0 + 2 * q;
+        const int m = ms + MB * mb + mlane;
+        const long long n = ((long long)m << log2R) + rlane;
         V x0 = cmul(make_double2(cr0, ci0), tw0);
         V x1 = cmul(make_double2(cr1, ci1), tw1);
-        tw0 = cmul(tw0, step8);
-        tw1 = cmul(tw1, step8);
+        tw0 = cmul(tw0, stepb);
+        tw1 = cmul(tw1, stepb);
         if (m < Nc && n < a.n0) {
           V *p = rowp + n;
           const bool two = n + 1 < a.n0;

@@ -359,3 +359,25 @@ def test_overlapped_fetch_equals_plain_fetch(pycwt):
     W3 = eng.cwt(x, 1.0, sj[perm], 0, 6.0)
     assert np.array_equal(W3, W1[perm])
     assert eng.last_kernel_ms() > 0
+
+
+def test_expansion_by_four(monkeypatch):
+    """R = Np/Nc = 4 is off by default (no gain); both expansion kernels implement it
+    (CWTB_EXPAND_MIN_R=2): the tensor-core kernel's 2-positions-by-4-phases column layout and the
+    scalar kernel must give the same coefficients as the oracle."""
+    from pycwt_b200 import _engine
+    n = 2 ** 14
+    x = chirp(n) + 0.1 * np.random.RandomState(4).randn(n)
+    sj = 2.0 * 2 ** (np.arange(8, 40) / 4.0)
+    Wr = orc.cwt(x, 1.0, wavelet=orc.Morlet(6), freqs=1 / (orc.Morlet(6).flambda() * sj))[0]
+    monkeypatch.setenv("CWTB_EXPAND_MIN_R", "2")
+    for mma in ("1", "0"):
+        monkeypatch.setenv("CWTB_EXPAND_MMA", mma)
+        eng = _engine.Engine(0)
+        try:
+            W = eng.cwt(x, 1.0, sj, _engine.MORLET, 6.0)
+            plan = eng.last_plan(len(sj))
+            assert -12 in plan, plan          # coarse grids of Np/4 points are in play
+            assert relerr(W, Wr) < TOL64, (mma, relerr(W, Wr))
+        finally:
+            eng.close()
