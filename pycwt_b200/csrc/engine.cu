@@ -206,6 +206,28 @@ struct cwtb_ctx {
   size_t wtab_uploaded = 0;      // elements already on the device
   Buf ctr, sig, sig2, spec, Z, Zc[3], Y, B, W, W2, descs, table, scratch, C, A12, F, aux, rowd, win, mask, hist, noise, wide, blueA, blueX, blueY;
   Job job;
+  // what the resident plan (job + uploaded descriptors) was built from: a call with the same
+  // geometry and settings reuses it (planning + descriptor upload: ~0.3 ms for 256 scales, several ms
+  // for the 8192 rows of a batch chunk)
+  struct PlanKey {
+    long long n0 = -1;
+    double dt = 0, param = 0, band_eps = 0, band_eps32 = 0, expand_eps = 0, expand_eps32 = 0;
+    int S = 0, family = 0, precision = 0, nbatch = 0, pad = 0;
+    std::vector<double> scales;
+    bool operator==(const PlanKey &o) const {
+      return n0 == o.n0 && dt == o.dt && param == o.param && band_eps == o.band_eps && band_eps32 == o.band_eps32 &&
+             expand_eps == o.expand_eps && expand_eps32 == o.expand_eps32 && S == o.S && family == o.family &&
+             precision == o.precision && nbatch == o.nbatch && pad == o.pad && scales == o.scales;
+    }
+  } plan_key;
+  int plan_reuse = 1;            // CWTB_PLAN_REUSE=0: plan every call
+  // cwtb_cwt_batch pipeline: two page-locked staging buffers and two device input buffers so that the
+  // host copy and the H2D of chunk k+1 overlap the kernels of chunk k; per-row power of every chunk is
+  // accumulated on the device and read back once
+  void *stage_host[2] = {nullptr, nullptr};
+  size_t stage_bytes = 0;
+  Buf stage_dev[2], batch_power;
+  int batch_pipeline = 1;        // CWTB_BATCH_PIPELINE=0: one synchronous chunk after the other
   const void *job_dsig = nullptr;  // device signal of the last cwt_dev call (not owned)
   double last_ms = 0;
   int launches = 0;
@@ -225,6 +247,7 @@ struct cwtb_ctx {
 #ifndef CWTB_HOST_EMU
   cudaEvent_t e0{}, e1{};
   cudaEvent_t ev_fork{}, ev_join{}, ev_joinc[3]{}, ev_coarse{};
+  cudaEvent_t ev_h2d[2]{}, ev_used[2]{};
 #endif
 };
 
@@ -1773,6 +1796,9 @@ int cwtb_create(int device, cwtb_ctx **out) {
     cudaStreamCreateWithPriority(&c->prio_stream, cudaStreamNonBlocking, hi);
   }
   cudaEventCreateWithFlags(&c->ev_coarse, cudaEventDisableTiming);
+  for (auto &ev : c->ev_h2d) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+  for (auto &ev : c->ev_used) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+  if (const char *g = getenv("CWTB_BATCH_PIPELINE")) c->batch_pipeline = atoi(g) != 0;
   if (const char *g = getenv("CWTB_PRIO")) c->prio_mode = std::min(2, std::max(0, atoi(g)));
   for (auto &st : c->chain_streams) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
   for (auto &ev : c->ev_joinc) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
@@ -1791,6 +1817,7 @@ int cwtb_create(int device, cwtb_ctx **out) {
   if (const char *g = getenv("CWTB_EXPAND_EPS32")) c->expand_eps32 = std::max(0.0, atof(g));
   if (const char *g = getenv("CWTB_EXPAND_MIN_R")) c->expand_min_log2R = std::min(14, std::max(2, atoi(g)));
   if (const char *g = getenv("CWTB_EXPAND_MMA")) c->expand_mma = atoi(g) != 0;
+  if (const char *g = getenv("CWTB_PLAN_REUSE")) c->plan_reuse = atoi(g) != 0;
   if (const char *g = getenv("CWTB_DENSE_MARGIN")) c->dense_margin = std::max(0, atoi(g));
   if (const char *g = getenv("CWTB_L2_PERSIST")) c->l2_persist = atoi(g);
   if (const char *g = getenv("CWTB_FUSED")) c->fused = atoi(g);
@@ -1826,7 +1853,7 @@ void cwtb_destroy(cwtb_ctx *c) {
   cudaStreamSynchronize(c->stream);
 #endif
   cwtb_comm_destroy(c);
-  for (Buf *b : {&c->filt, &c->comm_send, &c->comm_recv, &c->Zx, &c->Cin, &c->Cout, &c->wtab, &c->ctr, &c->sig, &c->sig2, &c->spec, &c->Z, &c->Zc[0], &c->Zc[1], &c->Zc[2], &c->Y, &c->B, &c->W, &c->W2, &c->descs, &c->table, &c->scratch,
+  for (Buf *b : {&c->stage_dev[0], &c->stage_dev[1], &c->batch_power, &c->filt, &c->comm_send, &c->comm_recv, &c->Zx, &c->Cin, &c->Cout, &c->wtab, &c->ctr, &c->sig, &c->sig2, &c->spec, &c->Z, &c->Zc[0], &c->Zc[1], &c->Zc[2], &c->Y, &c->B, &c->W, &c->W2, &c->descs, &c->table, &c->scratch,
                  &c->C, &c->A12, &c->F, &c->aux, &c->rowd, &c->win, &c->mask, &c->hist, &c->noise, &c->wide, &c->blueA, &c->blueX, &c->blueY})
     if (b->p) rt_free(b->p);
   for (auto &kv : c->ntabs) { rt_free(kv.second.hi); rt_free(kv.second.lo); }
@@ -1843,6 +1870,9 @@ void cwtb_destroy(cwtb_ctx *c) {
   cudaStreamDestroy(c->aux_stream);
   cudaStreamDestroy(c->prio_stream);
   cudaEventDestroy(c->ev_coarse);
+  for (auto &ev : c->ev_h2d) cudaEventDestroy(ev);
+  for (auto &ev : c->ev_used) cudaEventDestroy(ev);
+  for (void *p : c->stage_host) if (p) cudaFreeHost(p);
   for (auto &st : c->chain_streams) cudaStreamDestroy(st);
   for (auto &ev : c->ev_joinc) cudaEventDestroy(ev);
   cudaEventDestroy(c->ev_fork);
@@ -1916,6 +1946,13 @@ static int prepare(cwtb_ctx *c, long long n0, double dt, const double *scales, i
 #endif
   if (nbatch < 1 || (long long)nbatch * S > 60000) return fail(c, CWTB_ERR_ARG, "batch too large for one launch");
   ++c->serial;   // whatever was resident is about to be replaced
+  cwtb_ctx::PlanKey key;
+  key.n0 = n0; key.dt = dt; key.param = param; key.band_eps = c->band_eps; key.band_eps32 = c->band_eps32;
+  key.expand_eps = c->expand_eps; key.expand_eps32 = c->expand_eps32; key.S = S; key.family = family;
+  key.precision = precision; key.nbatch = nbatch; key.pad = c->pad_pow2;
+  key.scales.assign(scales, scales + std::max(S, 0));
+  if (c->plan_reuse && family != CWTB_TABLE && c->job.valid && key == c->plan_key) return 0;
+  c->plan_key = cwtb_ctx::PlanKey();   // invalid until the new plan is complete
   int e = build_job(c, c->job, n0, dt, scales, S, family, param, precision, table != nullptr, nbatch);
   if (e) return e;
   if (family == CWTB_TABLE) {
@@ -1923,7 +1960,9 @@ static int prepare(cwtb_ctx *c, long long n0, double dt, const double *scales, i
     if ((e = ensure(c, c->table, bytes))) return e;
     RT(rt_h2d(c->table.p, table, bytes, c->stream));
   }
-  return upload_descs(c, c->job);
+  if ((e = upload_descs(c, c->job))) return e;
+  if (family != CWTB_TABLE) c->plan_key = std::move(key);
+  return 0;
 }
 
 int cwtb_cwt_dev(cwtb_ctx *c, const void *d_signal, int signal_is_f32, int64_t n0, double dt,
@@ -2717,6 +2756,89 @@ int cwtb_profile_end(cwtb_ctx *c, char *out, size_t cap) {
 
 // Batched transform of independent channels: chunks of channels share every kernel launch
 // (one descriptor row per (channel, scale)).  X: host [n_chan][n0].
+#ifndef CWTB_HOST_EMU
+// Per-row sums of |W|^2 of the resident chunk into dsum (device, R doubles, zeroed by the caller), on
+// the engine's stream, no synchronisation.
+static int launch_row_power(cwtb_ctx *c, double *dsum) {
+  const Job &job = c->job;
+  const int R = job.S * job.nbatch;
+  const unsigned gx = (unsigned)((job.n0 + PowerBody<double>::PER * NT - 1) / (PowerBody<double>::PER * NT));
+  if (job.precision == CWTB_F64) {
+    PowerArgs<double> a{(const double2 *)c->W.p, nullptr, dsum, job.n0, nullptr, nullptr, nullptr};
+    return launch<PowerBody<double>>(c, gx, R, a);
+  }
+  PowerArgs<float> a{(const float2 *)c->W.p, nullptr, dsum, job.n0, nullptr, nullptr, nullptr};
+  return launch<PowerBody<float>>(c, gx, R, a);
+}
+
+// Spectra-only batch: chunk k+1 is copied into page-locked memory and sent to the device while the
+// kernels of chunk k run; nothing synchronises until the per-row power of all chunks is read back.
+static int cwt_batch_pipelined(cwtb_ctx *c, const void *X, int x_is_f32, int n_chan, int64_t n0, double dt,
+                               const double *scales, int n_scales, int family, double param, int precision,
+                               double *power_out, int nb) {
+  const bool f32 = (precision == CWTB_F32);
+  const size_t esz_in = x_is_f32 ? 4 : 8, esz = f32 ? 4 : 8;
+  const size_t chunk_bytes = (size_t)nb * n0 * esz;
+  int e;
+  if (c->stage_bytes < chunk_bytes) {
+    RT(rt_sync(c->stream));
+    for (auto &p : c->stage_host) {
+      if (p) RT(cudaFreeHost(p));
+      p = nullptr;
+      RT(cudaHostAlloc(&p, chunk_bytes, cudaHostAllocDefault));
+    }
+    c->stage_bytes = chunk_bytes;
+  }
+  for (auto &b : c->stage_dev)
+    if ((e = ensure(c, b, chunk_bytes))) return e;
+  if ((e = ensure(c, c->batch_power, (size_t)n_chan * n_scales * sizeof(double)))) return e;
+  double *dpow = (double *)c->batch_power.p;
+  rt_stream copy = c->copy_streams[0];
+  RT(rt_memset(dpow, 0, (size_t)n_chan * n_scales * sizeof(double), c->stream));
+  c->launches = 0;
+  bool timing = false;
+  int k = 0;
+  for (int ch0 = 0; ch0 < n_chan; ch0 += nb, ++k) {
+    const int nc = std::min(nb, n_chan - ch0), slot = k & 1;
+    // (re-plans only when the chunk geometry changes: first and a shorter last chunk)
+    if ((e = prepare(c, n0, dt, scales, n_scales, family, param, precision, nullptr, nc))) return e;
+    if (!timing) { RT(cudaEventRecord(c->e0, c->stream)); timing = true; }
+    const char *src = (const char *)X + (size_t)ch0 * n0 * esz_in;
+    const size_t cnt = (size_t)nc * n0;
+    const void *from = src;
+    if ((x_is_f32 != 0) != f32) {   // conversion: through the page-locked staging buffer
+      if (k >= 2) RT(cudaEventSynchronize(c->ev_h2d[slot]));   // the staging buffer is free again
+      if (f32) for (size_t i = 0; i < cnt; ++i) ((float *)c->stage_host[slot])[i] = (float)((const double *)src)[i];
+      else for (size_t i = 0; i < cnt; ++i) ((double *)c->stage_host[slot])[i] = (double)((const float *)src)[i];
+      from = c->stage_host[slot];
+    }
+    // (input of the engine's type: straight from the caller's pageable array -- the driver's own staged
+    // copy is faster than a host memcpy into page-locked memory plus a DMA, and while it blocks this
+    // thread the kernels of the previous chunk keep running)
+    if (k >= 2) RT(cudaStreamWaitEvent(copy, c->ev_used[slot], 0));   // chunk k-2 has consumed this device buffer
+    RT(cudaMemcpyAsync(c->stage_dev[slot].p, from, cnt * esz, cudaMemcpyHostToDevice, copy));
+    RT(cudaEventRecord(c->ev_h2d[slot], copy));
+    RT(cudaStreamWaitEvent(c->stream, c->ev_h2d[slot], 0));
+    c->job_dsig = c->stage_dev[slot].p;
+    c->job.sig_is_f32 = f32;
+    e = f32 ? run_job<float>(c, c->job, (const float *)c->stage_dev[slot].p)
+            : run_job<double>(c, c->job, (const double *)c->stage_dev[slot].p);
+    if (e) return e;
+    if ((e = launch_row_power(c, dpow + (size_t)ch0 * n_scales))) return e;
+    RT(cudaEventRecord(c->ev_used[slot], c->stream));
+  }
+  RT(cudaEventRecord(c->e1, c->stream));
+  RT(rt_d2h(power_out, dpow, (size_t)n_chan * n_scales * sizeof(double), c->stream));
+  RT(rt_sync(c->stream));
+  RT(rt_sync(copy));
+  float ms = 0;
+  RT(cudaEventElapsedTime(&ms, c->e0, c->e1));
+  c->last_ms = ms;
+  for (size_t i = 0; i < (size_t)n_chan * n_scales; ++i) power_out[i] /= (double)n0;
+  return 0;
+}
+#endif
+
 int cwtb_cwt_batch(cwtb_ctx *c, const void *X, int x_is_f32, int n_chan, int64_t n0, double dt,
                    const double *scales, int n_scales, int family, double param, int precision,
                    double *power_out, void *W_out) {
@@ -2729,6 +2851,10 @@ int cwtb_cwt_batch(cwtb_ctx *c, const void *X, int x_is_f32, int n_chan, int64_t
   size_t per_chan = wrow * n_scales;
   int nb = (int)std::max<size_t>(1, std::min<size_t>(c->batch_bytes / std::max<size_t>(per_chan, 1), 32768 / n_scales));
   nb = std::max(1, std::min(nb, n_chan));
+#ifndef CWTB_HOST_EMU
+  if (c->batch_pipeline && power_out && !W_out && (c->pad_pow2 || (n0 & (n0 - 1)) == 0))
+    return cwt_batch_pipelined(c, X, x_is_f32, n_chan, n0, dt, scales, n_scales, family, param, precision, power_out, nb);
+#endif
   std::vector<unsigned char> conv;
   for (int ch0 = 0; ch0 < n_chan; ch0 += nb) {
     const int nc = std::min(nb, n_chan - ch0);

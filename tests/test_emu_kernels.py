@@ -408,3 +408,39 @@ def test_generic_smoothing_for_paul_and_dog(emu):
         check_generic_smoothing(pycwt)
     finally:
         _engine.default_engine = saved
+
+
+def test_plan_reuse_and_invalidation(emu):
+    """A call with the geometry of the resident plan reuses it (no re-planning, no descriptor
+    upload); any change of geometry or tolerance builds a new one.  Results must not depend on
+    which of the two happened."""
+    rs = np.random.RandomState(12)
+    n = 3000
+    sj = 2.0 * 2 ** (np.arange(30) / 4.0)
+    m = orc.Morlet(6)
+
+    def ref(x, s):
+        return orc.cwt(x, 1.0, wavelet=m, freqs=1 / (m.flambda() * s))[0]
+
+    x1, x2 = rs.randn(n), rs.randn(n).cumsum()
+    W1 = emu.cwt(x1, 1.0, sj, 0, 6.0)
+    p1 = emu.last_plan(len(sj))
+    W2 = emu.cwt(x2, 1.0, sj, 0, 6.0)                    # same plan, other signal
+    assert emu.last_plan(len(sj)) == p1
+    assert relerr(W1, ref(x1, sj)) < 1e-10 and relerr(W2, ref(x2, sj)) < 1e-10
+    W3 = emu.cwt(x2, 1.0, sj[::-1].copy(), 0, 6.0)       # same values, other order: a different plan
+    assert relerr(W3, ref(x2, sj[::-1])) < 1e-10
+    W4 = emu.cwt(x2[:2999], 1.0, sj, 0, 6.0)             # other length
+    assert W4.shape == (30, 2999) and relerr(W4, ref(x2[:2999], sj)) < 1e-10
+    emu.set_expand_eps(0.0, 0.0)                          # same geometry, expansion off: must re-plan
+    try:
+        W5 = emu.cwt(x2[:2999], 1.0, sj, 0, 6.0)
+        assert min(emu.last_plan(len(sj))) > 0
+    finally:
+        emu.set_expand_eps()
+    assert relerr(W5, ref(x2[:2999], sj)) < 1e-10
+    W6 = emu.cwt(x2[:2999], 1.0, sj, 0, 6.0)             # back to the default tolerances
+    assert min(emu.last_plan(len(sj))) < 0 and relerr(W6, W4) < 1e-13
+    W7 = emu.cwt(x2[:2999], 1.0, sj, 1, 4.0)             # other wavelet family, same scales
+    W7r = orc.cwt(x2[:2999], 1.0, wavelet=orc.Paul(4), freqs=1 / (orc.Paul(4).flambda() * sj[:20]))[0]
+    assert W7r.shape[0] == 20 and relerr(W7[:20], W7r) < 1e-10   # (the largest scales are NaN rows for Paul)
