@@ -13,3 +13,4 @@ for k,v in d['configs'].items():
 PY
 timeout 300 $T bench.py --impl reference --gpus 2 --steps 1 --warmup 0 | cut -c1-300
 timeout 600 $T profiles/config4_mc_multi_gpu.py 2>&1 | grep -v Warn | tail -6
+timeout 600 $T profiles/config4_wct_sharded.py 2>&1 | grep -v Warn | tail -2
