@@ -895,6 +895,10 @@ template <typename T, int TAPS, int EPI = EPI_STORE> struct ExpandBody {
 // x 4 L / (min(R, 32) / 8) coarse positions = 32 L outputs.  Tap counts 10 and 14 are padded to 12 / 16
 // with zero weights.  Not part of the host-emulation build (warp-collective instruction): the
 // emulated tests run the scalar ExpandBody, which stays the fp32 engine's kernel and the fallback.
+// (An fp32 counterpart on 3xTF32 -- x = x_hi + x_lo, three mma.sync.m16n8k8.tf32 per component and eight
+// taps -- gives the same 5e-7 parity but runs SLOWER than the scalar fp32 kernel, 3.54 vs 2.74 ms on
+// config 5: the legacy HMMA path of sm_100a issues ~15 cycles per MMA and SM here, no faster than FFMA.
+// Measured and dropped: profiles/r2/sweep_x_tf32x3_expansion_dropped.txt.)
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
