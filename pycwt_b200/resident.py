@@ -148,7 +148,15 @@ class ResidentTransform(object):
     def icwt(self):
         """Inverse transform of the resident coefficients (wavelet.py:169-170)."""
         red = self.engine.icwt_sum()
-        return self.dj * np.sqrt(self.dt) / (self.wavelet.cdelta * self.wavelet.psi(0)) * red
+        fac = self.dj * np.sqrt(self.dt) / (self.wavelet.cdelta * self.wavelet.psi(0))
+        if not np.iscomplexobj(fac):
+            return fac * red
+        # complex factor (Morlet / Paul: psi(0) is complex in the reference, so is its icwt): one pass per
+        # component instead of NumPy's promote-then-multiply over N points
+        out = np.empty(red.shape, dtype=np.complex128)
+        np.multiply(red, np.real(fac), out=out.real)
+        np.multiply(red, np.imag(fac), out=out.imag)
+        return out
 
 
 def cwt_resident(signal, dt, dj=1/12, s0=-1, J=-1, wavelet='morlet', freqs=None, engine=None):
