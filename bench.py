@@ -74,57 +74,82 @@ def ncu_traffic(kernel_name):
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons of one GPU during the timed region: NVML in a sampling thread
+    (one query costs ~0.1 ms, so even a 15 ms region yields samples; `nvidia-smi -lms` needs
+    hundreds of ms to start on an 8-GPU box and returned nothing there), nvidia-smi as the
+    fallback.  `index` is the CUDA device index of this rank."""
+
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+               ("sw_power_cap", 0x4))
 
     def __init__(self, index):
         self.index = index
-        self.samples = []
-        self.proc = None
+        self.sm, self.bits = [], 0
+        self.max_mhz = None
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.nvml = None
+        self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may renumber devices: resolve through the PCI bus id
+            bus = subprocess.check_output(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id",
+                                           "--format=csv,noheader"], text=True).strip()
+            self.handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_once(self):
+        n = self.nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        try:
+            self.bits |= int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+        except Exception:
+            try:
+                self.bits |= int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            except Exception:
+                pass
+
+    def _loop(self):
+        while not self.stop_flag.is_set():
+            try:
+                self._sample_once()
+            except Exception:
+                break
+            self.stop_flag.wait(0.002)
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                 "--format=csv,noheader,nounits", "-lms", "20"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._loop, daemon=True)
             self.thread.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.samples.append(line.strip())
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
+        if self.nvml is None:
+            return self._smi_once()
+        self.stop_flag.set()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        if not self.sm:
+            return self._smi_once()
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.max_mhz, "samples": len(self.sm),
+                "reasons": sorted(nm for nm, bit in self.REASONS if self.bits & bit), "how": "nvml, 2 ms period"}
+
+    def _smi_once(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc.wait(timeout=2)
+            f = [x.strip() for x in subprocess.check_output(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                text=True, timeout=20).strip().split(",")]
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            return {"sm_mhz": float(f[0]), "sm_max_mhz": float(f[1]), "samples": 1,
+                    "reasons": sorted(nm for nm, v in zip(names, f[2:6]) if v.lower().startswith("active")),
+                    "how": "one nvidia-smi query right after the timed region"}
         except Exception:
-            pass
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            f = [x.strip() for x in s.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": float(max(mx)) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvidia-smi unavailable"]}
 
 
 class Dist(object):
@@ -587,6 +612,7 @@ def run_config5(args, D, eng, pycwt, _engine, comm=None):
     # warm-up: engine buffers and the communicator's first collective (NCCL connects lazily)
     p0, _ = eng.cwt_batch(X[:64], c["dt"], sj, _engine.MORLET, c["f0"], _engine.F32, want_power=True)
     Dm.gather_rows(p0, 64 * D.world, comm)
+    Dm.gather_rows(np.zeros((nch, S)), nch * D.world, comm)   # and once at the size of the timed gather
     D.barrier()
     t0 = time.perf_counter()
     power, _ = eng.cwt_batch(X, c["dt"], sj, _engine.MORLET, c["f0"], _engine.F32, want_power=True)
