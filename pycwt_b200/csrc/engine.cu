@@ -145,6 +145,11 @@ struct cwtb_ctx {
   rt_stream prio_stream{};       // highest-priority stream: the chain of small launches in front of the
                                  // expansion kernels (band products + coarse transforms) -- its CTAs are
                                  // dispatched before the pending CTAs of the big launches on the other streams
+  rt_stream prio_aux[7]{};       // the coarse transforms of different lengths are independent: they fan out
+                                 // over the priority stream and these (own intermediates Zxs[]), so that the
+                                 // chain in front of the expansion kernels is as long as its longest member,
+                                 // not their sum (CWTB_PRIO_FAN=1..8 streams)
+  int prio_fan = 4;
   int prio_mode = 1;             // CWTB_PRIO: 0 = no priority stream, 1 = coarse chain, 2 = coarse chain and
                                  // the expansion kernels
   rt_stream chain_streams[3]{};  // two-kernel classes rotate over the engine's stream and these (own Z
@@ -199,6 +204,7 @@ struct cwtb_ctx {
   Buf filt;                      // caller-supplied time-smoothing responses [S][N] (cwtb_set_smooth_filter)
   int filt_rows = 0;
   long long filt_n = 0;
+  Buf Zxs[7];                    // intermediates of the coarse transforms on prio_aux[]
   Buf Zx, Cin, Cout, wtab;       // expansion path: its own transform intermediate, coarse spectra /
                                  // samples, interpolation weight tables
   std::map<std::array<long long, 3>, long long> wtab_index;   // (log2R, taps, round(beta*1e6)) -> offset
@@ -248,6 +254,7 @@ struct cwtb_ctx {
   cudaEvent_t e0{}, e1{};
   cudaEvent_t ev_fork{}, ev_join{}, ev_joinc[3]{}, ev_coarse{};
   cudaEvent_t ev_h2d[2]{}, ev_used[2]{};
+  cudaEvent_t ev_xband{}, ev_pj[7]{};
 #endif
 };
 
@@ -1519,6 +1526,11 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
     if ((e = launch<ExpandBandBody<T>>(c, ((1u << maxl) + NT * XPER - 1) / (NT * XPER), nrows, xa))) return e;
     c->ztmp = &c->Zx;
     c->prof_tag = "coarse:";
+#ifndef CWTB_HOST_EMU
+    const int fan = prio ? c->prio_fan : 1;   // groups of one coarse length rotate over this many streams
+    int fan_used = 1, group = 0;
+    if (fan > 1) RT(cudaEventRecord(c->ev_xband, c->prio_stream));
+#endif
     for (size_t ci = 0; ci < job.classes.size() && !e; ++ci) {
       const ClassRun &cl = job.classes[ci];
       if (!cl.expand) continue;
@@ -1529,9 +1541,35 @@ static int run_job(cwtb_ctx *c, const Job &job, const T *dsig, cx<T> *Wout = nul
           rows += job.classes[cj].count;
         const long long off = job.descs[cl.first].ip_coff;
         const unsigned Nc = 1u << cl.log2Nc;
+#ifndef CWTB_HOST_EMU
+        if (fan > 1) {
+          const int slot = group++ % fan;
+          if (slot > 0) {
+            if (slot >= fan_used) {   // first use in this call: behind the band products
+              RT(cudaStreamWaitEvent(c->prio_aux[slot - 1], c->ev_xband, 0));
+              fan_used = slot + 1;
+            }
+            c->cur = c->prio_aux[slot - 1];
+            c->ztmp = &c->Zxs[slot - 1];
+          } else {
+            c->cur = c->prio_stream;
+            c->ztmp = &c->Zx;
+          }
+        }
+#endif
         e = fft_rows<T, +1>(c, (const V *)c->Cin.p + off, 0, Nc, Nc, (V *)c->Cout.p + off, Nc, Nc, rows);
       }
     }
+#ifndef CWTB_HOST_EMU
+    if (fan > 1) {   // join the fan on the priority stream
+      for (int k = 1; k < fan_used; ++k) {
+        RT(cudaEventRecord(c->ev_pj[k - 1], c->prio_aux[k - 1]));
+        RT(cudaStreamWaitEvent(c->prio_stream, c->ev_pj[k - 1], 0));
+      }
+      c->cur = c->prio_stream;
+      c->ztmp = &c->Zx;
+    }
+#endif
     c->prof_tag = "";
 #ifndef CWTB_HOST_EMU
     if (prio && c->prio_mode == 1) {   // expansion kernels: ordinary priority, after the coarse chain
@@ -1794,7 +1832,11 @@ int cwtb_create(int device, cwtb_ctx **out) {
     int lo = 0, hi = 0;   // numerically lower = higher priority
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     cudaStreamCreateWithPriority(&c->prio_stream, cudaStreamNonBlocking, hi);
+    for (auto &st : c->prio_aux) cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, hi);
   }
+  cudaEventCreateWithFlags(&c->ev_xband, cudaEventDisableTiming);
+  for (auto &ev : c->ev_pj) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+  if (const char *g = getenv("CWTB_PRIO_FAN")) c->prio_fan = std::min(8, std::max(1, atoi(g)));
   cudaEventCreateWithFlags(&c->ev_coarse, cudaEventDisableTiming);
   for (auto &ev : c->ev_h2d) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
   for (auto &ev : c->ev_used) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
@@ -1853,7 +1895,7 @@ void cwtb_destroy(cwtb_ctx *c) {
   cudaStreamSynchronize(c->stream);
 #endif
   cwtb_comm_destroy(c);
-  for (Buf *b : {&c->stage_dev[0], &c->stage_dev[1], &c->batch_power, &c->filt, &c->comm_send, &c->comm_recv, &c->Zx, &c->Cin, &c->Cout, &c->wtab, &c->ctr, &c->sig, &c->sig2, &c->spec, &c->Z, &c->Zc[0], &c->Zc[1], &c->Zc[2], &c->Y, &c->B, &c->W, &c->W2, &c->descs, &c->table, &c->scratch,
+  for (Buf *b : {&c->Zxs[0], &c->Zxs[1], &c->Zxs[2], &c->Zxs[3], &c->Zxs[4], &c->Zxs[5], &c->Zxs[6], &c->stage_dev[0], &c->stage_dev[1], &c->batch_power, &c->filt, &c->comm_send, &c->comm_recv, &c->Zx, &c->Cin, &c->Cout, &c->wtab, &c->ctr, &c->sig, &c->sig2, &c->spec, &c->Z, &c->Zc[0], &c->Zc[1], &c->Zc[2], &c->Y, &c->B, &c->W, &c->W2, &c->descs, &c->table, &c->scratch,
                  &c->C, &c->A12, &c->F, &c->aux, &c->rowd, &c->win, &c->mask, &c->hist, &c->noise, &c->wide, &c->blueA, &c->blueX, &c->blueY})
     if (b->p) rt_free(b->p);
   for (auto &kv : c->ntabs) { rt_free(kv.second.hi); rt_free(kv.second.lo); }
@@ -1869,6 +1911,9 @@ void cwtb_destroy(cwtb_ctx *c) {
   for (auto &st : c->copy_streams) cudaStreamDestroy(st);
   cudaStreamDestroy(c->aux_stream);
   cudaStreamDestroy(c->prio_stream);
+  for (auto &st : c->prio_aux) cudaStreamDestroy(st);
+  cudaEventDestroy(c->ev_xband);
+  for (auto &ev : c->ev_pj) cudaEventDestroy(ev);
   cudaEventDestroy(c->ev_coarse);
   for (auto &ev : c->ev_h2d) cudaEventDestroy(ev);
   for (auto &ev : c->ev_used) cudaEventDestroy(ev);
