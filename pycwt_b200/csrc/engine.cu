@@ -694,7 +694,8 @@ static int build_job(cwtb_ctx *c, Job &job, long long n0, double dt, const doubl
       double best = 1e300;
       // smallest expansion factor: 8.  Both kernels also run R = 4 (CWTB_EXPAND_MIN_R=2), but the coarse
       // transform of Np/4 points is a two-kernel one itself: measured no gain (config 2 1.480 -> 1.496 ms,
-      // xwt 1.00 -> 1.18 ms, profiles/r2/sweep_t_r4.txt)
+      // xwt 1.00 -> 1.18 ms; with the coarse transforms fanned out over streams 1.477 -> 1.466 ms, xwt
+      // unchanged, wct +0.7 %: profiles/r2/sweep_t_r4.txt)
       const int min_log2R = c->expand_min_log2R;
       for (int l = lmin; l <= lmin + 2 && job.log2N - l >= min_log2R; ++l) {
         double xi_b = 0;
