@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <set>
 #include <string>
 #include <type_traits>
@@ -495,7 +496,11 @@ static const int kExpandTaps32[] = {6, 8, 10};
 
 // smallest tap count whose alias bound at the bucket of `xi` is <= eps; 0 if none.  *xi_b: bucket.
 static int expand_taps(double xi, double eps, bool f32, int max_taps, double *xi_b) {
-  static std::map<std::pair<int, int>, double> cache;   // (bucket, taps) -> bound
+  // (bucket, taps) -> bound; shared by every context of the process (one per GPU, possibly driven from
+  // different host threads)
+  static std::map<std::pair<int, int>, double> cache;
+  static std::mutex cache_mutex;
+  std::lock_guard<std::mutex> cache_lock(cache_mutex);
   int b = -1;
   for (int i = 0; i < kExpandBuckets; ++i)
     if (xi <= kExpandXi[i] * (1 + 1e-12)) { b = i; break; }
@@ -2969,6 +2974,8 @@ struct NcclApi {
 };
 NcclApi &nccl_api() {
   static NcclApi a;
+  static std::mutex m;   // contexts of several host threads may bind NCCL at the same time
+  std::lock_guard<std::mutex> lock(m);
   if (a.h) return a;
   for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
     a.h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);

@@ -244,3 +244,41 @@ def test_seeded_monte_carlo_device_rng(pycwt):
 def test_generic_smoothing_for_paul_and_dog_gpu(pycwt):
     from test_emu_kernels import check_generic_smoothing
     check_generic_smoothing(pycwt)
+
+
+def test_batch_pipeline_equals_synchronous_chunks(monkeypatch):
+    """cwtb_cwt_batch overlaps the input copy of chunk k+1 with the kernels of chunk k and reads the
+    spectra back once (engine.cu: cwt_batch_pipelined); the spectra must equal the ones of the
+    chunk-after-chunk path (same kernels: differences only from the order of the row-sum atomics)."""
+    from pycwt_b200 import _engine
+    rs = np.random.RandomState(8)
+    X = rs.randn(21, 4096).astype(np.float32)
+    sj = 2.0 * 2 ** (np.arange(24) / 3.0)
+    monkeypatch.setenv("CWTB_BATCH_MB", "4")           # 5 channels per chunk: four full chunks and a short last one
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("CWTB_BATCH_PIPELINE", mode)
+        eng = _engine.Engine(0)
+        try:
+            out[mode], _ = eng.cwt_batch(X, 1.0, sj, _engine.MORLET, 6.0, _engine.F32, want_power=True)
+            out[mode] = np.array(out[mode])
+        finally:
+            eng.close()
+    assert out["1"].shape == (21, 24)
+    assert np.allclose(out["1"], out["0"], rtol=1e-12, atol=0)
+    ref = np.stack([(np.abs(orc.cwt(x.astype(np.float64), 1.0, wavelet=orc.Morlet(6),
+                                    freqs=1 / (orc.Morlet(6).flambda() * sj))[0]) ** 2).mean(axis=1) for x in X[:3]])
+    assert np.allclose(out["1"][:3], ref, rtol=2e-5)
+
+
+def test_wct_scale_sharded_single_process_equals_wct(pycwt):
+    """distributed.wct_scale_sharded without a communicator is the whole ladder: the same arrays as wct()."""
+    from pycwt_b200 import distributed as D
+    rs = np.random.RandomState(9)
+    t = np.arange(5000)
+    y1 = np.sin(2 * np.pi * t / 40.0) + rs.randn(5000)
+    y2 = np.sin(2 * np.pi * t / 40.0 + 1.0) + rs.randn(5000)
+    W, A, coi, freq, _ = pycwt.wct(y1, y2, 1.0, dj=1 / 6, s0=2.0, J=40, sig=False)
+    lo, hi, Ws, As, mean, freqs = D.wct_scale_sharded(y1, y2, 1.0, dj=1 / 6, s0=2.0, J=40)
+    assert (lo, hi) == (0, 41) and np.array_equal(Ws, W) and np.array_equal(As, A)
+    assert np.array_equal(freqs, freq) and np.allclose(mean, W.mean(axis=1), rtol=0, atol=0)
