@@ -61,8 +61,14 @@ class NcclComm(_CommBase):
             engine.comm_init(self.world, self.rank, uid)
 
     def _file_exchange(self, uid):
+        # one file per launch: under torchrun every rank has the launcher as its parent, so its pid
+        # separates two launches that reuse a port within minutes (a stale id of the previous launch
+        # made the second of two back-to-back runs fail); rank 0 removes the file in close()
         tag = "%s_%s" % (os.environ.get("MASTER_PORT", "0"), os.environ.get("TORCHELASTIC_RUN_ID", "run"))
+        if "TORCHELASTIC_RUN_ID" in os.environ:
+            tag += "_%d" % os.getppid()
         path = os.path.join(os.environ.get("CWTB_COMM_DIR", "/tmp"), "cwtb_comm_%s.id" % tag)
+        self._id_path = path
         if self.rank == 0:
             tmp = path + ".tmp%d" % os.getpid()
             with open(tmp, "wb") as f:
@@ -99,6 +105,11 @@ class NcclComm(_CommBase):
     def close(self):
         if self.world > 1:
             self.engine.comm_destroy()
+            if self.rank == 0 and getattr(self, "_id_path", None):
+                try:
+                    os.remove(self._id_path)
+                except OSError:
+                    pass
 
 
 class TorchComm(_CommBase):
