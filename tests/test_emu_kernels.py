@@ -444,3 +444,29 @@ def test_plan_reuse_and_invalidation(emu):
     W7 = emu.cwt(x2[:2999], 1.0, sj, 1, 4.0)             # other wavelet family, same scales
     W7r = orc.cwt(x2[:2999], 1.0, wavelet=orc.Paul(4), freqs=1 / (orc.Paul(4).flambda() * sj[:20]))[0]
     assert W7r.shape[0] == 20 and relerr(W7[:20], W7r) < 1e-10   # (the largest scales are NaN rows for Paul)
+
+
+def test_wide_band_expansion_plans(emu):
+    """Coarse grids below 2x oversampling (band half-width up to 11/32 of Nc, 16-20 taps) are planned
+    for fp64; a response that peaks off-centre in such a band (Paul) keeps the 2x rule (engine.cu:
+    expand_gain).  Either way the coefficients match the oracle."""
+    n = 2 ** 13
+    rs = np.random.RandomState(21)
+    x = rs.randn(n).cumsum() + 50.0          # red spectrum with a large mean: the hard case for the coarse grid
+    # Morlet: band half-width hw = 8.58 / s * n / (2 pi) bins; Nc = n/8 = 1024: xi = hw / Nc
+    for xi_target, expect_log2Nc in ((0.20, 10), (0.30, 10), (0.33, 10), (0.36, None)):
+        s = 8.58 * n / (2 * np.pi) / (xi_target * 1024)
+        sj = np.array([s, 1.01 * s])
+        W = emu.cwt(x, 1.0, sj, 0, 6.0)
+        plan = emu.last_plan(2)
+        # beyond 11/32 the next coarse grid would be n/4 (expansion by four is off): pruned transform
+        assert (plan[0] == -expect_log2Nc) if expect_log2Nc else (plan[0] > 0), (xi_target, plan)
+        Wr = orc.cwt(x, 1.0, wavelet=orc.Morlet(6), freqs=1 / (orc.Morlet(6).flambda() * sj))[0]
+        assert relerr(W, Wr) < 1e-12, (xi_target, relerr(W, Wr))
+    # Paul(4): one-sided band [0, f_c / s], response peak at f = 4 of f_c ~ 51: far from the band centre
+    m = orc.Paul(4)
+    for s in (60.0, 80.0, 100.0, 140.0):
+        sj = np.array([s])
+        W = emu.cwt(x, 1.0, sj, 1, 4.0)
+        Wr = orc.cwt(x, 1.0, wavelet=m, freqs=1 / (m.flambda() * sj))[0]
+        assert relerr(W, Wr) < 1e-12, (s, emu.last_plan(1), relerr(W, Wr))
