@@ -235,6 +235,8 @@ struct cwtb_ctx {
   size_t stage_bytes = 0;
   Buf stage_dev[2], batch_power;
   int batch_pipeline = 1;        // CWTB_BATCH_PIPELINE=0: one synchronous chunk after the other
+  double *angle_host = nullptr;  // cwtb_wct: host destination of the phase angle, copied on a copy stream
+                                 // as soon as it exists (before the smoothing transforms), not after them
   const void *job_dsig = nullptr;  // device signal of the last cwt_dev call (not owned)
   double last_ms = 0;
   int launches = 0;
@@ -255,7 +257,7 @@ struct cwtb_ctx {
   cudaEvent_t e0{}, e1{};
   cudaEvent_t ev_fork{}, ev_join{}, ev_joinc[3]{}, ev_coarse{};
   cudaEvent_t ev_h2d[2]{}, ev_used[2]{};
-  cudaEvent_t ev_xband{}, ev_pj[7]{};
+  cudaEvent_t ev_xband{}, ev_pj[7]{}, ev_angle{};
 #endif
 };
 
@@ -704,8 +706,10 @@ static int build_job(cwtb_ctx *c, Job &job, long long n0, double dt, const doubl
       const int min_log2R = c->expand_min_log2R;
       for (int l = lmin; l <= lmin + 2 && job.log2N - l >= min_log2R; ++l) {
         double xi_b = 0;
-        const int w = expand_taps((double)hw / (double)(1ll << l), xeps, precision != CWTB_F64, max_taps, &xi_b);
+        int w = expand_taps((double)hw / (double)(1ll << l), xeps, precision != CWTB_F64, max_taps, &xi_b);
         if (!w) continue;
+        if (mma) w = (w + 3) / 4 * 4;   // the tensor-core kernel pads to DMMA steps of four taps anyway: 10 -> 12 and
+                                        // 14 -> 16 cost nothing, lower the alias error and merge two launches
         if (xi_b > 0.25 && expand_gain(fam, s, klo, khi, kc, l, w, M_PI * w * (1.0 - xi_b)) > 64.0) continue;
         // cost model (us at Np = 2^20): the expansion kernel + the coarse transform.  Scalar kernel: its
         // fp64 work; tensor-core kernel: the W store until the DMMA steps of four taps exceed it
@@ -1841,6 +1845,7 @@ int cwtb_create(int device, cwtb_ctx **out) {
     for (auto &st : c->prio_aux) cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, hi);
   }
   cudaEventCreateWithFlags(&c->ev_xband, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&c->ev_angle, cudaEventDisableTiming);
   for (auto &ev : c->ev_pj) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
   if (const char *g = getenv("CWTB_PRIO_FAN")) c->prio_fan = std::min(8, std::max(1, atoi(g)));
   cudaEventCreateWithFlags(&c->ev_coarse, cudaEventDisableTiming);
@@ -1919,6 +1924,7 @@ void cwtb_destroy(cwtb_ctx *c) {
   cudaStreamDestroy(c->prio_stream);
   for (auto &st : c->prio_aux) cudaStreamDestroy(st);
   cudaEventDestroy(c->ev_xband);
+  cudaEventDestroy(c->ev_angle);
   for (auto &ev : c->ev_pj) cudaEventDestroy(ev);
   cudaEventDestroy(c->ev_coarse);
   for (auto &ev : c->ev_h2d) cudaEventDestroy(ev);
@@ -2316,6 +2322,13 @@ static int wct_core(cwtb_ctx *c, const Job &job, const double *dsig1, const doub
                  (double2 *)c->A12.p, daWCT, n0};
   const unsigned gx = (unsigned)((n0 + NT - 1) / NT);
   if ((e = launch<WctPrepBody>(c, gx, S, pa))) return e;
+#ifndef CWTB_HOST_EMU
+  if (c->angle_host && daWCT) {   // the angle is final here: its 8 B per point cross PCIe under the smoothing
+    RT(cudaEventRecord(c->ev_angle, c->stream));
+    RT(cudaStreamWaitEvent(c->copy_streams[0], c->ev_angle, 0));
+    RT(cudaMemcpyAsync(c->angle_host, daWCT, cnt * sizeof(double), cudaMemcpyDeviceToHost, c->copy_streams[0]));
+  }
+#endif
   if ((e = smooth_time(c, (double2 *)c->C.p, S, n0, job.N, d_g))) return e;
   if ((e = smooth_time(c, (double2 *)c->A12.p, S, n0, job.N, d_g))) return e;
   WctFinalArgs fa{(const double2 *)c->C.p, (const double2 *)c->A12.p, (const double *)c->win.p, dWCT,
@@ -2581,14 +2594,23 @@ int cwtb_wct(cwtb_ctx *c, const double *y1, const double *y2, int64_t n0, double
   double *dW = (double *)c->aux.p, *dA = dW + cnt;
   c->launches = 0;
   if ((e = time_begin(c))) return e;
-  if ((e = wct_core(c, c->job, (const double *)c->sig.p, (const double *)c->sig2.p, boxcar_len, dW,
-                    aWCT_out ? dA : nullptr, nullptr, 0, 0, nullptr)))
-    return e;
+  bool early_angle = false;
+#ifndef CWTB_HOST_EMU
+  c->angle_host = aWCT_out;
+  early_angle = aWCT_out != nullptr;
+#endif
+  e = wct_core(c, c->job, (const double *)c->sig.p, (const double *)c->sig2.p, boxcar_len, dW,
+               aWCT_out ? dA : nullptr, nullptr, 0, 0, nullptr);
+  c->angle_host = nullptr;
+  if (e) return e;
   if ((e = time_end(c))) return e;
   c->job_dsig = nullptr;
   if (WCT_out) RT(rt_d2h(WCT_out, dW, cnt * sizeof(double), c->stream));
-  if (aWCT_out) RT(rt_d2h(aWCT_out, dA, cnt * sizeof(double), c->stream));
+  if (aWCT_out && !early_angle) RT(rt_d2h(aWCT_out, dA, cnt * sizeof(double), c->stream));
   RT(rt_sync(c->stream));
+#ifndef CWTB_HOST_EMU
+  if (early_angle) RT(rt_sync(c->copy_streams[0]));
+#endif
   return 0;
 }
 
