@@ -153,7 +153,7 @@ class ResidentTransform(object):
             return fac * red
         # complex factor (Morlet / Paul: psi(0) is complex in the reference, so is its icwt): one pass per
         # component instead of NumPy's promote-then-multiply over N points
-        out = np.empty(red.shape, dtype=np.complex128)
+        out = self.engine.result_array(red.shape, np.complex128)   # pooled: no first-touch page faults per call
         np.multiply(red, np.real(fac), out=out.real)
         np.multiply(red, np.imag(fac), out=out.imag)
         return out
