@@ -216,7 +216,12 @@ int cwtb_mc_surrogates(cwtb_ctx *ctx, uint64_t seed, int64_t first_pair, int n_p
 /* X: host [n_chan, n0] (float or double).  The per-channel transforms stay on
  * the device; `power_out` (may be NULL) receives the per-channel global wavelet
  * spectra [n_chan, n_scales] (doubles); `W_out` (may be NULL) receives all
- * coefficients [n_chan, n_scales, n0] in the engine precision. */
+ * coefficients [n_chan, n_scales, n0] in the engine precision.  The channels are
+ * processed in chunks (CWTB_BATCH_MB of coefficients each).  With `power_out` only,
+ * the chunks are pipelined: the input copy of chunk k+1 (straight from the caller's
+ * array, pageable memory is fine) overlaps the kernels of chunk k, the spectra are
+ * accumulated on the device and copied back once; the call returns when
+ * `power_out` is complete. */
 int cwtb_cwt_batch(cwtb_ctx *ctx, const void *X, int x_is_f32, int n_chan,
                    int64_t n0, double dt, const double *scales, int n_scales,
                    int family, double param, int precision, double *power_out,
